@@ -1,0 +1,120 @@
+/*
+ * vo_b200.h -- C ABI of the B200-native visual-odometry front end (libvo_b200.so).
+ *
+ * Drop-in boundary for the data-parallel hot path of saegsali/visual-odometry-project.
+ * Every entry point names the reference interface it replaces (file:line under
+ * /root/reference).  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *  - `*_dev` functions take DEVICE pointers and a cudaStream_t (passed as void*; NULL = the
+ *    context's own stream) and are asynchronous.  `*_host` functions take HOST pointers, stage
+ *    through pinned memory, run on the context's stream and return after the result is on the
+ *    host.
+ *  - All functions return 0 on success, non-zero on failure; vo_last_error() describes it.
+ *  - Images are uint8, row-major, `pitch` bytes between rows, `frame_stride` bytes between the
+ *    frames of a batch.  Points are (x, y) = (column, row), as in the reference's (N, 2, 1) arrays.
+ *  - There is no CPU fallback: without a CUDA device vo_ctx_create fails.
+ */
+#ifndef VO_B200_H
+#define VO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vo_ctx vo_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int vo_ctx_create(vo_ctx** out, int device);
+void vo_ctx_destroy(vo_ctx* ctx);
+const char* vo_last_error(void);
+int vo_abi_version(void);
+/* number of kernels launched through this context so far (bench.py's gpu_launches) */
+unsigned long long vo_ctx_launch_count(const vo_ctx* ctx);
+int vo_ctx_synchronize(vo_ctx* ctx);
+/* the context's stream as a cudaStream_t (for event timing on the launching stream) */
+void* vo_ctx_stream(vo_ctx* ctx);
+
+/* ---- Harris: src/vo/features/harris.py ---------------------------------------------------- */
+/* harris.py:102-137  float64 score map [n_frames][H][W], zero border of patch_size/2+1 pixels.  */
+int vo_harris_response_dev(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
+                           size_t frame_stride, int patch_size, double kappa, double* d_resp, void* stream);
+/* harris.py:139-152  greedy non-maximum suppression -> int32 [n_frames][num_keypoints][2] = (x, y),
+ * in the reference's selection order.  d_stats (optional, may be NULL): uint32 [n_frames][4] =
+ * {local maxima, alive after round 0, rounds, picks}.                                           */
+int vo_harris_nms_dev(vo_ctx* ctx, const double* d_resp, int n_frames, int H, int W, int nms_radius,
+                      int num_keypoints, int32_t* d_kp_xy, uint32_t* d_stats, void* stream);
+/* harris.py:86-158  HarrisCornerDetector.extractKeypoints = response + NMS.                     */
+int vo_harris_detect_dev(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
+                         size_t frame_stride, int patch_size, double kappa, int nms_radius, int num_keypoints,
+                         double* d_resp, int32_t* d_kp_xy, void* stream);
+/* harris.py:160-194  extractDescriptors: uint8 [n_frames][K][(2r+1)^2] patches, zero padded.    */
+int vo_harris_descriptors_dev(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
+                              size_t frame_stride, const int32_t* d_kp_xy, int K, int desc_radius,
+                              uint8_t* d_desc, void* stream);
+/* Host-buffer variant of extractKeypoints (+ optional response / descriptors).  h_resp and h_desc
+ * may be NULL.  h_img is tightly packed (pitch == W).                                           */
+int vo_harris_detect_host(vo_ctx* ctx, const uint8_t* h_img, int n_frames, int H, int W, int patch_size,
+                          double kappa, int nms_radius, int num_keypoints, int desc_radius, double* h_resp,
+                          int32_t* h_kp_xy, uint8_t* h_desc);
+
+/* ---- KLT: src/vo/features/klt.py:233-239 (cv2.calcOpticalFlowPyrLK) ------------------------- */
+/* Gaussian 5x5 pyramid (cv2.pyrDown, BORDER_REFLECT_101) of a batch of frames.  Level l of frame f
+ * lives at d_pyr + level_offset[l] + f * level_size[l]; offsets come from vo_klt_pyramid_layout. */
+int vo_klt_pyramid_layout(int H, int W, int max_level, int win, int* n_levels, int* level_h, int* level_w,
+                          size_t* level_pitch, size_t* level_frame_bytes, size_t* total_bytes_per_frame);
+int vo_klt_build_pyramid_dev(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
+                             size_t frame_stride, int max_level, int win, uint8_t* d_pyr, void* stream);
+/* Pyramidal Lucas-Kanade, one warp per point.  Points float32 [n_frames][n_pts][2]; outputs
+ * next points, status (uint8) and the L1 patch error (float32), as cv2 returns them.             */
+int vo_klt_track_dev(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d_pyr_next, int n_frames, int H,
+                     int W, int max_level, int win, int max_iters, double epsilon, double min_eig_threshold,
+                     const float* d_prev_pts, int n_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
+                     void* stream);
+int vo_klt_track_host(vo_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next, int n_frames, int H, int W,
+                      int max_level, int win, int max_iters, double epsilon, double min_eig_threshold,
+                      const float* h_prev_pts, int n_pts, float* h_next_pts, uint8_t* h_status, float* h_err);
+
+/* ---- P3P + RANSAC: src/vo/pose_estimation/p3p.py:51-108, src/vo/algorithms/ransac.py:69-129 --- */
+/* For every hypothesis h (4 sample indices: 3 for P3P, the 4th disambiguates, as cv2.solvePnP with
+ * SOLVEPNP_P3P does) solve the pose, count reprojection inliers (squared pixel error < threshold,
+ * p3p.py:104-108 / ransac.py:104-106), and return per-hypothesis models, validity and counts.
+ * landmarks float64 [n_frames][N][3], keypoints float64 [n_frames][N][2], K float64 [9] row-major,
+ * sample_idx int32 [n_frames][n_hyp][4].  models float64 [n_frames][n_hyp][12] = R (row-major) | t. */
+int vo_p3p_ransac_score_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
+                            int N, const double* K9, const int32_t* d_sample_idx, int n_hyp, double threshold,
+                            double* d_models, uint8_t* d_valid, int32_t* d_counts, void* stream);
+/* ransac.py:90-121 sequential scan with the adaptive iteration count; iters_for_count is the
+ * host-computed table n_iterations(best_n_inliers), best_n_inliers = 0..N (ransac.py:58-67,115-120).
+ * Outputs per frame: best hypothesis index (-1 if none), number of hypotheses consumed (valid and
+ * invalid), n_iterations at exit, inlier mask uint8 [N], model [12].                              */
+int vo_p3p_ransac_select_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
+                             int N, const double* K9, const double* d_models, const uint8_t* d_valid,
+                             const int32_t* d_counts, int n_hyp, double threshold, const int32_t* d_iters_for_count,
+                             int initial_iters, int32_t* d_best, int32_t* d_consumed, int32_t* d_iters_out,
+                             uint8_t* d_inliers, double* d_best_model, void* stream);
+int vo_p3p_ransac_host(vo_ctx* ctx, const double* h_landmarks, const double* h_keypoints, int n_frames, int N,
+                       const double* K9, const int32_t* h_sample_idx, int n_hyp, double threshold,
+                       const int32_t* h_iters_for_count, int initial_iters, int32_t* h_best, int32_t* h_consumed,
+                       int32_t* h_iters_out, uint8_t* h_inliers, double* h_best_model, int32_t* h_counts,
+                       uint8_t* h_valid, double* h_models);
+
+/* ---- Triangulation: src/vo/landmarks/triangulation.py:352-389, 38-86 -------------------------- */
+/* Linear (DLT) triangulation, one point per thread, one-sided Jacobi SVD in registers.
+ * p1, p2 float64 [n][2]; proj1 float64 [n or 1][12] (row-major 3x4; per-point when
+ * proj1_per_point != 0, as triangulate_candidates uses); proj2 float64 [12].
+ * mode 0: 6x4 system [p1]x C1 ; [p2]x C2   (triangulation.py:379-387, use_opencv=False)
+ * mode 1: 4x4 system x*P3-P1, y*P3-P2      (cv2.triangulatePoints, triangulation.py:59-74)
+ * out float64 [n][3] (cartesian).                                                              */
+int vo_triangulate_dev(vo_ctx* ctx, const double* d_p1, const double* d_p2, int n, const double* d_proj1,
+                       int proj1_per_point, const double* d_proj2, int mode, double* d_out, void* stream);
+int vo_triangulate_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int n, const double* h_proj1,
+                        int proj1_per_point, const double* h_proj2, int mode, double* h_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VO_B200_H */

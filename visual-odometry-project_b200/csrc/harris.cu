@@ -1,0 +1,547 @@
+// Harris corner detector for sm_100a: fused Sobel -> structure tensor -> box sums -> response,
+// followed by an exact parallel evaluation of the reference's greedy non-maximum suppression.
+//
+// Replaces  /root/reference/src/vo/features/harris.py:86-158 (HarrisCornerDetector.extractKeypoints)
+//           /root/reference/src/vo/features/harris.py:160-194 (extractDescriptors)
+//
+// Exactness: gradients, products and box sums are exact int32; the response is evaluated in
+// float64 with individually rounded operations (__dmul_rn/__dadd_rn/__dsub_rn, no FMA
+// contraction) in the same order as the numpy expression harris.py:123-126, so the response map
+// is bit-identical to the reference's float64 `harris_scores`.
+//
+// NMS: the reference repeats {argmax; zero a (2r+1)^2 box} K times (harris.py:148-152).  That
+// sequence equals the first K elements, in priority order (score desc, linear index asc), of the
+// greedy maximal independent set of the "within Chebyshev distance r" graph.  It is computed here
+// by (1) a dense local-maximum pass, (2) a per-frame threshold = K-th best local maximum (nothing
+// below it can be among the first K picks), (3) iterated local-maximum rounds over the still-alive
+// pixels above the threshold, (4) a final select + sort of the K best picks.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// Response kernel v1: 64x32 output tile per CTA, three shared-memory stages.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int RT_W = 64;   // output tile width
+constexpr int RT_H = 32;   // output tile height
+constexpr int R_THREADS = 256;
+constexpr int PR_MAX = 7;  // patch_size <= 15
+
+__device__ __forceinline__ double harris_score(int a, int b, int c, double kappa) {
+    // harris.py:123-127, one rounding per numpy ufunc call.
+    const double sa = (double)a, sb = (double)b, sc = (double)c;
+    const double trace = __dadd_rn(sa, sb);
+    const double det = __dsub_rn(__dmul_rn(sa, sb), __dmul_rn(sc, sc));
+    const double s = __dsub_rn(det, __dmul_rn(kappa, __dmul_rn(trace, trace)));
+    return s < 0.0 ? 0.0 : s;
+}
+
+__global__ void __launch_bounds__(R_THREADS)
+harris_response_tiled(const uint8_t* __restrict__ img, size_t pitch, size_t frame_stride,
+                      int H, int W, int pr, double kappa, double* __restrict__ resp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int pad = pr + 1;
+    const int in_w = RT_W + 2 * pad, in_h = RT_H + 2 * pad;
+    const int pw = RT_W + 2 * pr, ph = RT_H + 2 * pr;  // product region
+    int* pxx = reinterpret_cast<int*>(smem_raw);
+    int* pyy = pxx + ph * pw;
+    int* pxy = pyy + ph * pw;
+    int* hxx = pxy + ph * pw;                          // [ph][RT_W]
+    int* hyy = hxx + ph * RT_W;
+    int* hxy = hyy + ph * RT_W;
+    uint8_t* tile = reinterpret_cast<uint8_t*>(hxy + ph * RT_W);  // [in_h][in_w]
+
+    const int x0 = blockIdx.x * RT_W, y0 = blockIdx.y * RT_H;
+    const uint8_t* src = img + (size_t)blockIdx.z * frame_stride;
+    double* dst = resp + (size_t)blockIdx.z * H * W;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < in_h * in_w; i += R_THREADS) {
+        const int ty = i / in_w, tx = i - ty * in_w;
+        const int gy = y0 - pad + ty, gx = x0 - pad + tx;
+        uint8_t v = 0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = src[(size_t)gy * pitch + gx];
+        tile[i] = v;
+    }
+    __syncthreads();
+    // stage 1: Sobel + products at product-region position (py, px) <-> tile (py+1, px+1)
+    for (int i = tid; i < ph * pw; i += R_THREADS) {
+        const int py = i / pw, px = i - py * pw;
+        const uint8_t* t0 = tile + py * in_w + px;
+        const uint8_t* t1 = t0 + in_w;
+        const uint8_t* t2 = t1 + in_w;
+        const int gx = ((int)t0[0] + 2 * (int)t1[0] + (int)t2[0]) - ((int)t0[2] + 2 * (int)t1[2] + (int)t2[2]);
+        const int gy = ((int)t0[0] + 2 * (int)t0[1] + (int)t0[2]) - ((int)t2[0] + 2 * (int)t2[1] + (int)t2[2]);
+        pxx[i] = gx * gx;
+        pyy[i] = gy * gy;
+        pxy[i] = gx * gy;
+    }
+    __syncthreads();
+    // stage 2: horizontal sliding sums, one (row, 8-column segment) per item
+    const int ps = 2 * pr + 1;
+    for (int i = tid; i < ph * (RT_W / 8); i += R_THREADS) {
+        const int row = i / (RT_W / 8), seg = i - row * (RT_W / 8);
+        const int* rxx = pxx + row * pw + seg * 8;
+        const int* ryy = pyy + row * pw + seg * 8;
+        const int* rxy = pxy + row * pw + seg * 8;
+        int sxx = 0, syy = 0, sxy = 0;
+        for (int k = 0; k < ps; k++) { sxx += rxx[k]; syy += ryy[k]; sxy += rxy[k]; }
+        const int o = row * RT_W + seg * 8;
+        hxx[o] = sxx; hyy[o] = syy; hxy[o] = sxy;
+#pragma unroll
+        for (int k = 1; k < 8; k++) {
+            sxx += rxx[k + ps - 1] - rxx[k - 1];
+            syy += ryy[k + ps - 1] - ryy[k - 1];
+            sxy += rxy[k + ps - 1] - rxy[k - 1];
+            hxx[o + k] = sxx; hyy[o + k] = syy; hxy[o + k] = sxy;
+        }
+    }
+    __syncthreads();
+    // stage 3: vertical sliding sums + response; thread = (column, 8-row segment)
+    {
+        const int col = tid % RT_W, rseg = tid / RT_W;  // 64 x 4
+        int sxx = 0, syy = 0, sxy = 0;
+        const int r0 = rseg * 8;
+        for (int k = 0; k < ps; k++) {
+            sxx += hxx[(r0 + k) * RT_W + col];
+            syy += hyy[(r0 + k) * RT_W + col];
+            sxy += hxy[(r0 + k) * RT_W + col];
+        }
+        const int gx = x0 + col;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int gy = y0 + r0 + k;
+            if (k > 0) {
+                sxx += hxx[(r0 + k + ps - 1) * RT_W + col] - hxx[(r0 + k - 1) * RT_W + col];
+                syy += hyy[(r0 + k + ps - 1) * RT_W + col] - hyy[(r0 + k - 1) * RT_W + col];
+                sxy += hxy[(r0 + k + ps - 1) * RT_W + col] - hxy[(r0 + k - 1) * RT_W + col];
+            }
+            if (gx < W && gy < H) {
+                double s = 0.0;
+                if (gx >= pad && gx < W - pad && gy >= pad && gy < H - pad) s = harris_score(sxx, syy, sxy, kappa);
+                dst[(size_t)gy * W + gx] = s;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NMS step 1: dense local-maximum detection (window radius r, raster-order tie break).
+// ---------------------------------------------------------------------------------------------
+constexpr int LT_W = 64, LT_H = 16, L_THREADS = 256;
+
+__global__ void __launch_bounds__(L_THREADS)
+harris_localmax(const double* __restrict__ resp, int H, int W, int r, unsigned int lm_cap,
+                unsigned long long* __restrict__ lm_key, unsigned int* __restrict__ lm_idx,
+                unsigned int* __restrict__ lm_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* tile = reinterpret_cast<double*>(smem_raw);
+    const int tw = LT_W + 2 * r, th = LT_H + 2 * r;
+    const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;
+    const int f = blockIdx.z;
+    const double* src = resp + (size_t)f * H * W;
+    for (int i = threadIdx.x; i < tw * th; i += L_THREADS) {
+        const int ty = i / tw, tx = i - ty * tw;
+        const int gy = y0 - r + ty, gx = x0 - r + tx;
+        double v = 0.0;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = src[(size_t)gy * W + gx];
+        tile[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < LT_W * LT_H; i += L_THREADS) {
+        const int ly = i / LT_W, lx = i - ly * LT_W;
+        const int gy = y0 + ly, gx = x0 + lx;
+        if (gy >= H || gx >= W) continue;
+        const double* c = tile + (ly + r) * tw + (lx + r);
+        const double s = *c;
+        if (!(s > 0.0)) continue;
+        // cheap reject on the 8-neighbourhood
+        bool ok = true;
+        if (r >= 1)
+            ok = s > c[-tw - 1] && s > c[-tw] && s > c[-tw + 1] && s > c[-1] &&
+                 s >= c[1] && s >= c[tw - 1] && s >= c[tw] && s >= c[tw + 1];
+        if (!ok) continue;
+        for (int dy = -r; dy <= r && ok; dy++) {
+            const double* row = c + dy * tw;
+            for (int dx = -r; dx <= r; dx++) {
+                const double q = row[dx];
+                const bool before = (dy < 0) || (dy == 0 && dx < 0);
+                if (before ? (q >= s) : (q > s)) { ok = false; break; }
+            }
+        }
+        if (ok) {
+            const unsigned int slot = atomicAdd(&lm_count[f], 1u);
+            if (slot < lm_cap) {
+                lm_key[(size_t)f * lm_cap + slot] = (unsigned long long)__double_as_longlong(s);
+                lm_idx[(size_t)f * lm_cap + slot] = (unsigned int)(gy * W + gx);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// NMS steps 2-4: one CTA per frame.
+// ---------------------------------------------------------------------------------------------
+constexpr int N_THREADS = 1024;
+
+// priority: key descending, index ascending.
+__device__ __forceinline__ bool prio_ge(unsigned long long k, unsigned int i, unsigned long long tk, unsigned int ti) {
+    return k > tk || (k == tk && i <= ti);
+}
+__device__ __forceinline__ bool prio_gt(unsigned long long k, unsigned int i, unsigned long long tk, unsigned int ti) {
+    return k > tk || (k == tk && i < ti);
+}
+
+// byte `b` (0 = most significant) of the 96-bit composite (key, ~idx): larger composite = higher priority
+__device__ __forceinline__ unsigned int comp_byte(unsigned long long k, unsigned int i, int b) {
+    if (b < 8) return (unsigned int)(k >> (56 - 8 * b)) & 0xFFu;
+    return ((~i) >> (24 - 8 * (b - 8))) & 0xFFu;
+}
+
+// Block-wide radix select of the kth (1-based) highest-priority entry among n entries.
+// Returns the threshold entry (tk, ti) to all threads.  Requires 1 <= kth <= n.
+__device__ void block_select_kth(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ idxs,
+                                 unsigned int n, unsigned int kth, unsigned int* hist /*smem[256]*/,
+                                 unsigned int* s_misc /*smem[4]*/, unsigned long long* tk_out, unsigned int* ti_out) {
+    unsigned long long pk = 0;  // chosen prefix of key
+    unsigned int pi = 0;        // chosen prefix of ~idx
+    unsigned int remaining = kth;
+    for (int b = 0; b < 12; b++) {
+        for (int j = threadIdx.x; j < 256; j += blockDim.x) hist[j] = 0;
+        __syncthreads();
+        for (unsigned int j = threadIdx.x; j < n; j += blockDim.x) {
+            const unsigned long long k = keys[j];
+            const unsigned int ni = ~idxs[j];
+            bool match;
+            if (b == 0) match = true;
+            else if (b < 8) match = (k >> (64 - 8 * b)) == (pk >> (64 - 8 * b));
+            else if (b == 8) match = (k == pk);
+            else match = (k == pk) && ((ni >> (32 - 8 * (b - 8))) == (pi >> (32 - 8 * (b - 8))));
+            if (match) atomicAdd(&hist[comp_byte(k, ~ni, b)], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int acc = 0;
+            int d = 255;
+            for (; d > 0; d--) {
+                if (acc + hist[d] >= remaining) break;
+                acc += hist[d];
+            }
+            s_misc[0] = (unsigned int)d;
+            s_misc[1] = remaining - acc;
+        }
+        __syncthreads();
+        const unsigned int d = s_misc[0];
+        remaining = s_misc[1];
+        if (b < 8) pk |= (unsigned long long)d << (56 - 8 * b);
+        else pi |= d << (24 - 8 * (b - 8));
+        __syncthreads();
+    }
+    *tk_out = pk;
+    *ti_out = ~pi;
+}
+
+struct NmsArgs {
+    const double* resp;            // [F][H][W]
+    int H, W, r, K;
+    unsigned int lm_cap;
+    const unsigned long long* lm_key;  // [F][lm_cap]
+    const unsigned int* lm_idx;
+    const unsigned int* lm_count;      // [F]
+    unsigned char* state;              // [F][H*W]  0 alive/unknown, 1 suppressed, 2 picked
+    unsigned int* alive_a;             // [F][H*W]
+    unsigned int* alive_b;             // [F][H*W]
+    unsigned long long* pick_key;      // [F][lm_cap]
+    unsigned int* pick_idx;            // [F][lm_cap]
+    unsigned int* new_idx;             // [F][lm_cap]
+    int* kp_xy;                        // [F][K][2]
+    unsigned int* stats;               // [F][4]: n_lm, n_alive0, n_rounds, n_picks
+};
+
+__device__ __forceinline__ void mark_window(unsigned char* st, int H, int W, int r, unsigned int p) {
+    const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
+    const int ya = max(py - r, 0), yb = min(py + r, H - 1);
+    const int xa = max(px - r, 0), xb = min(px + r, W - 1);
+    for (int y = ya; y <= yb; y++)
+        for (int x = xa; x <= xb; x++) st[y * W + x] = 1;
+    st[p] = 2;
+}
+
+__global__ void __launch_bounds__(N_THREADS)
+harris_nms_frame(NmsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_misc[4];
+    __shared__ unsigned int s_cnt[4];  // 0: alive count, 1: picks count, 2: new picks, 3: next alive
+    const int f = blockIdx.x;
+    const int H = a.H, W = a.W, r = a.r, K = a.K;
+    const unsigned int npx = (unsigned int)H * W;
+    const double* resp = a.resp + (size_t)f * npx;
+    const unsigned long long* lmk = a.lm_key + (size_t)f * a.lm_cap;
+    const unsigned int* lmi = a.lm_idx + (size_t)f * a.lm_cap;
+    unsigned char* st = a.state + (size_t)f * npx;
+    unsigned int* alive = a.alive_a + (size_t)f * npx;
+    unsigned int* alive_next = a.alive_b + (size_t)f * npx;
+    unsigned long long* pk = a.pick_key + (size_t)f * a.lm_cap;
+    unsigned int* pi = a.pick_idx + (size_t)f * a.lm_cap;
+    unsigned int* newp = a.new_idx + (size_t)f * a.lm_cap;
+    const unsigned int n_lm = min(a.lm_count[f], a.lm_cap);
+    const int tid = threadIdx.x;
+
+    // ---- threshold = K-th best local maximum (or "everything positive" if fewer than K) ----
+    unsigned long long tk = 1ull;
+    unsigned int ti = 0xFFFFFFFFu;
+    if (n_lm >= (unsigned)K && K > 0) block_select_kth(lmk, lmi, n_lm, (unsigned)K, hist, s_misc, &tk, &ti);
+    if (tid < 4) s_cnt[tid] = 0;
+    for (unsigned int p = tid; p < npx; p += N_THREADS) st[p] = 0;
+    __syncthreads();
+    // ---- local maxima above the threshold are picks; suppress their windows ----
+    for (unsigned int j = tid; j < n_lm; j += N_THREADS) {
+        const unsigned long long k = lmk[j];
+        const unsigned int i = lmi[j];
+        if (prio_ge(k, i, tk, ti)) {
+            const unsigned int s = atomicAdd(&s_cnt[1], 1u);
+            pk[s] = k; pi[s] = i;
+            mark_window(st, H, W, r, i);
+        }
+    }
+    __syncthreads();
+    // ---- dense scan: alive = above threshold and not suppressed ----
+    for (unsigned int p = tid; p < npx; p += N_THREADS) {
+        const unsigned long long k = (unsigned long long)__double_as_longlong(resp[p]);
+        if (k != 0ull && prio_ge(k, p, tk, ti) && st[p] == 0) {
+            const unsigned int s = atomicAdd(&s_cnt[0], 1u);
+            alive[s] = p;
+        }
+    }
+    __syncthreads();
+    unsigned int n_alive = s_cnt[0];
+    const unsigned int n_alive0 = n_alive;
+    unsigned int rounds = 0;
+    // ---- rounds: local maxima among the alive pixels become picks ----
+    while (n_alive > 0) {
+        for (unsigned int j = tid; j < n_alive; j += N_THREADS) {
+            const unsigned int p = alive[j];
+            const unsigned long long k = (unsigned long long)__double_as_longlong(resp[p]);
+            const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
+            const int ya = max(py - r, 0), yb = min(py + r, H - 1);
+            const int xa = max(px - r, 0), xb = min(px + r, W - 1);
+            bool is_max = true;
+            for (int y = ya; y <= yb && is_max; y++) {
+                for (int x = xa; x <= xb; x++) {
+                    const unsigned int q = (unsigned int)(y * W + x);
+                    if (q == p || st[q] != 0) continue;
+                    const unsigned long long kq = (unsigned long long)__double_as_longlong(resp[q]);
+                    if (prio_gt(kq, q, k, p)) { is_max = false; break; }
+                }
+            }
+            if (is_max) {
+                const unsigned int s = atomicAdd(&s_cnt[2], 1u);
+                newp[s] = p;
+            }
+        }
+        __syncthreads();
+        const unsigned int n_new = s_cnt[2];
+        for (unsigned int j = tid; j < n_new; j += N_THREADS) {
+            const unsigned int p = newp[j];
+            const unsigned int s = atomicAdd(&s_cnt[1], 1u);
+            pk[s] = (unsigned long long)__double_as_longlong(resp[p]);
+            pi[s] = p;
+            mark_window(st, H, W, r, p);
+        }
+        __syncthreads();
+        for (unsigned int j = tid; j < n_alive; j += N_THREADS) {
+            const unsigned int p = alive[j];
+            if (st[p] == 0) {
+                const unsigned int s = atomicAdd(&s_cnt[3], 1u);
+                alive_next[s] = p;
+            }
+        }
+        __syncthreads();
+        n_alive = s_cnt[3];
+        __syncthreads();
+        if (tid == 0) { s_cnt[2] = 0; s_cnt[3] = 0; }
+        unsigned int* t = alive; alive = alive_next; alive_next = t;
+        rounds++;
+        __syncthreads();
+    }
+    // ---- final: K best picks in priority order ----
+    const unsigned int n_picks = s_cnt[1];
+    if (tid == 0) {
+        a.stats[f * 4 + 0] = n_lm; a.stats[f * 4 + 1] = n_alive0;
+        a.stats[f * 4 + 2] = rounds; a.stats[f * 4 + 3] = n_picks;
+    }
+    unsigned long long fk = 0ull;
+    unsigned int fi = 0xFFFFFFFFu;
+    const unsigned int n_out = min(n_picks, (unsigned)K);
+    if (n_picks > (unsigned)K) block_select_kth(pk, pi, n_picks, (unsigned)K, hist, s_misc, &fk, &fi);
+    // gather into shared memory, padded to a power of two
+    unsigned int P2 = 1;
+    while (P2 < (unsigned)max(K, 1)) P2 <<= 1;
+    unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned int* si = reinterpret_cast<unsigned int*>(sk + P2);
+    for (unsigned int j = tid; j < P2; j += N_THREADS) { sk[j] = 0ull; si[j] = 0xFFFFFFFFu; }
+    if (tid == 0) s_cnt[0] = 0;
+    __syncthreads();
+    for (unsigned int j = tid; j < n_picks; j += N_THREADS) {
+        const unsigned long long k = pk[j];
+        const unsigned int i = pi[j];
+        if (prio_ge(k, i, fk, fi)) {
+            const unsigned int s = atomicAdd(&s_cnt[0], 1u);
+            if (s < P2) { sk[s] = k; si[s] = i; }
+        }
+    }
+    __syncthreads();
+    // bitonic sort, highest priority first
+    for (unsigned int size = 2; size <= P2; size <<= 1) {
+        for (unsigned int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned int j = tid; j < P2; j += N_THREADS) {
+                const unsigned int l = j ^ stride;
+                if (l > j) {
+                    const bool desc = ((j & size) == 0);
+                    const unsigned long long kj = sk[j], kl = sk[l];
+                    const unsigned int ij = si[j], il = si[l];
+                    const bool j_first = prio_gt(kj, ij, kl, il);  // j has higher priority
+                    if (desc ? !j_first : j_first) {
+                        if (!(kj == kl && ij == il)) { sk[j] = kl; sk[l] = kj; si[j] = il; si[l] = ij; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // harris.py:150 with a negative slice start zeroes nothing: the same pixel is returned for
+    // every remaining iteration.  Find the first such pick (if any).
+    if (tid == 0) s_misc[0] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (unsigned int j = tid; j < n_out; j += N_THREADS) {
+        const unsigned int p = si[j];
+        const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
+        if (py < r || px < r) atomicMin(&s_misc[0], j);
+    }
+    __syncthreads();
+    const unsigned int stuck = s_misc[0];
+    int* out = a.kp_xy + (size_t)f * K * 2;
+    for (unsigned int j = tid; j < (unsigned)K; j += N_THREADS) {
+        unsigned int src = j;
+        if (stuck != 0xFFFFFFFFu && j > stuck) src = stuck;
+        int x = 0, y = 0;
+        if (src < n_out) {
+            const unsigned int p = si[src];
+            y = (int)(p / (unsigned)W); x = (int)(p - (unsigned)y * W);
+        }
+        out[2 * j] = x; out[2 * j + 1] = y;
+    }
+}
+
+// harris.py:160-194: raw (2r+1)^2 patches around each keypoint from a zero-padded image.
+__global__ void harris_descriptors_kernel(const uint8_t* __restrict__ img, size_t pitch, size_t frame_stride,
+                                          int H, int W, const int* __restrict__ kp_xy, int K, int r,
+                                          uint8_t* __restrict__ desc) {
+    const int f = blockIdx.y, k = blockIdx.x;
+    const int d = 2 * r + 1;
+    const int cx = kp_xy[((size_t)f * K + k) * 2], cy = kp_xy[((size_t)f * K + k) * 2 + 1];
+    const uint8_t* src = img + (size_t)f * frame_stride;
+    uint8_t* out = desc + ((size_t)f * K + k) * d * d;
+    for (int i = threadIdx.x; i < d * d; i += blockDim.x) {
+        const int dy = i / d - r, dx = i % d - r;
+        const int y = cy + dy, x = cx + dx;
+        uint8_t v = 0;
+        if (y >= 0 && y < H && x >= 0 && x < W) v = src[(size_t)y * pitch + x];
+        out[i] = v;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// Host-side launchers (called from the C ABI in abi.cu)
+// ---------------------------------------------------------------------------------------------
+int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
+                              size_t frame_stride, int patch_size, double kappa, double* d_resp,
+                              cudaStream_t stream) {
+    VO_REQUIRE(patch_size >= 1 && (patch_size & 1) && patch_size / 2 <= PR_MAX,
+               "harris: patch_size must be odd and <= %d (got %d)", 2 * PR_MAX + 1, patch_size);
+    const int pr = patch_size / 2, pad = pr + 1;
+    VO_REQUIRE(H >= 2 * pad + 1 && W >= 2 * pad + 1, "harris: image %dx%d too small for patch_size %d", W, H, patch_size);
+    VO_REQUIRE(n_frames >= 1 && pitch >= (size_t)W, "harris: bad n_frames/pitch");
+    const int pw = RT_W + 2 * pr, ph = RT_H + 2 * pr;
+    const size_t smem = (size_t)3 * ph * pw * 4 + (size_t)3 * ph * RT_W * 4 + (size_t)(RT_W + 2 * pad) * (RT_H + 2 * pad);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VO_CUDA(cudaFuncSetAttribute(harris_response_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+    }
+    dim3 grid(vo_div_up(W, RT_W), vo_div_up(H, RT_H), n_frames);
+    harris_response_tiled<<<grid, R_THREADS, smem, stream>>>(d_img, pitch, frame_stride, H, W, pr, kappa, d_resp);
+    ctx->launches++;
+    VO_CHECK_LAUNCH();
+    return VO_OK;
+}
+
+size_t vo_harris_lm_cap(int H, int W, int r) {
+    return (size_t)vo_div_up(H, r + 1) * (size_t)vo_div_up(W, r + 1);
+}
+
+// scratch layout for NMS (per call, n_frames frames)
+int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H, int W, int radius,
+                         int num_keypoints, int* d_kp_xy, unsigned int* d_stats_or_null, cudaStream_t stream) {
+    VO_REQUIRE(radius >= 0 && radius <= 15, "harris nms: radius must be in [0, 15] (got %d)", radius);
+    VO_REQUIRE(num_keypoints >= 1 && num_keypoints <= 8192, "harris nms: num_keypoints must be in [1, 8192]");
+    VO_REQUIRE(H >= 2 * radius + 1 && W >= 2 * radius + 1, "harris nms: image smaller than the suppression box");
+    const size_t npx = (size_t)H * W;
+    const size_t lm_cap = vo_harris_lm_cap(H, W, radius);
+    const size_t F = n_frames;
+    // carve scratch
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_lmk = carve(F * lm_cap * 8), o_lmi = carve(F * lm_cap * 4), o_cnt = carve(F * 4);
+    const size_t o_state = carve(F * npx), o_aa = carve(F * npx * 4), o_ab = carve(F * npx * 4);
+    const size_t o_pk = carve(F * lm_cap * 8), o_pi = carve(F * lm_cap * 4), o_new = carve(F * lm_cap * 4);
+    const size_t o_stats = carve(F * 16);
+    int rc = vo_buf_reserve(&ctx->scratch[0], off);
+    if (rc) return rc;
+    unsigned char* base = (unsigned char*)ctx->scratch[0].p;
+    VO_CUDA(cudaMemsetAsync(base + o_cnt, 0, F * 4, stream));
+
+    const size_t smem_lm = (size_t)(LT_W + 2 * radius) * (LT_H + 2 * radius) * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VO_CUDA(cudaFuncSetAttribute(harris_localmax, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        VO_CUDA(cudaFuncSetAttribute(harris_nms_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        attr_set = true;
+    }
+    dim3 g1(vo_div_up(W, LT_W), vo_div_up(H, LT_H), n_frames);
+    harris_localmax<<<g1, L_THREADS, smem_lm, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap,
+                                                        (unsigned long long*)(base + o_lmk),
+                                                        (unsigned int*)(base + o_lmi), (unsigned int*)(base + o_cnt));
+    ctx->launches++;
+    VO_CHECK_LAUNCH();
+    NmsArgs a;
+    a.resp = d_resp; a.H = H; a.W = W; a.r = radius; a.K = num_keypoints; a.lm_cap = (unsigned)lm_cap;
+    a.lm_key = (unsigned long long*)(base + o_lmk); a.lm_idx = (unsigned int*)(base + o_lmi);
+    a.lm_count = (unsigned int*)(base + o_cnt);
+    a.state = base + o_state; a.alive_a = (unsigned int*)(base + o_aa); a.alive_b = (unsigned int*)(base + o_ab);
+    a.pick_key = (unsigned long long*)(base + o_pk); a.pick_idx = (unsigned int*)(base + o_pi);
+    a.new_idx = (unsigned int*)(base + o_new);
+    a.kp_xy = d_kp_xy;
+    a.stats = d_stats_or_null ? d_stats_or_null : (unsigned int*)(base + o_stats);
+    unsigned int P2 = 1;
+    while (P2 < (unsigned)num_keypoints) P2 <<= 1;
+    const size_t smem_nms = (size_t)P2 * 12;
+    harris_nms_frame<<<n_frames, N_THREADS, smem_nms, stream>>>(a);
+    ctx->launches++;
+    VO_CHECK_LAUNCH();
+    return VO_OK;
+}
+
+int vo_launch_harris_descriptors(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
+                                 size_t frame_stride, const int* d_kp_xy, int K, int r, uint8_t* d_desc,
+                                 cudaStream_t stream) {
+    VO_REQUIRE(r >= 0 && r <= 32 && K >= 1, "harris descriptors: bad radius / K");
+    dim3 grid(K, n_frames);
+    harris_descriptors_kernel<<<grid, 128, 0, stream>>>(d_img, pitch, frame_stride, H, W, d_kp_xy, K, r, d_desc);
+    ctx->launches++;
+    VO_CHECK_LAUNCH();
+    return VO_OK;
+}

@@ -1,0 +1,123 @@
+"""ctypes binding of libvo_b200.so (include/vo_b200.h).
+
+This is the only way the Python `vo` package reaches the GPU: there is no CPU fallback and no
+import of the test oracle.  If the shared library is missing or no B200 is visible, every
+compute entry point raises.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libvo_b200.so")
+
+_lib = None
+_lock = threading.Lock()
+
+
+class VoNativeError(RuntimeError):
+    pass
+
+
+def _sig(fn, restype, argtypes):
+    fn.restype = restype
+    fn.argtypes = argtypes
+
+
+def lib():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise VoNativeError(
+                f"{LIB_PATH} not found: build it with `python visual-odometry-project_b200/build.py` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, u64, sz, dbl = C.c_void_p, C.c_int, C.c_ulonglong, C.c_size_t, C.c_double
+        _sig(L.vo_abi_version, i32, [])
+        _sig(L.vo_last_error, C.c_char_p, [])
+        _sig(L.vo_ctx_create, i32, [C.POINTER(vp), i32])
+        _sig(L.vo_ctx_destroy, None, [vp])
+        _sig(L.vo_ctx_launch_count, u64, [vp])
+        _sig(L.vo_ctx_synchronize, i32, [vp])
+        _sig(L.vo_ctx_stream, vp, [vp])
+        _sig(L.vo_harris_response_dev, i32, [vp, vp, i32, i32, i32, sz, sz, i32, dbl, vp, vp])
+        _sig(L.vo_harris_nms_dev, i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp])
+        _sig(L.vo_harris_detect_dev, i32, [vp, vp, i32, i32, i32, sz, sz, i32, dbl, i32, i32, vp, vp, vp])
+        _sig(L.vo_harris_descriptors_dev, i32, [vp, vp, i32, i32, i32, sz, sz, vp, i32, i32, vp, vp])
+        _sig(L.vo_harris_detect_host, i32, [vp, vp, i32, i32, i32, i32, dbl, i32, i32, i32, vp, vp, vp])
+        _optional = {
+            "vo_klt_pyramid_layout": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+            "vo_klt_build_pyramid_dev": (i32, [vp, vp, i32, i32, i32, sz, sz, i32, i32, vp, vp]),
+            "vo_klt_track_dev": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, dbl, dbl, vp, i32, vp, vp, vp, vp]),
+            "vo_klt_track_host": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, dbl, dbl, vp, i32, vp, vp, vp]),
+            "vo_p3p_ransac_score_dev": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, dbl, vp, vp, vp, vp]),
+            "vo_p3p_ransac_select_dev": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, dbl, vp, i32,
+                                               vp, vp, vp, vp, vp, vp]),
+            "vo_p3p_ransac_host": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, dbl, vp, i32,
+                                         vp, vp, vp, vp, vp, vp, vp, vp]),
+            "vo_triangulate_dev": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp, vp]),
+            "vo_triangulate_host": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp]),
+        }
+        for name, (rt, at) in _optional.items():
+            if hasattr(L, name):  # all are present in a complete build; tests/test_abi.py checks that
+                _sig(getattr(L, name), rt, at)
+        _lib = L
+        return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().vo_last_error().decode("utf-8", "replace")
+        raise VoNativeError(f"{what} failed (rc={rc}): {msg}")
+
+
+class Context:
+    """Owns a vo_ctx (device scratch + stream) on one GPU."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().vo_ctx_create(C.byref(self._h), int(device)), "vo_ctx_create")
+        self.device = int(device)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def launch_count(self) -> int:
+        return int(lib().vo_ctx_launch_count(self._h))
+
+    def synchronize(self) -> None:
+        check(lib().vo_ctx_synchronize(self._h), "vo_ctx_synchronize")
+
+    def stream(self) -> int:
+        return int(lib().vo_ctx_stream(self._h) or 0)
+
+    def close(self):
+        if self._h:
+            lib().vo_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
