@@ -62,10 +62,13 @@ int vo_harris_detect_host(vo_ctx* ctx, const uint8_t* h_img, int n_frames, int H
                           int32_t* h_kp_xy, uint8_t* h_desc);
 
 /* ---- KLT: src/vo/features/klt.py:233-239 (cv2.calcOpticalFlowPyrLK) ------------------------- */
-/* Gaussian 5x5 pyramid (cv2.pyrDown, BORDER_REFLECT_101) of a batch of frames.  Level l of frame f
- * lives at d_pyr + level_offset[l] + f * level_size[l]; offsets come from vo_klt_pyramid_layout. */
+/* Gaussian 5x5 pyramid (cv2.pyrDown, BORDER_REFLECT_101) of a batch of frames, frame-major: level l
+ * of frame f lives at d_pyr + f * frame_bytes + level_offset[l] with row pitch level_pitch[l]
+ * (arrays of up to 8 entries filled by vo_klt_pyramid_layout; the pyramid stops before a level that
+ * is not larger than the window, as cv2.buildOpticalFlowPyramid does).  If d_img already is the
+ * level-0 slot (d_img == d_pyr, pitch == level_pitch[0], frame_stride == frame_bytes) no copy is made. */
 int vo_klt_pyramid_layout(int H, int W, int max_level, int win, int* n_levels, int* level_h, int* level_w,
-                          size_t* level_pitch, size_t* level_frame_bytes, size_t* total_bytes_per_frame);
+                          size_t* level_pitch, size_t* level_offset, size_t* frame_bytes);
 int vo_klt_build_pyramid_dev(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
                              size_t frame_stride, int max_level, int win, uint8_t* d_pyr, void* stream);
 /* Pyramidal Lucas-Kanade, one warp per point.  Points float32 [n_frames][n_pts][2]; outputs
@@ -82,25 +85,30 @@ int vo_klt_track_host(vo_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next,
 /* For every hypothesis h (4 sample indices: 3 for P3P, the 4th disambiguates, as cv2.solvePnP with
  * SOLVEPNP_P3P does) solve the pose, count reprojection inliers (squared pixel error < threshold,
  * p3p.py:104-108 / ransac.py:104-106), and return per-hypothesis models, validity and counts.
- * landmarks float64 [n_frames][N][3], keypoints float64 [n_frames][N][2], K float64 [9] row-major,
+ * landmarks float64 [n_frames][N][3], keypoints float64 [n_frames][N][2], K9 float64 [9] row-major (HOST pointer),
  * sample_idx int32 [n_frames][n_hyp][4].  models float64 [n_frames][n_hyp][12] = R (row-major) | t. */
 int vo_p3p_ransac_score_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
                             int N, const double* K9, const int32_t* d_sample_idx, int n_hyp, double threshold,
                             double* d_models, uint8_t* d_valid, int32_t* d_counts, void* stream);
-/* ransac.py:90-121 sequential scan with the adaptive iteration count; iters_for_count is the
- * host-computed table n_iterations(best_n_inliers), best_n_inliers = 0..N (ransac.py:58-67,115-120).
- * Outputs per frame: best hypothesis index (-1 if none), number of hypotheses consumed (valid and
- * invalid), n_iterations at exit, inlier mask uint8 [N], model [12].                              */
+/* ransac.py:90-121 sequential scan with the adaptive iteration count.  d_iters_for_count is the
+ * host-computed table n_iterations(best_n_inliers), best_n_inliers = 0..N (ransac.py:58-67,115-120);
+ * initial_iters / start_n / start_best carry the loop state in (ransac.py:56,81,84; start_best = -1
+ * and start_n = 0 for a fresh call).  Outputs per frame: d_best4 int32 [4] = {best hypothesis index
+ * or -1 if none beat start_best, best inlier count, n (iterations counted), exhausted flag: 1 if the
+ * hypotheses ran out before n reached n_iterations}; d_consumed = hypotheses consumed (valid and
+ * invalid, i.e. RNG draws); d_iters_out = n_iterations at exit; inlier mask uint8 [N]; model [12]. */
 int vo_p3p_ransac_select_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
                              int N, const double* K9, const double* d_models, const uint8_t* d_valid,
                              const int32_t* d_counts, int n_hyp, double threshold, const int32_t* d_iters_for_count,
-                             int initial_iters, int32_t* d_best, int32_t* d_consumed, int32_t* d_iters_out,
-                             uint8_t* d_inliers, double* d_best_model, void* stream);
+                             int initial_iters, int start_n, int start_best, int32_t* d_best4, int32_t* d_consumed,
+                             int32_t* d_iters_out, uint8_t* d_inliers, double* d_best_model, void* stream);
+/* Host-buffer variant: score + select.  h_counts / h_valid / h_models may be NULL.  K9 and
+ * h_iters_for_count (int32 [N+1]) are host pointers in every variant.                           */
 int vo_p3p_ransac_host(vo_ctx* ctx, const double* h_landmarks, const double* h_keypoints, int n_frames, int N,
                        const double* K9, const int32_t* h_sample_idx, int n_hyp, double threshold,
-                       const int32_t* h_iters_for_count, int initial_iters, int32_t* h_best, int32_t* h_consumed,
-                       int32_t* h_iters_out, uint8_t* h_inliers, double* h_best_model, int32_t* h_counts,
-                       uint8_t* h_valid, double* h_models);
+                       const int32_t* h_iters_for_count, int initial_iters, int start_n, int start_best,
+                       int32_t* h_best4, int32_t* h_consumed, int32_t* h_iters_out, uint8_t* h_inliers,
+                       double* h_best_model, int32_t* h_counts, uint8_t* h_valid, double* h_models);
 
 /* ---- Triangulation: src/vo/landmarks/triangulation.py:352-389, 38-86 -------------------------- */
 /* Linear (DLT) triangulation, one point per thread, one-sided Jacobi SVD in registers.

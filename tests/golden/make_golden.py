@@ -72,6 +72,140 @@ def make_harris():
     print("harris.npz", {k: v.shape for k, v in out.items()})
 
 
+def make_klt():
+    """klt.py:29-33 parameters; cv2.calcOpticalFlowPyrLK is the reference's own call (klt.py:233-239)."""
+    from vo.features.klt import KLTTracker
+    from vo.primitives import Frame
+
+    out = {}
+    g0, g1 = kitti_gray(0), kitti_gray(1)
+    c0 = np.ascontiguousarray(g0[100:292, 400:720])
+    c1 = np.ascontiguousarray(g1[100:292, 400:720])
+    out["prev"], out["next"] = c0, c1
+    lk = dict(winSize=(17, 17), maxLevel=2, criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 10, 0.03))
+    pts = cv2.goodFeaturesToTrack(c0, maxCorners=500, qualityLevel=0.01, minDistance=8, blockSize=7).reshape(-1, 2)
+    rng = np.random.default_rng(7)
+    H, W = c0.shape
+    edge = np.stack([rng.uniform(-12, W + 12, 120), rng.uniform(-12, H + 12, 120)], 1).astype(np.float32)
+    pts = np.concatenate([pts, edge]).astype(np.float32)
+    nxt, st, err = cv2.calcOpticalFlowPyrLK(c0, c1, pts.reshape(-1, 1, 2), None, **lk)
+    out["pts"], out["next_pts"], out["status"], out["err"] = pts, nxt.reshape(-1, 2), st.ravel(), err.ravel()
+    # a 4-level pyramid / other window, as BASELINE config 4 uses
+    lk2 = dict(winSize=(21, 21), maxLevel=3, criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 30, 0.01))
+    nxt, st, err = cv2.calcOpticalFlowPyrLK(c0, c1, pts.reshape(-1, 1, 2), None, **lk2)
+    out["next_pts_w21_l3"], out["status_w21_l3"], out["err_w21_l3"] = nxt.reshape(-1, 2), st.ravel(), err.ravel()
+    out["pyr1"] = cv2.pyrDown(c0)
+    out["pyr2"] = cv2.pyrDown(out["pyr1"])
+    # the reference class end to end (BGR frames; equal channels convert back to the same gray)
+    f0 = Frame(np.stack([c0] * 3, -1))
+    f1 = Frame(np.stack([c1] * 3, -1))
+    np.random.seed(0)
+    trk = KLTTracker(f0)
+    out["tracker_init_kp"] = f0.features.keypoints.reshape(-1, 2).astype(np.float32)
+    m = trk.track_features(f0, f1)
+    out["tracker_kp1"] = m.frame1.features.keypoints.reshape(-1, 2).astype(np.float32)
+    out["tracker_kp2"] = m.frame2.features.keypoints.reshape(-1, 2).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "klt.npz"), **out)
+    print("klt.npz", {k: v.shape for k, v in out.items()}, "tracked", int(out["status"].sum()))
+
+
+def _cameras():
+    from vo.sensors import Camera
+    K = np.array([[500, 0, 320], [0, 500, 240], [0, 0, 1]], dtype=float)
+    th1, th2 = np.pi / 8, np.pi / 32
+    R = np.array([[np.cos(th1), -np.sin(th1), 0], [np.sin(th1), np.cos(th1), 0], [0, 0, 1]])
+    R = R @ np.array([[np.cos(th2), 0, np.sin(th2)], [0, 1, 0], [-np.sin(th2), 0, np.cos(th2)]])
+    t = np.array([[1, 1, -1]], dtype=float).T
+    return Camera(K, R=np.eye(3), t=np.zeros((3, 1))), Camera(K, R=R, t=t)
+
+
+def make_p3p():
+    """tests/test_p3p.py's configuration through the reference's own P3PPoseEstimator (use_opencv=False)."""
+    from vo.pose_estimation import P3PPoseEstimator
+    from vo.primitives import Features
+
+    out = {}
+    cam1, cam2 = _cameras()
+    out["K"], out["R_true"], out["t_true"] = cam2.intrinsic_matrix, cam2.R, cam2.t
+    rng = np.random.default_rng(2023)
+    for tag, N, noise, outl, thr in [("clean", 1000, 0.0, 0.0, 1.0), ("noisy", 600, 0.4, 0.35, 2.0)]:
+        L = rng.uniform(-1, 1, size=(N, 3, 1))
+        L[:, 2] = L[:, 2] * 5 + 10
+        p2 = cam2.project_points_world_frame(L)
+        p2 = p2 + rng.normal(0, noise, p2.shape) if noise > 0 else p2
+        n_out = int(outl * N)
+        if n_out:
+            idx = rng.choice(N, n_out, replace=False)
+            p2[idx] += rng.uniform(-60, 60, (n_out, 2, 1))
+        out[f"{tag}_landmarks"], out[f"{tag}_keypoints"], out[f"{tag}_threshold"] = L.reshape(N, 3), p2.reshape(N, 2), thr
+        for refine in (False, True):
+            est = P3PPoseEstimator(intrinsic_matrix=cam2.intrinsic_matrix, use_opencv=False, inlier_threshold=thr,
+                                   outlier_ratio=0.9, confidence=0.99, max_iterations=1000,
+                                   nonlinear_refinement=refine)
+            (R, t), inl = est.estimate_pose(Features(keypoints=p2.copy(), landmarks=L.copy()))
+            k = f"{tag}_refine{int(refine)}"
+            out[k + "_R"], out[k + "_t"], out[k + "_inliers"] = R, np.asarray(t).reshape(3, 1), inl
+            out[k + "_n_iterations"] = est.ransac.n_iterations
+            out[k + "_outlier_ratio"] = est.ransac.outlier_ratio
+            # second call on the same estimator: rng / n_iterations / outlier_ratio state carries over
+            (R, t), inl = est.estimate_pose(Features(keypoints=p2.copy(), landmarks=L.copy()))
+            out[k + "_second_R"], out[k + "_second_t"], out[k + "_second_inliers"] = R, np.asarray(t).reshape(3, 1), inl
+        # the solver alone: cv2.solvePnP on the first 96 sample sets of the reference's rng stream
+        r = np.random.default_rng(2023)
+        S, valid, models = [], [], []
+        for _ in range(96):
+            ids = r.choice(np.arange(N), replace=False, size=4)
+            ok, rv, tv = cv2.solvePnP(L[ids], p2[ids], cam2.intrinsic_matrix, None, flags=cv2.SOLVEPNP_P3P)
+            S.append(ids)
+            valid.append(ok)
+            models.append(np.concatenate([cv2.Rodrigues(rv)[0].ravel(), tv.ravel()]) if ok else np.zeros(12))
+        out[f"{tag}_sample_idx"], out[f"{tag}_cv_valid"], out[f"{tag}_cv_models"] = np.array(S, np.int32), np.array(valid), np.array(models)
+    np.savez_compressed(os.path.join(OUT, "p3p.npz"), **out)
+    print("p3p.npz", {k: np.shape(v) for k, v in out.items()})
+
+
+def make_triangulation():
+    """tests/test_triangulation.py's two-camera configuration through LandmarksTriangulator."""
+    from vo.landmarks.triangulation import LandmarksTriangulator
+    from vo.primitives import Features
+
+    out = {}
+    cam1, cam2 = _cameras()
+    rng = np.random.default_rng(2023)
+    N = 400
+    L = rng.uniform(-1, 1, size=(N, 3, 1))
+    L[:, 2] = L[:, 2] * 5 + 10
+    out["landmarks"] = L.reshape(N, 3)
+    out["C1"], out["C2"] = cam1.projection_matrix, cam2.projection_matrix
+    for tag, noise in [("clean", 0.0), ("noisy", 0.5)]:
+        p1 = cam1.project_points_world_frame(L) + rng.normal(0, noise, (N, 2, 1))
+        p2 = cam2.project_points_world_frame(L) + rng.normal(0, noise, (N, 2, 1))
+        out[f"{tag}_p1"], out[f"{tag}_p2"] = p1.reshape(N, 2), p2.reshape(N, 2)
+        tri = LandmarksTriangulator(cam1, cam2, use_ransac=False, use_opencv=False)
+        out[f"{tag}_linear"] = tri._linear_triangulation(p1, p2, cam1.projection_matrix, cam2.projection_matrix).reshape(N, 3)
+        # triangulate_candidates: per-point start poses (triangulation.py:50-57), both code paths
+        poses = np.stack([np.eye(4)] * N)
+        poses[:, :3, 3] = rng.normal(0, 0.05, (N, 3))        # slightly different start pose per track
+        K = cam1.intrinsic_matrix
+        starts = np.stack([to_pixels(K, np.linalg.inv(poses[i])[:3], L[i]) for i in range(N)]) + rng.normal(0, noise, (N, 2, 1))
+        feats = Features(keypoints=p2.copy())
+        feats.tracks = starts
+        feats.poses = poses
+        feats.candidate_mask = np.ones(N, dtype=bool)
+        cur = np.linalg.inv(cam2.c_T_w)
+        out[f"{tag}_cand_tracks"], out[f"{tag}_cand_poses"], out[f"{tag}_cand_current_pose"] = starts.reshape(N, 2), poses, cur
+        for use_cv in (False, True):
+            tri = LandmarksTriangulator(cam1, cam2, use_ransac=False, use_opencv=use_cv)
+            out[f"{tag}_cand_cv{int(use_cv)}"] = tri.triangulate_candidates(feats, cur).reshape(N, 3)
+    np.savez_compressed(os.path.join(OUT, "triangulation.npz"), **out)
+    print("triangulation.npz", {k: np.shape(v) for k, v in out.items()})
+
+
+def to_pixels(K, M, X):
+    x = K @ (M[:, :3] @ X + M[:, 3:])
+    return x[:2] / x[2:]
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["harris", "klt", "p3p", "triangulation"]
     for w in which:

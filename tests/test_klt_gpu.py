@@ -1,0 +1,74 @@
+"""GPU parity: CUDA pyramidal LK (C ABI) vs the oracle (bit-exact: same integer sums, same float32
+op order) and vs cv2.calcOpticalFlowPyrLK golden vectors (status identical, tracks within 1e-2 px)."""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import synthetic_image
+
+pytestmark = pytest.mark.gpu
+
+
+def _track(ctx, a, b, pts, **kw):
+    from vo import _ops
+    return _ops.klt_track(a, b, pts, ctx=ctx, **kw)
+
+
+def test_golden_vs_cv2(ctx, golden):
+    g = golden("klt")
+    for suffix, kw in [("", {}), ("_w21_l3", dict(win=21, max_level=3, max_iters=30, epsilon=0.01))]:
+        nxt, st, err = _track(ctx, g["prev"], g["next"], g["pts"], **kw)
+        st_ref = g["status" + suffix]
+        assert np.array_equal(st, st_ref)
+        ok = st_ref == 1
+        d = np.abs(nxt - g["next_pts" + suffix]).max(axis=1)[ok]
+        assert d.max() < 1e-2                       # BASELINE north_star tolerance: 1e-2 px
+        assert np.median(d) < 1e-4
+        assert np.abs(err - g["err" + suffix])[ok].max() < 5e-2
+
+
+def _shifted_pair(h, w, seed, dx, dy):
+    big = synthetic_image(h + 40, w + 40, seed)
+    a = np.ascontiguousarray(big[20:20 + h, 20:20 + w])
+    b = np.ascontiguousarray(big[20 - dy:20 - dy + h, 20 - dx:20 - dx + w])
+    return a, b
+
+
+@pytest.mark.parametrize("shape,win,lvl,n", [
+    ((97, 131), 17, 2, 200),
+    ((376, 1241), 17, 2, 1000),     # BASELINE configs[1]
+    ((240, 320), 21, 3, 300),
+    ((60, 70), 9, 4, 100),          # pyramid truncated by the window-size rule
+    ((120, 160), 17, 0, 100),       # no pyramid
+])
+def test_vs_oracle_bitexact(ctx, shape, win, lvl, n):
+    a, b = _shifted_pair(shape[0], shape[1], seed=shape[0] + win, dx=3, dy=-2)
+    rng = np.random.default_rng(n)
+    pts = np.stack([rng.uniform(-win, shape[1] + win, n), rng.uniform(-win, shape[0] + win, n)], 1).astype(np.float32)
+    nxt, st, err = _track(ctx, a, b, pts, win=win, max_level=lvl)
+    nxt_o, st_o, err_o = oracle.klt_track(a, b, pts, win=win, max_level=lvl)
+    assert np.array_equal(st, st_o)
+    assert np.array_equal(nxt, nxt_o)               # bit-exact float32
+    assert np.array_equal(err, err_o)
+    good = st_o == 1
+    assert good.sum() > n // 4
+    # property: a pure integer shift is recovered for well-textured interior points
+    inner = good & (pts[:, 0] > 2 * win) & (pts[:, 0] < shape[1] - 2 * win) & \
+        (pts[:, 1] > 2 * win) & (pts[:, 1] < shape[0] - 2 * win) & (err_o < 2)
+    if inner.sum():
+        flow = nxt[inner] - pts[inner]
+        assert np.median(np.abs(flow - np.array([3, -2], np.float32))) < 0.1
+
+
+def test_batch_and_empty(ctx):
+    pairs = [_shifted_pair(100, 140, s, 1, 1) for s in range(3)]
+    a = np.stack([p[0] for p in pairs])
+    b = np.stack([p[1] for p in pairs])
+    rng = np.random.default_rng(0)
+    pts = np.stack([rng.uniform(0, 140, (3, 64)), rng.uniform(0, 100, (3, 64))], -1).astype(np.float32)
+    nxt, st, err = _track(ctx, a, b, pts)
+    for f in range(3):
+        n1, s1, e1 = _track(ctx, a[f], b[f], pts[f])
+        assert np.array_equal(n1, nxt[f]) and np.array_equal(s1, st[f]) and np.array_equal(e1, err[f])
+    n0, s0, e0 = _track(ctx, a[0], b[0], np.zeros((0, 2), np.float32))
+    assert n0.shape == (0, 2) and s0.shape == (0,)

@@ -1,0 +1,113 @@
+"""GPU parity: batched P3P + RANSAC scoring (C ABI) vs the oracle (bit-exact models, counts, masks)
+and vs the reference's own estimator run (tests/golden/p3p.npz)."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _rot_angle(Ra, Rb):
+    return float(np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1)))
+
+
+def _samples(N, n, seed=2023):
+    rng = np.random.default_rng(seed)
+    return np.array([rng.choice(np.arange(N), replace=False, size=4) for _ in range(n)], np.int32)
+
+
+@pytest.mark.parametrize("tag", ["clean", "noisy"])
+def test_score_bitexact_vs_oracle(ctx, golden, tag):
+    from vo import _ops
+    g = golden("p3p")
+    L, P, thr = g[f"{tag}_landmarks"], g[f"{tag}_keypoints"], float(g[f"{tag}_threshold"])
+    N = L.shape[0]
+    S = _samples(N, 1500)
+    table = oracle.ransac_iterations_table(N, 4, 0.99, 1000)
+    init = oracle.ransac_initial_iterations(4, 0.9, 0.99, 1000)
+    r = _ops.p3p_ransac(L, P, g["K"], S, thr, table, init, want_all=True, ctx=ctx)
+    models, valid, counts = oracle.p3p_ransac_score(L, P, g["K"], S, thr)
+    assert np.array_equal(r["valid"], valid)
+    assert np.array_equal(r["counts"], counts)
+    assert np.array_equal(r["models"], models)              # float64 bit-exact
+    best_h, consumed, n_iter, n, best, exhausted = oracle.ransac_scan(valid, counts, table, init)
+    assert (int(r["best"]), int(r["consumed"]), int(r["n_iterations"]), int(r["n"]), int(r["best_count"]),
+            bool(r["exhausted"])) == (best_h, consumed, n_iter, n, best, exhausted)
+    inl = oracle.reproj_errors(models[best_h, :9], models[best_h, 9:], L, P, g["K"]) < thr
+    assert np.array_equal(r["inliers"], inl)                # bit-exact inlier mask
+    # ... and against the reference's own estimator (P3PPoseEstimator, use_opencv=False)
+    assert np.array_equal(r["inliers"], g[f"{tag}_refine0_inliers"])
+    assert _rot_angle(r["R"], g[f"{tag}_refine0_R"]) < 1e-5                       # 1e-5 rad
+    t_ref = g[f"{tag}_refine0_t"]
+    assert np.linalg.norm(r["t"] - t_ref) <= 1e-4 * np.linalg.norm(t_ref)        # 1e-4 relative
+    assert int(r["n_iterations"]) == int(g[f"{tag}_refine0_n_iterations"])
+
+
+def test_solver_vs_cv2_golden(ctx, golden):
+    from vo import _ops
+    g = golden("p3p")
+    for tag in ("clean", "noisy"):
+        L, P, S = g[f"{tag}_landmarks"], g[f"{tag}_keypoints"], g[f"{tag}_sample_idx"]
+        N = L.shape[0]
+        table = np.full(N + 1, 10 ** 6, np.int32)
+        r = _ops.p3p_ransac(L, P, g["K"], S, 1.0, table, 10 ** 6, want_all=True, ctx=ctx)
+        cvm = g[f"{tag}_cv_models"]
+        cv_ok = g[f"{tag}_cv_valid"].astype(bool) & np.isfinite(cvm).all(axis=1)
+        assert np.array_equal(r["valid"].astype(bool), cv_ok)
+        for h in np.where(cv_ok)[0]:
+            assert _rot_angle(r["models"][h, :9].reshape(3, 3), cvm[h, :9].reshape(3, 3)) < 1e-5
+            assert np.linalg.norm(r["models"][h, 9:] - cvm[h, 9:]) <= 1e-4 * np.linalg.norm(cvm[h, 9:])
+
+
+def test_batched_frames_and_continuation(ctx, golden):
+    """Frames are independent; a run split into two batches (state carried) equals one run."""
+    from vo import _ops
+    g = golden("p3p")
+    L, P, thr = g["noisy_landmarks"], g["noisy_keypoints"], float(g["noisy_threshold"])
+    N = L.shape[0]
+    table = oracle.ransac_iterations_table(N, 4, 0.99, 1000)
+    init = oracle.ransac_initial_iterations(4, 0.9, 0.99, 1000)
+    S = _samples(N, 512, seed=5)
+    Lb = np.stack([L, L[::-1].copy()])
+    Pb = np.stack([P, P[::-1].copy()])
+    Sb = np.stack([S, S])
+    rb = _ops.p3p_ransac(Lb, Pb, g["K"], Sb, thr, table, init, want_all=True, ctx=ctx)
+    r0 = _ops.p3p_ransac(L, P, g["K"], S, thr, table, init, want_all=True, ctx=ctx)
+    assert np.array_equal(rb["counts"][0], r0["counts"]) and np.array_equal(rb["inliers"][0], r0["inliers"])
+    # split: the first 8 hypotheses, then the rest with the loop state carried over
+    k = 8
+    a = _ops.p3p_ransac(L, P, g["K"], S[:k], thr, table, init, ctx=ctx)
+    assert bool(a["exhausted"]) and int(a["consumed"]) == k
+    b = _ops.p3p_ransac(L, P, g["K"], S[k:], thr, table, int(a["n_iterations"]), start_n=int(a["n"]),
+                        start_best=int(a["best_count"]), ctx=ctx)
+    total_best = (k + int(b["best"])) if int(b["best"]) >= 0 else int(a["best"])
+    assert total_best == int(r0["best"])
+    assert k + int(b["consumed"]) == int(r0["consumed"])
+
+
+def test_large_sweep_property(ctx):
+    """BASELINE configs[2]-sized sweep: the winner's mask must equal the count, and the count must be
+    the maximum over hypotheses scanned (no adaptive stop)."""
+    from vo import _ops
+    rng = np.random.default_rng(3)
+    N, Hn = 2500, 16384
+    K = np.array([[707.0912, 0, 601.8873], [0, 707.0912, 183.1104], [0, 0, 1.0]])
+    L = rng.uniform(-10, 10, (N, 3))
+    L[:, 2] = rng.uniform(4, 40, N)
+    uv = (K @ L.T).T
+    uv = uv[:, :2] / uv[:, 2:] + rng.normal(0, 0.3, (N, 2))
+    out = rng.choice(N, N // 3, replace=False)
+    uv[out] += rng.uniform(-80, 80, (len(out), 2))
+    S = rng.integers(0, N, (Hn, 4)).astype(np.int32)
+    table = np.full(N + 1, 10 ** 7, np.int32)
+    r = _ops.p3p_ransac(L, uv, K, S, 1.5, table, 10 ** 7, want_all=True, ctx=ctx)
+    assert int(r["consumed"]) == Hn and bool(r["exhausted"])
+    assert int(r["best_count"]) == int(r["counts"][r["valid"].astype(bool)].max())
+    assert int(r["inliers"].sum()) == int(r["best_count"])
+    assert int(r["best"]) == int(np.argmax(np.where(r["valid"].astype(bool), r["counts"], -1)))
+    assert int(r["best_count"]) > N // 2
+    # spot-check 64 hypotheses against the oracle
+    sel = rng.choice(Hn, 64, replace=False)
+    m, v, c = oracle.p3p_ransac_score(L, uv, K, S[sel], 1.5)
+    assert np.array_equal(r["counts"][sel], c) and np.array_equal(r["models"][sel], m)

@@ -160,4 +160,178 @@ int vo_harris_detect_host(vo_ctx* ctx, const uint8_t* h_img, int n_frames, int H
     return VO_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// KLT
+// ------------------------------------------------------------------------------------------
+int vo_klt_pyramid_layout(int H, int W, int max_level, int win, int* n_levels, int* level_h, int* level_w,
+                          size_t* level_pitch, size_t* level_offset, size_t* frame_bytes) {
+    VO_REQUIRE(n_levels && frame_bytes, "vo_klt_pyramid_layout: null argument");
+    return vo_klt_layout_host(H, W, max_level, win, n_levels, level_h, level_w, level_pitch, level_offset, frame_bytes);
+}
+
+int vo_klt_build_pyramid_dev(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
+                             size_t frame_stride, int max_level, int win, uint8_t* d_pyr, void* stream) {
+    VO_REQUIRE(ctx && d_img && d_pyr, "vo_klt_build_pyramid_dev: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_launch_klt_pyramid(ctx, d_img, n_frames, H, W, pitch, frame_stride, max_level, win, d_pyr,
+                                 pick_stream(ctx, stream));
+}
+
+int vo_klt_track_dev(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d_pyr_next, int n_frames, int H,
+                     int W, int max_level, int win, int max_iters, double epsilon, double min_eig_threshold,
+                     const float* d_prev_pts, int n_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
+                     void* stream) {
+    VO_REQUIRE(ctx && d_pyr_prev && d_pyr_next && (n_pts == 0 || (d_prev_pts && d_next_pts && d_status && d_err)),
+               "vo_klt_track_dev: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_launch_klt_track(ctx, d_pyr_prev, d_pyr_next, n_frames, H, W, max_level, win, max_iters, epsilon,
+                               min_eig_threshold, d_prev_pts, n_pts, d_next_pts, d_status, d_err,
+                               pick_stream(ctx, stream));
+}
+
+int vo_klt_track_host(vo_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next, int n_frames, int H, int W,
+                      int max_level, int win, int max_iters, double epsilon, double min_eig_threshold,
+                      const float* h_prev_pts, int n_pts, float* h_next_pts, uint8_t* h_status, float* h_err) {
+    VO_REQUIRE(ctx && h_prev && h_next, "vo_klt_track_host: null argument");
+    VO_REQUIRE(n_pts == 0 || (h_prev_pts && h_next_pts && h_status && h_err), "vo_klt_track_host: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int n_levels = 0, lh[8], lw[8];
+    size_t lp[8], lo[8], fb = 0;
+    int rc = vo_klt_layout_host(H, W, max_level, win, &n_levels, lh, lw, lp, lo, &fb);
+    if (rc) return rc;
+    if (n_pts == 0) return VO_OK;
+    const size_t pts_b = (size_t)n_frames * n_pts * 2 * sizeof(float);
+    if ((rc = vo_buf_reserve(&ctx->scratch[5], fb * n_frames))) return rc;
+    if ((rc = vo_buf_reserve(&ctx->scratch[6], fb * n_frames))) return rc;
+    if ((rc = vo_buf_reserve(&ctx->scratch[7], 2 * pts_b + (size_t)n_frames * n_pts * 8 + 1024))) return rc;
+    uint8_t* pa = (uint8_t*)ctx->scratch[5].p;
+    uint8_t* pb = (uint8_t*)ctx->scratch[6].p;
+    float* d_prev = (float*)ctx->scratch[7].p;
+    float* d_next = d_prev + (size_t)n_frames * n_pts * 2;
+    float* d_err = d_next + (size_t)n_frames * n_pts * 2;
+    uint8_t* d_st = (uint8_t*)(d_err + (size_t)n_frames * n_pts);
+    // frames go straight into the level-0 slots of the pyramids
+    for (int f = 0; f < n_frames; f++) {
+        VO_CUDA(cudaMemcpy2DAsync(pa + f * fb, lp[0], h_prev + (size_t)f * H * W, W, W, H, cudaMemcpyHostToDevice, s));
+        VO_CUDA(cudaMemcpy2DAsync(pb + f * fb, lp[0], h_next + (size_t)f * H * W, W, W, H, cudaMemcpyHostToDevice, s));
+    }
+    VO_CUDA(cudaMemcpyAsync(d_prev, h_prev_pts, pts_b, cudaMemcpyHostToDevice, s));
+    if ((rc = vo_launch_klt_pyramid(ctx, pa, n_frames, H, W, lp[0], fb, max_level, win, pa, s))) return rc;
+    if ((rc = vo_launch_klt_pyramid(ctx, pb, n_frames, H, W, lp[0], fb, max_level, win, pb, s))) return rc;
+    if ((rc = vo_launch_klt_track(ctx, pa, pb, n_frames, H, W, max_level, win, max_iters, epsilon, min_eig_threshold,
+                                  d_prev, n_pts, d_next, d_st, d_err, s))) return rc;
+    VO_CUDA(cudaMemcpyAsync(h_next_pts, d_next, pts_b, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_err, d_err, (size_t)n_frames * n_pts * sizeof(float), cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_status, d_st, (size_t)n_frames * n_pts, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
+    return VO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// P3P + RANSAC
+// ------------------------------------------------------------------------------------------
+int vo_p3p_ransac_score_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
+                            int N, const double* K9, const int32_t* d_sample_idx, int n_hyp, double threshold,
+                            double* d_models, uint8_t* d_valid, int32_t* d_counts, void* stream) {
+    VO_REQUIRE(ctx && d_landmarks && d_keypoints && K9 && d_sample_idx && d_models && d_valid && d_counts,
+               "vo_p3p_ransac_score_dev: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_launch_p3p_score(ctx, d_landmarks, d_keypoints, n_frames, N, K9, d_sample_idx, n_hyp, threshold,
+                               d_models, d_valid, d_counts, pick_stream(ctx, stream));
+}
+
+int vo_p3p_ransac_select_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
+                             int N, const double* K9, const double* d_models, const uint8_t* d_valid,
+                             const int32_t* d_counts, int n_hyp, double threshold, const int32_t* d_iters_for_count,
+                             int initial_iters, int start_n, int start_best, int32_t* d_best4, int32_t* d_consumed,
+                             int32_t* d_iters_out, uint8_t* d_inliers, double* d_best_model, void* stream) {
+    VO_REQUIRE(ctx && d_landmarks && d_keypoints && K9 && d_models && d_valid && d_counts && d_iters_for_count &&
+               d_best4 && d_consumed && d_iters_out && d_inliers && d_best_model,
+               "vo_p3p_ransac_select_dev: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_launch_p3p_select(ctx, d_landmarks, d_keypoints, n_frames, N, K9, d_models, d_valid, d_counts, n_hyp,
+                                threshold, d_iters_for_count, initial_iters, start_n, start_best, d_best4, d_consumed,
+                                d_iters_out, d_inliers, d_best_model, pick_stream(ctx, stream));
+}
+
+int vo_p3p_ransac_host(vo_ctx* ctx, const double* h_landmarks, const double* h_keypoints, int n_frames, int N,
+                       const double* K9, const int32_t* h_sample_idx, int n_hyp, double threshold,
+                       const int32_t* h_iters_for_count, int initial_iters, int start_n, int start_best,
+                       int32_t* h_best4, int32_t* h_consumed, int32_t* h_iters_out, uint8_t* h_inliers,
+                       double* h_best_model, int32_t* h_counts, uint8_t* h_valid, double* h_models) {
+    VO_REQUIRE(ctx && h_landmarks && h_keypoints && K9 && h_sample_idx && h_iters_for_count && h_best4 &&
+               h_consumed && h_iters_out && h_inliers && h_best_model, "vo_p3p_ransac_host: null argument");
+    VO_REQUIRE(n_frames >= 1 && N >= 4 && n_hyp >= 1, "vo_p3p_ransac_host: bad sizes");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t F = n_frames;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_l = carve(F * N * 24), o_k = carve(F * N * 16), o_s = carve(F * n_hyp * 16);
+    const size_t o_m = carve(F * n_hyp * 96), o_v = carve(F * n_hyp), o_c = carve(F * n_hyp * 4);
+    const size_t o_t = carve((size_t)(N + 1) * 4), o_b = carve(F * 16), o_con = carve(F * 4), o_it = carve(F * 4);
+    const size_t o_in = carve(F * N), o_bm = carve(F * 96);
+    int rc = vo_buf_reserve(&ctx->scratch[8], off);
+    if (rc) return rc;
+    unsigned char* b = (unsigned char*)ctx->scratch[8].p;
+    VO_CUDA(cudaMemcpyAsync(b + o_l, h_landmarks, F * N * 24, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(b + o_k, h_keypoints, F * N * 16, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(b + o_s, h_sample_idx, F * n_hyp * 16, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(b + o_t, h_iters_for_count, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = vo_launch_p3p_score(ctx, (double*)(b + o_l), (double*)(b + o_k), n_frames, N, K9, (int*)(b + o_s), n_hyp,
+                                  threshold, (double*)(b + o_m), b + o_v, (int*)(b + o_c), s))) return rc;
+    if ((rc = vo_launch_p3p_select(ctx, (double*)(b + o_l), (double*)(b + o_k), n_frames, N, K9, (double*)(b + o_m),
+                                   b + o_v, (int*)(b + o_c), n_hyp, threshold, (int*)(b + o_t), initial_iters, start_n,
+                                   start_best, (int*)(b + o_b), (int*)(b + o_con), (int*)(b + o_it), b + o_in,
+                                   (double*)(b + o_bm), s))) return rc;
+    VO_CUDA(cudaMemcpyAsync(h_best4, b + o_b, F * 16, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_consumed, b + o_con, F * 4, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_iters_out, b + o_it, F * 4, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_inliers, b + o_in, F * N, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_best_model, b + o_bm, F * 96, cudaMemcpyDeviceToHost, s));
+    if (h_counts) VO_CUDA(cudaMemcpyAsync(h_counts, b + o_c, F * n_hyp * 4, cudaMemcpyDeviceToHost, s));
+    if (h_valid) VO_CUDA(cudaMemcpyAsync(h_valid, b + o_v, F * n_hyp, cudaMemcpyDeviceToHost, s));
+    if (h_models) VO_CUDA(cudaMemcpyAsync(h_models, b + o_m, F * n_hyp * 96, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
+    return VO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Triangulation
+// ------------------------------------------------------------------------------------------
+int vo_triangulate_dev(vo_ctx* ctx, const double* d_p1, const double* d_p2, int n, const double* d_proj1,
+                       int proj1_per_point, const double* d_proj2, int mode, double* d_out, void* stream) {
+    VO_REQUIRE(ctx && (n == 0 || (d_p1 && d_p2 && d_proj1 && d_proj2 && d_out)), "vo_triangulate_dev: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_launch_triangulate(ctx, d_p1, d_p2, n, d_proj1, proj1_per_point, d_proj2, mode, d_out,
+                                 pick_stream(ctx, stream));
+}
+
+int vo_triangulate_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int n, const double* h_proj1,
+                        int proj1_per_point, const double* h_proj2, int mode, double* h_out) {
+    VO_REQUIRE(ctx && n >= 0, "vo_triangulate_host: bad arguments");
+    if (n == 0) return VO_OK;
+    VO_REQUIRE(h_p1 && h_p2 && h_proj1 && h_proj2 && h_out, "vo_triangulate_host: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t np1 = proj1_per_point ? (size_t)n : 1;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_a = carve((size_t)n * 16), o_b = carve((size_t)n * 16), o_c1 = carve(np1 * 96), o_c2 = carve(96);
+    const size_t o_o = carve((size_t)n * 24);
+    int rc = vo_buf_reserve(&ctx->scratch[9], off);
+    if (rc) return rc;
+    unsigned char* b = (unsigned char*)ctx->scratch[9].p;
+    VO_CUDA(cudaMemcpyAsync(b + o_a, h_p1, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(b + o_b, h_p2, (size_t)n * 16, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(b + o_c1, h_proj1, np1 * 96, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(b + o_c2, h_proj2, 96, cudaMemcpyHostToDevice, s));
+    if ((rc = vo_launch_triangulate(ctx, (double*)(b + o_a), (double*)(b + o_b), n, (double*)(b + o_c1),
+                                    proj1_per_point, (double*)(b + o_c2), mode, (double*)(b + o_o), s))) return rc;
+    VO_CUDA(cudaMemcpyAsync(h_out, b + o_o, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
+    return VO_OK;
+}
+
 }  // extern "C"

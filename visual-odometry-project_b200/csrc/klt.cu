@@ -1,0 +1,346 @@
+// Pyramidal Lucas-Kanade tracker for sm_100a: one warp per keypoint.
+//
+// Replaces  /root/reference/src/vo/features/klt.py:233-239  cv2.calcOpticalFlowPyrLK(winSize=(17,17),
+//           maxLevel=2, criteria=(EPS|COUNT, 10, 0.03))  and the status/error outputs used at klt.py:244-249.
+//
+// The algorithm is OpenCV's (video/src/lkpyramid.cpp, imgproc pyrDown): reflect-101 Gaussian
+// pyramid, Scharr derivatives, 14-bit fixed-point bilinear patches, 2x2 normal equations, Newton
+// steps with the EPS / oscillation stopping rules.  Per warp: the (win+3)^2 neighbourhood of the
+// point is staged in shared memory, lanes stride over the win^2 window pixels, the Gram matrix
+// and mismatch vector are reduced with warp shuffles as exact integers, and every lane carries
+// the (uniform) float32 iteration state in OpenCV's operation order (--fmad=false).
+#include "common.cuh"
+
+namespace {
+
+constexpr int W_BITS = 14;
+constexpr int KLT_MAX_LEVELS = 8;
+constexpr int KLT_WARPS = 4;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        if (i < 0) i = -i;
+        else i = 2 * n - 2 - i;
+    }
+    return i;
+}
+
+// cv2.pyrDown (uint8, 1 channel): thread per output pixel
+__global__ void __launch_bounds__(256)
+pyr_down_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch, size_t sframe,
+                uint8_t* __restrict__ dst, int dh, int dw, size_t dpitch, size_t dframe) {
+    const int dx = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (dx >= dw || dy >= dh) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * sframe;
+    int xs[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) xs[k] = reflect101(2 * dx + k - 2, W);
+    const int wts[5] = {1, 4, 6, 4, 1};
+    int acc = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const uint8_t* r = s + (size_t)reflect101(2 * dy + j - 2, H) * spitch;
+        const int rowsum = (int)r[xs[0]] + (int)r[xs[4]] + 4 * ((int)r[xs[1]] + (int)r[xs[3]]) + 6 * (int)r[xs[2]];
+        acc += wts[j] * rowsum;
+    }
+    dst[(size_t)blockIdx.z * dframe + (size_t)dy * dpitch + dx] = (uint8_t)((acc + 128) >> 8);
+}
+
+__global__ void copy_level0_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch, size_t sframe,
+                                   uint8_t* __restrict__ dst, size_t dpitch, size_t dframe) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x < W) dst[(size_t)blockIdx.z * dframe + (size_t)y * dpitch + x] = src[(size_t)blockIdx.z * sframe + (size_t)y * spitch + x];
+}
+
+struct PyrLayout {
+    int n_levels;
+    int h[KLT_MAX_LEVELS], w[KLT_MAX_LEVELS];
+    size_t pitch[KLT_MAX_LEVELS], offset[KLT_MAX_LEVELS];
+    size_t frame_bytes;
+};
+
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// Stage the reflect-101 extended image region [x0, x0+n) x [y0, y0+n) into shared memory.
+__device__ __forceinline__ void stage_patch(const uint8_t* __restrict__ img, int rows, int cols, size_t pitch,
+                                            int x0, int y0, int n, uint8_t* sm, int lane) {
+    for (int i = lane; i < n * n; i += 32) {
+        const int py = i / n, px = i - py * n;
+        sm[i] = img[(size_t)reflect101(y0 + py, rows) * pitch + reflect101(x0 + px, cols)];
+    }
+}
+
+__global__ void __launch_bounds__(KLT_WARPS * 32)
+klt_track_kernel(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__ pyr_next, PyrLayout lay,
+                 int win, int max_iters, double eps2, double min_eig, const float* __restrict__ prev_pts, int n_pts,
+                 float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pt = blockIdx.x * KLT_WARPS + warp;
+    const int f = blockIdx.y;
+    if (pt >= n_pts) return;
+    const int w2 = win * win;
+    const int pn = win + 3;                 // staged I neighbourhood
+    const int dn = win + 1;                 // integer positions where derivatives / J are needed
+    // per-warp shared memory slices
+    const size_t per_warp = (size_t)((pn * pn + 15) & ~15) + (size_t)dn * dn * 4 + (size_t)w2 * 2 + (size_t)w2 * 4;
+    unsigned char* base = smem_raw + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
+    uint8_t* patch = base;                                                     // [pn*pn] u8 (I), reused for J [dn*dn]
+    short* dpatch = reinterpret_cast<short*>(base + ((pn * pn + 15) & ~15));  // [dn*dn][2]
+    short* Iw = dpatch + dn * dn * 2;                                          // [w2]
+    short* dIw = Iw + w2;                                                      // [w2][2]
+
+    const uint8_t* Ip = pyr_prev + (size_t)f * lay.frame_bytes;
+    const uint8_t* Jp = pyr_next + (size_t)f * lay.frame_bytes;
+    const size_t pidx = (size_t)f * n_pts + pt;
+    const float px0 = prev_pts[2 * pidx], py0 = prev_pts[2 * pidx + 1];
+    const float half = (float)(win - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const int top = lay.n_levels - 1;
+    bool st = true;
+    float e_out = 0.f;
+    float outx = 0.f, outy = 0.f;  // nextPts[ptidx]
+
+    for (int level = top; level >= 0; level--) {
+        const int cols = lay.w[level], rows = lay.h[level];
+        const size_t pitch = lay.pitch[level];
+        const uint8_t* I = Ip + lay.offset[level];
+        const uint8_t* J = Jp + lay.offset[level];
+        const float sc = (float)(1. / (1 << level));
+        float prx = px0 * sc, pry = py0 * sc;
+        float nx, ny;
+        if (level == top) { nx = prx; ny = pry; }
+        else { nx = outx * 2.f; ny = outy * 2.f; }
+        outx = nx; outy = ny;
+        prx -= half; pry -= half;
+        const int ipx = (int)floorf(prx), ipy = (int)floorf(pry);
+        if (ipx < -win || ipx >= cols || ipy < -win || ipy >= rows) {
+            if (level == 0) { st = false; e_out = 0.f; }
+            continue;
+        }
+        float a = prx - ipx, b = pry - ipy;
+        int iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS));
+        int iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
+        int iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
+        int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+
+        __syncwarp();
+        stage_patch(I, rows, cols, pitch, ipx - 1, ipy - 1, pn, patch, lane);
+        __syncwarp();
+        // Scharr derivatives at the (win+1)^2 integer positions; zero outside the image
+        for (int i = lane; i < dn * dn; i += 32) {
+            const int qy = i / dn, qx = i - qy * dn;
+            const int gx = ipx + qx, gy = ipy + qy;
+            int dx = 0, dy = 0;
+            if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+                const uint8_t* r0 = patch + qy * pn + qx;  // top-left of the 3x3 neighbourhood
+                const uint8_t* r1 = r0 + pn;
+                const uint8_t* r2 = r1 + pn;
+                const int t0m = ((int)r0[0] + (int)r2[0]) * 3 + (int)r1[0] * 10;
+                const int t0p = ((int)r0[2] + (int)r2[2]) * 3 + (int)r1[2] * 10;
+                const int t1m = (int)r2[0] - (int)r0[0], t1c = (int)r2[1] - (int)r0[1], t1p = (int)r2[2] - (int)r0[2];
+                dx = t0p - t0m;
+                dy = (t1p + t1m) * 3 + t1c * 10;
+            }
+            dpatch[2 * i] = (short)dx;
+            dpatch[2 * i + 1] = (short)dy;
+        }
+        __syncwarp();
+        int sA11 = 0, sA12 = 0, sA22 = 0;
+        for (int i = lane; i < w2; i += 32) {
+            const int y = i / win, x = i - y * win;
+            const uint8_t* s0 = patch + (y + 1) * pn + (x + 1);
+            const int ival = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[pn] * iw10 + (int)s0[pn + 1] * iw11,
+                                     W_BITS - 5);
+            const short* d0 = dpatch + 2 * (y * dn + x);
+            const short* d1 = d0 + 2 * dn;
+            const int ixval = descale((int)d0[0] * iw00 + (int)d0[2] * iw01 + (int)d1[0] * iw10 + (int)d1[2] * iw11, W_BITS);
+            const int iyval = descale((int)d0[1] * iw00 + (int)d0[3] * iw01 + (int)d1[1] * iw10 + (int)d1[3] * iw11, W_BITS);
+            Iw[i] = (short)ival;
+            dIw[2 * i] = (short)ixval;
+            dIw[2 * i + 1] = (short)iyval;
+            sA11 += ixval * ixval;
+            sA12 += ixval * iyval;
+            sA22 += iyval * iyval;
+        }
+        const long long iA11 = warp_sum_ll(sA11), iA12 = warp_sum_ll(sA12), iA22 = warp_sum_ll(sA22);
+        const float A11 = (float)iA11 * FLT_SCALE, A12 = (float)iA12 * FLT_SCALE, A22 = (float)iA22 * FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+        if ((double)minEig < min_eig || D < 1.1920928955078125e-07f) {
+            if (level == 0) st = false;
+            continue;
+        }
+        D = 1.f / D;
+        nx -= half; ny -= half;
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < max_iters; j++) {
+            const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+            if (inx < -win || inx >= cols || iny < -win || iny >= rows) {
+                if (level == 0) st = false;
+                break;
+            }
+            a = nx - inx; b = ny - iny;
+            iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS));
+            iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
+            iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
+            iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+            __syncwarp();
+            stage_patch(J, rows, cols, pitch, inx, iny, dn, patch, lane);
+            __syncwarp();
+            int sb1 = 0, sb2 = 0;
+            for (int i = lane; i < w2; i += 32) {
+                const int y = i / win, x = i - y * win;
+                const uint8_t* s0 = patch + y * dn + x;
+                const int diff = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[dn] * iw10 + (int)s0[dn + 1] * iw11,
+                                         W_BITS - 5) - (int)Iw[i];
+                sb1 += diff * (int)dIw[2 * i];
+                sb2 += diff * (int)dIw[2 * i + 1];
+            }
+            const long long ib1 = warp_sum_ll(sb1), ib2 = warp_sum_ll(sb2);
+            const float b1 = (float)ib1 * FLT_SCALE, b2 = (float)ib2 * FLT_SCALE;
+            const float dx = (float)((A12 * b2 - A22 * b1) * D);
+            const float dy = (float)((A12 * b1 - A11 * b2) * D);
+            nx += dx; ny += dy;
+            outx = nx + half; outy = ny + half;
+            if ((double)dx * dx + (double)dy * dy <= eps2) break;
+            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+                outx -= dx * 0.5f;
+                outy -= dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (st && level == 0) {
+            const float fx = outx - half, fy = outy - half;
+            const int inx = (int)floorf(fx), iny = (int)floorf(fy);
+            if (inx < -win || inx >= cols || iny < -win || iny >= rows) {
+                st = false;
+                continue;
+            }
+            const float aa = fx - inx, bb = fy - iny;
+            iw00 = __float2int_rn((1.f - aa) * (1.f - bb) * (1 << W_BITS));
+            iw01 = __float2int_rn(aa * (1.f - bb) * (1 << W_BITS));
+            iw10 = __float2int_rn((1.f - aa) * bb * (1 << W_BITS));
+            iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+            __syncwarp();
+            stage_patch(J, rows, cols, pitch, inx, iny, dn, patch, lane);
+            __syncwarp();
+            int se = 0;
+            for (int i = lane; i < w2; i += 32) {
+                const int y = i / win, x = i - y * win;
+                const uint8_t* s0 = patch + y * dn + x;
+                const int diff = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[dn] * iw10 + (int)s0[dn + 1] * iw11,
+                                         W_BITS - 5) - (int)Iw[i];
+                se += diff < 0 ? -diff : diff;
+            }
+            const long long e = warp_sum_ll(se);
+            e_out = (float)e * 1.f / (float)(32 * win * win);
+        }
+    }
+    if (lane == 0) {
+        next_pts[2 * pidx] = outx;
+        next_pts[2 * pidx + 1] = outy;
+        status[pidx] = st ? 1 : 0;
+        err[pidx] = e_out;
+    }
+}
+
+}  // namespace
+
+static int klt_layout(int H, int W, int max_level, int win, PyrLayout* L) {
+    if (max_level < 0 || max_level >= KLT_MAX_LEVELS) return 1;
+    int h = H, w = W, level = 0;
+    size_t off = 0;
+    for (;;) {
+        L->h[level] = h; L->w[level] = w;
+        L->pitch[level] = ((size_t)w + 15) & ~(size_t)15;
+        L->offset[level] = off;
+        off += (L->pitch[level] * h + 255) & ~(size_t)255;
+        if (level == max_level) break;
+        const int nh = (h + 1) / 2, nw = (w + 1) / 2;
+        if (nw <= win || nh <= win) break;
+        h = nh; w = nw; level++;
+    }
+    L->n_levels = level + 1;
+    L->frame_bytes = off;
+    return 0;
+}
+
+int vo_klt_layout_host(int H, int W, int max_level, int win, int* n_levels, int* level_h, int* level_w,
+                       size_t* level_pitch, size_t* level_offset, size_t* frame_bytes) {
+    PyrLayout L;
+    VO_REQUIRE(H >= 1 && W >= 1 && win >= 3 && win <= 31, "klt: bad image size / window (3..31)");
+    VO_REQUIRE(klt_layout(H, W, max_level, win, &L) == 0, "klt: max_level must be in [0, %d)", KLT_MAX_LEVELS);
+    *n_levels = L.n_levels;
+    for (int l = 0; l < L.n_levels; l++) {
+        if (level_h) level_h[l] = L.h[l];
+        if (level_w) level_w[l] = L.w[l];
+        if (level_pitch) level_pitch[l] = L.pitch[l];
+        if (level_offset) level_offset[l] = L.offset[l];
+    }
+    *frame_bytes = L.frame_bytes;
+    return VO_OK;
+}
+
+int vo_launch_klt_pyramid(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
+                          size_t frame_stride, int max_level, int win, uint8_t* d_pyr, cudaStream_t stream) {
+    PyrLayout L;
+    VO_REQUIRE(H >= 1 && W >= 1 && win >= 3 && win <= 31 && n_frames >= 1, "klt pyramid: bad arguments");
+    VO_REQUIRE(klt_layout(H, W, max_level, win, &L) == 0, "klt: max_level must be in [0, %d)", KLT_MAX_LEVELS);
+    // level 0: copy unless the caller already placed the frames in the pyramid's level-0 slots
+    if (!(d_img == d_pyr && pitch == L.pitch[0] && frame_stride == L.frame_bytes)) {
+        dim3 g(vo_div_up(W, 256), H, n_frames);
+        copy_level0_kernel<<<g, 256, 0, stream>>>(d_img, H, W, pitch, frame_stride, d_pyr, L.pitch[0], L.frame_bytes);
+        ctx->launches++;
+        VO_CHECK_LAUNCH();
+    }
+    for (int l = 1; l < L.n_levels; l++) {
+        dim3 g(vo_div_up(L.w[l], 32), vo_div_up(L.h[l], 8), n_frames);
+        pyr_down_kernel<<<g, 256, 0, stream>>>(d_pyr + L.offset[l - 1], L.h[l - 1], L.w[l - 1], L.pitch[l - 1],
+                                               L.frame_bytes, d_pyr + L.offset[l], L.h[l], L.w[l], L.pitch[l],
+                                               L.frame_bytes);
+        ctx->launches++;
+        VO_CHECK_LAUNCH();
+    }
+    return VO_OK;
+}
+
+int vo_launch_klt_track(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d_pyr_next, int n_frames, int H, int W,
+                        int max_level, int win, int max_iters, double epsilon, double min_eig,
+                        const float* d_prev_pts, int n_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
+                        cudaStream_t stream) {
+    PyrLayout L;
+    VO_REQUIRE(H >= 1 && W >= 1 && win >= 3 && win <= 31 && n_frames >= 1 && n_pts >= 0, "klt track: bad arguments");
+    VO_REQUIRE(klt_layout(H, W, max_level, win, &L) == 0, "klt: max_level must be in [0, %d)", KLT_MAX_LEVELS);
+    if (n_pts == 0) return VO_OK;
+    // criteria clamps of cv2.calcOpticalFlowPyrLK
+    if (max_iters < 0) max_iters = 0;
+    if (max_iters > 100) max_iters = 100;
+    if (epsilon < 0.) epsilon = 0.;
+    if (epsilon > 10.) epsilon = 10.;
+    const int pn = win + 3, dn = win + 1, w2 = win * win;
+    size_t per_warp = (size_t)((pn * pn + 15) & ~15) + (size_t)dn * dn * 4 + (size_t)w2 * 2 + (size_t)w2 * 4;
+    per_warp = (per_warp + 15) & ~(size_t)15;
+    const size_t smem = per_warp * KLT_WARPS;
+    static bool attr_set = false;
+    if (!attr_set) {
+        VO_CUDA(cudaFuncSetAttribute(klt_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        attr_set = true;
+    }
+    dim3 g(vo_div_up(n_pts, KLT_WARPS), n_frames);
+    klt_track_kernel<<<g, KLT_WARPS * 32, smem, stream>>>(d_pyr_prev, d_pyr_next, L, win, max_iters, epsilon * epsilon,
+                                                          min_eig, d_prev_pts, n_pts, d_next_pts, d_status, d_err);
+    ctx->launches++;
+    VO_CHECK_LAUNCH();
+    return VO_OK;
+}

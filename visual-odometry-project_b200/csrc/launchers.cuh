@@ -12,3 +12,25 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
 int vo_launch_harris_descriptors(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
                                  size_t frame_stride, const int* d_kp_xy, int K, int r, uint8_t* d_desc,
                                  cudaStream_t stream);
+
+// klt.cu
+int vo_klt_layout_host(int H, int W, int max_level, int win, int* n_levels, int* level_h, int* level_w,
+                       size_t* level_pitch, size_t* level_offset, size_t* frame_bytes);
+int vo_launch_klt_pyramid(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
+                          size_t frame_stride, int max_level, int win, uint8_t* d_pyr, cudaStream_t stream);
+int vo_launch_klt_track(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d_pyr_next, int n_frames, int H, int W,
+                        int max_level, int win, int max_iters, double epsilon, double min_eig,
+                        const float* d_prev_pts, int n_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
+                        cudaStream_t stream);
+// p3p.cu
+int vo_launch_p3p_score(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames, int N,
+                        const double* K9, const int* d_sample_idx, int n_hyp, double threshold, double* d_models,
+                        unsigned char* d_valid, int* d_counts, cudaStream_t stream);
+int vo_launch_p3p_select(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames, int N,
+                         const double* K9, const double* d_models, const unsigned char* d_valid, const int* d_counts,
+                         int n_hyp, double threshold, const int* d_iters_for_count, int initial_iters, int start_n,
+                         int start_best, int* d_best4, int* d_consumed, int* d_iters_out, unsigned char* d_inliers,
+                         double* d_best_model, cudaStream_t stream);
+// triangulation.cu
+int vo_launch_triangulate(vo_ctx* ctx, const double* d_p1, const double* d_p2, int n, const double* d_proj1,
+                          int proj1_per_point, const double* d_proj2, int mode, double* d_out, cudaStream_t stream);

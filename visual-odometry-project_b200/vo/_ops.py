@@ -45,3 +45,104 @@ def harris_detect(img, num_keypoints=1000, patch_size=9, kappa=0.09, nms_radius=
     if single:
         return kp[0], (resp[0] if resp is not None else None), (desc[0] if desc is not None else None)
     return kp, resp, desc
+
+
+# ------------------------------------------------------------------------------------------------
+# KLT  (reference: src/vo/features/klt.py:233-239 -> cv2.calcOpticalFlowPyrLK)
+# ------------------------------------------------------------------------------------------------
+def klt_track(prev, nxt, pts, win=17, max_level=2, max_iters=10, epsilon=0.03, min_eig=1e-4, ctx=None):
+    """Pyramidal LK for one frame pair (H, W) or a batch (F, H, W); pts (N, 2) or (F, N, 2) float32.
+
+    Returns (next_pts float32, status uint8, err float32) shaped like cv2's outputs (without the
+    middle singleton axis)."""
+    ctx = _ctx(ctx)
+    a = np.ascontiguousarray(prev, dtype=np.uint8)
+    b = np.ascontiguousarray(nxt, dtype=np.uint8)
+    if a.shape != b.shape:
+        raise ValueError("klt_track: prev and next images must have the same shape")
+    single = a.ndim == 2
+    if single:
+        a, b = a[None], b[None]
+    F, H, W = a.shape
+    p = np.ascontiguousarray(np.asarray(pts, dtype=np.float32).reshape(F, -1, 2))
+    n = p.shape[1]
+    out = np.zeros((F, n, 2), dtype=np.float32)
+    status = np.zeros((F, n), dtype=np.uint8)
+    err = np.zeros((F, n), dtype=np.float32)
+    rc = nat.lib().vo_klt_track_host(ctx.handle, nat.ptr(a), nat.ptr(b), F, H, W, int(max_level), int(win),
+                                     int(max_iters), C.c_double(epsilon), C.c_double(min_eig), nat.ptr(p), n,
+                                     nat.ptr(out), nat.ptr(status), nat.ptr(err))
+    nat.check(rc, "vo_klt_track_host")
+    if single:
+        return out[0], status[0], err[0]
+    return out, status, err
+
+
+# ------------------------------------------------------------------------------------------------
+# P3P + RANSAC  (reference: src/vo/pose_estimation/p3p.py, src/vo/algorithms/ransac.py)
+# ------------------------------------------------------------------------------------------------
+def p3p_ransac(landmarks, keypoints, K, sample_idx, threshold, iters_for_count, initial_iters, start_n=0,
+               start_best=-1, want_all=False, ctx=None):
+    """Score every 4-index sample set and replay the reference's adaptive loop over them.
+
+    landmarks (N, 3) / keypoints (N, 2) or batched (F, N, .); sample_idx (H, 4) or (F, H, 4) int32.
+    Returns a dict with best (index or -1), best_count, n, exhausted, consumed, n_iterations,
+    inliers (bool), R, t and, with want_all, counts / valid / models for every hypothesis."""
+    ctx = _ctx(ctx)
+    L = np.asarray(landmarks, dtype=np.float64)
+    single = L.ndim == 2 or (L.ndim == 3 and L.shape[-1] == 1)
+    L = np.ascontiguousarray(L.reshape((1, -1, 3)) if single else L.reshape(L.shape[0], -1, 3))
+    F, N = L.shape[0], L.shape[1]
+    P = np.ascontiguousarray(np.asarray(keypoints, dtype=np.float64).reshape(F, N, 2))
+    S = np.ascontiguousarray(np.asarray(sample_idx, dtype=np.int32).reshape(F, -1, 4))
+    Hn = S.shape[1]
+    K9 = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    table = np.ascontiguousarray(np.asarray(iters_for_count, dtype=np.int32).reshape(-1))
+    if table.shape[0] != N + 1:
+        raise ValueError("p3p_ransac: iters_for_count must have N + 1 entries")
+    best4 = np.zeros((F, 4), dtype=np.int32)
+    consumed = np.zeros(F, dtype=np.int32)
+    iters_out = np.zeros(F, dtype=np.int32)
+    inl = np.zeros((F, N), dtype=np.uint8)
+    bm = np.zeros((F, 12), dtype=np.float64)
+    counts = np.zeros((F, Hn), dtype=np.int32) if want_all else None
+    valid = np.zeros((F, Hn), dtype=np.uint8) if want_all else None
+    models = np.zeros((F, Hn, 12), dtype=np.float64) if want_all else None
+    rc = nat.lib().vo_p3p_ransac_host(
+        ctx.handle, nat.ptr(L), nat.ptr(P), F, N, nat.ptr(K9), nat.ptr(S), Hn, C.c_double(threshold), nat.ptr(table),
+        int(initial_iters), int(start_n), int(start_best), nat.ptr(best4), nat.ptr(consumed), nat.ptr(iters_out),
+        nat.ptr(inl), nat.ptr(bm), nat.ptr(counts) if want_all else None, nat.ptr(valid) if want_all else None,
+        nat.ptr(models) if want_all else None)
+    nat.check(rc, "vo_p3p_ransac_host")
+    res = dict(best=best4[:, 0], best_count=best4[:, 1], n=best4[:, 2], exhausted=best4[:, 3].astype(bool),
+               consumed=consumed, n_iterations=iters_out, inliers=inl.astype(bool), R=bm[:, :9].reshape(F, 3, 3),
+               t=bm[:, 9:].reshape(F, 3, 1), counts=counts, valid=valid, models=models)
+    if single:
+        res = {k: (v[0] if v is not None else None) for k, v in res.items()}
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# Triangulation  (reference: src/vo/landmarks/triangulation.py:352-389, 38-86)
+# ------------------------------------------------------------------------------------------------
+def triangulate(p1, p2, C1, C2, mode=0, ctx=None):
+    """DLT triangulation: p1, p2 (N, 2[, 1]); C1 (3, 4) or (N, 3, 4); C2 (3, 4) -> (N, 3) float64."""
+    ctx = _ctx(ctx)
+    a = np.ascontiguousarray(np.asarray(p1, dtype=np.float64).reshape(-1, 2))
+    b = np.ascontiguousarray(np.asarray(p2, dtype=np.float64).reshape(-1, 2))
+    if a.shape != b.shape:
+        raise ValueError("triangulate: input points dimension mismatch")
+    n = a.shape[0]
+    c1 = np.asarray(C1, dtype=np.float64)
+    per_point = 1 if c1.ndim == 3 else 0
+    if per_point and c1.shape[0] != n:
+        raise ValueError("triangulate: per-point projection matrices must match the number of points")
+    c1 = np.ascontiguousarray(c1.reshape(-1, 12))
+    c2 = np.ascontiguousarray(np.asarray(C2, dtype=np.float64).reshape(12))
+    out = np.empty((n, 3), dtype=np.float64)
+    if n == 0:
+        return out
+    rc = nat.lib().vo_triangulate_host(ctx.handle, nat.ptr(a), nat.ptr(b), n, nat.ptr(c1), per_point, nat.ptr(c2),
+                                       int(mode), nat.ptr(out))
+    nat.check(rc, "vo_triangulate_host")
+    return out
