@@ -37,6 +37,8 @@ unsigned long long vo_ctx_launch_count(const vo_ctx* ctx);
 int vo_ctx_synchronize(vo_ctx* ctx);
 /* the context's stream as a cudaStream_t (for event timing on the launching stream) */
 void* vo_ctx_stream(vo_ctx* ctx);
+/* synchronous device -> host copy of a resident result buffer (after a device-wide sync) */
+int vo_copy_to_host(vo_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 
 /* ---- Harris: src/vo/features/harris.py ---------------------------------------------------- */
 /* harris.py:102-137  float64 score map [n_frames][H][W], zero border of patch_size/2+1 pixels.  */
@@ -121,6 +123,50 @@ int vo_triangulate_dev(vo_ctx* ctx, const double* d_p1, const double* d_p2, int 
                        int proj1_per_point, const double* d_proj2, int mode, double* d_out, void* stream);
 int vo_triangulate_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int n, const double* h_proj1,
                         int proj1_per_point, const double* h_proj2, int mode, double* h_out);
+
+/* ---- The front end as one resident object: src/main.py:248-287 (loop body) --------------------- */
+/* Per-sequence state (pyramids of the previous / current frame, last keypoints) stays in HBM; one
+ * call advances n_seq independent sequences by one frame: pyramid -> KLT (previous keypoints into
+ * the new frame, klt.py:233-239) -> Harris on the new frame (harris.py:86-158) -> P3P-RANSAC on
+ * the supplied 3D-2D correspondences (p3p.py:123-186, use_opencv=False) -> DLT triangulation of the
+ * supplied tracks (triangulation.py:38-86).                                                       */
+typedef struct vo_frontend vo_frontend;
+typedef struct {
+    int n_seq, H, W;
+    int patch_size; double kappa; int nms_radius; int num_keypoints;          /* harris.py:16-34   */
+    int klt_win, klt_max_level, klt_max_iters; double klt_epsilon, klt_min_eig; /* klt.py:29-33    */
+    int n_corr, n_hyp; double p3p_threshold;                                   /* p3p.py:14-40      */
+    int n_tri, tri_mode;                                                       /* triangulation.py  */
+} vo_frontend_params;
+typedef struct {
+    double* d_resp; int32_t* d_kp_xy; float* d_tracked; uint8_t* d_status; float* d_err;
+    int32_t* d_best4; uint8_t* d_inliers; double* d_pose; double* d_tri_out; int32_t* d_counts;
+    uint8_t* d_cur_pyramid; size_t pyr_pitch0, pyr_frame_bytes;
+} vo_frontend_outputs_t;
+int vo_frontend_create(vo_ctx* ctx, const vo_frontend_params* params, vo_frontend** out);
+void vo_frontend_destroy(vo_frontend* fe);
+/* device pointers of the resident result buffers (valid until destroy) */
+int vo_frontend_outputs(vo_frontend* fe, vo_frontend_outputs_t* out);
+/* level-0 slots the next step will read: upload frames here to skip the copy kernel */
+uint8_t* vo_frontend_next_frame_slot(vo_frontend* fe, size_t* pitch, size_t* frame_stride);
+/* Device-resident step (asynchronous on `stream`).  d_frames uint8 [n_seq] frames with the given
+ * pitch / frame_stride; P3P inputs as vo_p3p_ransac_*; triangulation inputs [n_seq * n_tri] points,
+ * per-point start projections [n_seq * n_tri][12], one end projection per sequence [n_seq][12].  */
+int vo_frontend_step_dev(vo_frontend* fe, const uint8_t* d_frames, size_t pitch, size_t frame_stride,
+                         const double* d_landmarks, const double* d_kp2d, const double* K9,
+                         const int32_t* d_sample_idx, const int32_t* d_iters_table, int initial_iters,
+                         const double* d_tri_p1, const double* d_tri_p2, const double* d_tri_proj1,
+                         const double* d_tri_proj2, void* stream);
+/* Host-buffer step: uploads the frames (tightly packed) and the P3P / triangulation inputs, runs
+ * the step, downloads keypoints int32 [n_seq][K][2], tracked points / status / err of the previous
+ * keypoints, best4 / inlier masks / poses [n_seq][12] and landmarks [n_seq * n_tri][3]; returns when
+ * the results are on the host.  h_tracked, h_status, h_err, h_best4, h_inliers may be NULL.       */
+int vo_frontend_step_host(vo_frontend* fe, const uint8_t* h_frames, const double* h_landmarks, const double* h_kp2d,
+                          const double* K9, const int32_t* h_sample_idx, const int32_t* h_iters_table,
+                          int initial_iters, const double* h_tri_p1, const double* h_tri_p2,
+                          const double* h_tri_proj1, const double* h_tri_proj2, int32_t* h_kp_xy, float* h_tracked,
+                          uint8_t* h_status, float* h_err, int32_t* h_best4, uint8_t* h_inliers, double* h_pose,
+                          double* h_tri_out);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,14 @@ int vo_ctx_synchronize(vo_ctx* ctx) {
 
 void* vo_ctx_stream(vo_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
+int vo_copy_to_host(vo_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+    VO_REQUIRE(ctx && h_dst && d_src, "vo_copy_to_host: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    VO_CUDA(cudaDeviceSynchronize());
+    VO_CUDA(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return VO_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Harris
 // ------------------------------------------------------------------------------------------
@@ -304,7 +312,7 @@ int vo_triangulate_dev(vo_ctx* ctx, const double* d_p1, const double* d_p2, int 
                        int proj1_per_point, const double* d_proj2, int mode, double* d_out, void* stream) {
     VO_REQUIRE(ctx && (n == 0 || (d_p1 && d_p2 && d_proj1 && d_proj2 && d_out)), "vo_triangulate_dev: null argument");
     VO_CUDA(cudaSetDevice(ctx->device));
-    return vo_launch_triangulate(ctx, d_p1, d_p2, n, d_proj1, proj1_per_point, d_proj2, mode, d_out,
+    return vo_launch_triangulate(ctx, d_p1, d_p2, n, d_proj1, proj1_per_point, d_proj2, 0, mode, d_out,
                                  pick_stream(ctx, stream));
 }
 
@@ -328,7 +336,7 @@ int vo_triangulate_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int
     VO_CUDA(cudaMemcpyAsync(b + o_c1, h_proj1, np1 * 96, cudaMemcpyHostToDevice, s));
     VO_CUDA(cudaMemcpyAsync(b + o_c2, h_proj2, 96, cudaMemcpyHostToDevice, s));
     if ((rc = vo_launch_triangulate(ctx, (double*)(b + o_a), (double*)(b + o_b), n, (double*)(b + o_c1),
-                                    proj1_per_point, (double*)(b + o_c2), mode, (double*)(b + o_o), s))) return rc;
+                                    proj1_per_point, (double*)(b + o_c2), 0, mode, (double*)(b + o_o), s))) return rc;
     VO_CUDA(cudaMemcpyAsync(h_out, b + o_o, (size_t)n * 24, cudaMemcpyDeviceToHost, s));
     VO_CUDA(cudaStreamSynchronize(s));
     return VO_OK;

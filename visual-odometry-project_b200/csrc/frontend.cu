@@ -1,0 +1,195 @@
+// The VO front end as one resident object: per-sequence state (image pyramids of the previous and
+// the current frame, last keypoints) stays in HBM; one call advances every sequence by one frame:
+//   pyramid -> KLT (previous keypoints into the new frame) -> Harris on the new frame ->
+//   P3P-RANSAC on the supplied 3D-2D correspondences -> DLT triangulation of the supplied tracks.
+// This is the loop body of /root/reference/src/main.py:248-287 (tracker.trackFeatures,
+// pose_estimator.estimate_pose, triangulator.triangulate_candidates) for S independent sequences.
+// Host code only: it sequences the launchers of harris.cu / klt.cu / p3p.cu / triangulation.cu on
+// one stream, so the whole step is capturable in a CUDA graph.
+#include "../../include/vo_b200.h"
+#include "common.cuh"
+#include "launchers.cuh"
+
+struct vo_frontend {
+    vo_ctx* ctx;
+    vo_frontend_params p;
+    int n_levels;
+    size_t pitch0, frame_bytes;
+    unsigned char* base;      // one allocation, carved below
+    uint8_t* pyr[2];
+    int cur;
+    long long steps;
+    double* resp;
+    int32_t* kp;
+    float *pts_prev, *pts_next, *err;
+    uint8_t* status;
+    double* models; uint8_t* valid; int32_t* counts;
+    int32_t *best4, *consumed, *iters_out; uint8_t* inliers; double* pose;
+    double* tri_out;
+    // staging for the host entry point
+    double *s_landmarks, *s_kp2d, *s_tri_p1, *s_tri_p2, *s_tri_proj1, *s_tri_proj2;
+    int32_t *s_samples, *s_table;
+};
+
+extern "C" {
+
+int vo_frontend_create(vo_ctx* ctx, const vo_frontend_params* prm, vo_frontend** out) {
+    VO_REQUIRE(ctx && prm && out, "vo_frontend_create: null argument");
+    *out = nullptr;
+    const vo_frontend_params& p = *prm;
+    VO_REQUIRE(p.n_seq >= 1 && p.H > 0 && p.W > 0 && p.num_keypoints >= 1 && p.n_corr >= 4 && p.n_hyp >= 1 && p.n_tri >= 0,
+               "vo_frontend_create: bad sizes");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    vo_frontend* fe = new vo_frontend();
+    fe->ctx = ctx; fe->p = p; fe->cur = 0; fe->steps = 0;
+    int lh[8], lw[8]; size_t lp[8], lo[8];
+    int rc = vo_klt_layout_host(p.H, p.W, p.klt_max_level, p.klt_win, &fe->n_levels, lh, lw, lp, lo, &fe->frame_bytes);
+    if (rc) { delete fe; return rc; }
+    fe->pitch0 = lp[0];
+    const size_t S = p.n_seq, K = p.num_keypoints, N = p.n_corr, Hn = p.n_hyp, T = p.n_tri, npx = (size_t)p.H * p.W;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_p0 = carve(S * fe->frame_bytes), o_p1 = carve(S * fe->frame_bytes), o_resp = carve(S * npx * 8);
+    const size_t o_kp = carve(S * K * 8), o_pp = carve(S * K * 8), o_pn = carve(S * K * 8), o_err = carve(S * K * 4);
+    const size_t o_st = carve(S * K), o_m = carve(S * Hn * 96), o_v = carve(S * Hn), o_c = carve(S * Hn * 4);
+    const size_t o_b4 = carve(S * 16), o_con = carve(S * 4), o_it = carve(S * 4), o_in = carve(S * N), o_pose = carve(S * 96);
+    const size_t o_to = carve(S * T * 24 + 256);
+    const size_t o_sl = carve(S * N * 24), o_sk = carve(S * N * 16), o_ss = carve(S * Hn * 16), o_stb = carve((N + 1) * 4);
+    const size_t o_t1 = carve(S * T * 16 + 256), o_t2 = carve(S * T * 16 + 256), o_tp1 = carve(S * T * 96 + 256), o_tp2 = carve(S * 96);
+    cudaError_t e = cudaMalloc(&fe->base, off);
+    if (e != cudaSuccess) {
+        vo_set_error("vo_frontend_create: cudaMalloc(%zu) -> %s", off, cudaGetErrorString(e));
+        delete fe;
+        return VO_ERR_CUDA;
+    }
+    unsigned char* b = fe->base;
+    VO_CUDA(cudaMemsetAsync(b, 0, off, ctx->stream));
+    fe->pyr[0] = b + o_p0; fe->pyr[1] = b + o_p1; fe->resp = (double*)(b + o_resp);
+    fe->kp = (int32_t*)(b + o_kp); fe->pts_prev = (float*)(b + o_pp); fe->pts_next = (float*)(b + o_pn);
+    fe->err = (float*)(b + o_err); fe->status = b + o_st;
+    fe->models = (double*)(b + o_m); fe->valid = b + o_v; fe->counts = (int32_t*)(b + o_c);
+    fe->best4 = (int32_t*)(b + o_b4); fe->consumed = (int32_t*)(b + o_con); fe->iters_out = (int32_t*)(b + o_it);
+    fe->inliers = b + o_in; fe->pose = (double*)(b + o_pose); fe->tri_out = (double*)(b + o_to);
+    fe->s_landmarks = (double*)(b + o_sl); fe->s_kp2d = (double*)(b + o_sk); fe->s_samples = (int32_t*)(b + o_ss);
+    fe->s_table = (int32_t*)(b + o_stb); fe->s_tri_p1 = (double*)(b + o_t1); fe->s_tri_p2 = (double*)(b + o_t2);
+    fe->s_tri_proj1 = (double*)(b + o_tp1); fe->s_tri_proj2 = (double*)(b + o_tp2);
+    VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = fe;
+    return VO_OK;
+}
+
+void vo_frontend_destroy(vo_frontend* fe) {
+    if (!fe) return;
+    cudaSetDevice(fe->ctx->device);
+    cudaStreamSynchronize(fe->ctx->stream);
+    cudaFree(fe->base);
+    delete fe;
+}
+
+int vo_frontend_outputs(vo_frontend* fe, vo_frontend_outputs_t* o) {
+    VO_REQUIRE(fe && o, "vo_frontend_outputs: null argument");
+    o->d_resp = fe->resp; o->d_kp_xy = fe->kp; o->d_tracked = fe->pts_next; o->d_status = fe->status; o->d_err = fe->err;
+    o->d_best4 = fe->best4; o->d_inliers = fe->inliers; o->d_pose = fe->pose; o->d_tri_out = fe->tri_out;
+    o->d_counts = fe->counts; o->d_cur_pyramid = fe->pyr[fe->cur];
+    o->pyr_pitch0 = fe->pitch0; o->pyr_frame_bytes = fe->frame_bytes;
+    return VO_OK;
+}
+
+// the level-0 slots of the pyramid the NEXT step will fill (so a caller can upload frames in place)
+uint8_t* vo_frontend_next_frame_slot(vo_frontend* fe, size_t* pitch, size_t* frame_stride) {
+    if (!fe) return nullptr;
+    if (pitch) *pitch = fe->pitch0;
+    if (frame_stride) *frame_stride = fe->frame_bytes;
+    return fe->pyr[1 - fe->cur];
+}
+
+int vo_frontend_step_dev(vo_frontend* fe, const uint8_t* d_frames, size_t pitch, size_t frame_stride,
+                         const double* d_landmarks, const double* d_kp2d, const double* K9,
+                         const int32_t* d_sample_idx, const int32_t* d_iters_table, int initial_iters,
+                         const double* d_tri_p1, const double* d_tri_p2, const double* d_tri_proj1,
+                         const double* d_tri_proj2, void* stream) {
+    VO_REQUIRE(fe && d_frames && d_landmarks && d_kp2d && K9 && d_sample_idx && d_iters_table,
+               "vo_frontend_step_dev: null argument");
+    vo_ctx* ctx = fe->ctx;
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const vo_frontend_params& p = fe->p;
+    const int S = p.n_seq;
+    const int nxt = 1 - fe->cur;
+    int rc;
+    // 1. pyramid of the new frames (level 0 copied unless already uploaded into the slot)
+    if ((rc = vo_launch_klt_pyramid(ctx, d_frames, S, p.H, p.W, pitch, frame_stride, p.klt_max_level, p.klt_win,
+                                    fe->pyr[nxt], s))) return rc;
+    // 2. KLT: last frame's keypoints into the new frame (klt.py:233-239)
+    if (fe->steps > 0) {
+        if ((rc = vo_launch_klt_track(ctx, fe->pyr[fe->cur], fe->pyr[nxt], S, p.H, p.W, p.klt_max_level, p.klt_win,
+                                      p.klt_max_iters, p.klt_epsilon, p.klt_min_eig, fe->pts_prev, p.num_keypoints,
+                                      fe->pts_next, fe->status, fe->err, s))) return rc;
+    }
+    // 3. Harris on the new frame (harris.py:86-158); its keypoints seed the next step's tracking
+    if ((rc = vo_launch_harris_response(ctx, fe->pyr[nxt], S, p.H, p.W, fe->pitch0, fe->frame_bytes, p.patch_size,
+                                        p.kappa, fe->resp, s))) return rc;
+    if ((rc = vo_launch_harris_nms(ctx, fe->resp, S, p.H, p.W, p.nms_radius, p.num_keypoints, fe->kp, nullptr, s))) return rc;
+    if ((rc = vo_launch_kp_to_points(ctx, fe->kp, (size_t)S * p.num_keypoints, fe->pts_prev, s))) return rc;
+    // 4. P3P + RANSAC (p3p.py:123-186 with use_opencv=False)
+    if ((rc = vo_launch_p3p_score(ctx, d_landmarks, d_kp2d, S, p.n_corr, K9, d_sample_idx, p.n_hyp, p.p3p_threshold,
+                                  fe->models, fe->valid, fe->counts, s))) return rc;
+    if ((rc = vo_launch_p3p_select(ctx, d_landmarks, d_kp2d, S, p.n_corr, K9, fe->models, fe->valid, fe->counts, p.n_hyp,
+                                   p.p3p_threshold, d_iters_table, initial_iters, 0, -1, fe->best4, fe->consumed,
+                                   fe->iters_out, fe->inliers, fe->pose, s))) return rc;
+    // 5. triangulation of new landmarks (triangulation.py:38-86)
+    if (p.n_tri > 0) {
+        VO_REQUIRE(d_tri_p1 && d_tri_p2 && d_tri_proj1 && d_tri_proj2, "vo_frontend_step_dev: null triangulation input");
+        if ((rc = vo_launch_triangulate(ctx, d_tri_p1, d_tri_p2, S * p.n_tri, d_tri_proj1, 1, d_tri_proj2, p.n_tri,
+                                        p.tri_mode, fe->tri_out, s))) return rc;
+    }
+    fe->cur = nxt;
+    fe->steps++;
+    return VO_OK;
+}
+
+int vo_frontend_step_host(vo_frontend* fe, const uint8_t* h_frames, const double* h_landmarks, const double* h_kp2d,
+                          const double* K9, const int32_t* h_sample_idx, const int32_t* h_iters_table,
+                          int initial_iters, const double* h_tri_p1, const double* h_tri_p2,
+                          const double* h_tri_proj1, const double* h_tri_proj2, int32_t* h_kp_xy, float* h_tracked,
+                          uint8_t* h_status, float* h_err, int32_t* h_best4, uint8_t* h_inliers, double* h_pose,
+                          double* h_tri_out) {
+    VO_REQUIRE(fe && h_frames && h_landmarks && h_kp2d && K9 && h_sample_idx && h_iters_table && h_kp_xy && h_pose,
+               "vo_frontend_step_host: null argument");
+    vo_ctx* ctx = fe->ctx;
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const vo_frontend_params& p = fe->p;
+    const size_t S = p.n_seq, K = p.num_keypoints, N = p.n_corr, Hn = p.n_hyp, T = p.n_tri;
+    uint8_t* slot = fe->pyr[1 - fe->cur];
+    for (size_t f = 0; f < S; f++)   // frames land directly in the level-0 slots (pitched, TMA-legal rows)
+        VO_CUDA(cudaMemcpy2DAsync(slot + f * fe->frame_bytes, fe->pitch0, h_frames + f * (size_t)p.H * p.W, p.W, p.W, p.H,
+                                  cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(fe->s_landmarks, h_landmarks, S * N * 24, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(fe->s_kp2d, h_kp2d, S * N * 16, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(fe->s_samples, h_sample_idx, S * Hn * 16, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(fe->s_table, h_iters_table, (N + 1) * 4, cudaMemcpyHostToDevice, s));
+    if (T > 0) {
+        VO_REQUIRE(h_tri_p1 && h_tri_p2 && h_tri_proj1 && h_tri_proj2 && h_tri_out, "vo_frontend_step_host: null triangulation buffer");
+        VO_CUDA(cudaMemcpyAsync(fe->s_tri_p1, h_tri_p1, S * T * 16, cudaMemcpyHostToDevice, s));
+        VO_CUDA(cudaMemcpyAsync(fe->s_tri_p2, h_tri_p2, S * T * 16, cudaMemcpyHostToDevice, s));
+        VO_CUDA(cudaMemcpyAsync(fe->s_tri_proj1, h_tri_proj1, S * T * 96, cudaMemcpyHostToDevice, s));
+        VO_CUDA(cudaMemcpyAsync(fe->s_tri_proj2, h_tri_proj2, S * 96, cudaMemcpyHostToDevice, s));
+    }
+    const bool had_prev = fe->steps > 0;
+    int rc = vo_frontend_step_dev(fe, slot, fe->pitch0, fe->frame_bytes, fe->s_landmarks, fe->s_kp2d, K9, fe->s_samples,
+                                  fe->s_table, initial_iters, fe->s_tri_p1, fe->s_tri_p2, fe->s_tri_proj1, fe->s_tri_proj2, s);
+    if (rc) return rc;
+    VO_CUDA(cudaMemcpyAsync(h_kp_xy, fe->kp, S * K * 8, cudaMemcpyDeviceToHost, s));
+    if (had_prev && h_tracked) VO_CUDA(cudaMemcpyAsync(h_tracked, fe->pts_next, S * K * 8, cudaMemcpyDeviceToHost, s));
+    if (had_prev && h_status) VO_CUDA(cudaMemcpyAsync(h_status, fe->status, S * K, cudaMemcpyDeviceToHost, s));
+    if (had_prev && h_err) VO_CUDA(cudaMemcpyAsync(h_err, fe->err, S * K * 4, cudaMemcpyDeviceToHost, s));
+    if (h_best4) VO_CUDA(cudaMemcpyAsync(h_best4, fe->best4, S * 16, cudaMemcpyDeviceToHost, s));
+    if (h_inliers) VO_CUDA(cudaMemcpyAsync(h_inliers, fe->inliers, S * N, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_pose, fe->pose, S * 96, cudaMemcpyDeviceToHost, s));
+    if (T > 0) VO_CUDA(cudaMemcpyAsync(h_tri_out, fe->tri_out, S * T * 24, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
+    return VO_OK;
+}
+
+}  // extern "C"

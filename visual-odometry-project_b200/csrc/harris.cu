@@ -452,7 +452,21 @@ __global__ void harris_descriptors_kernel(const uint8_t* __restrict__ img, size_
     }
 }
 
+__global__ void kp_to_points_kernel(const int* __restrict__ kp, size_t n2, float* __restrict__ pts) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n2) pts[i] = (float)kp[i];
+}
+
 }  // namespace
+
+int vo_launch_kp_to_points(vo_ctx* ctx, const int* d_kp_xy, size_t n, float* d_pts, cudaStream_t stream) {
+    if (n == 0) return VO_OK;
+    const size_t n2 = n * 2;
+    kp_to_points_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, stream>>>(d_kp_xy, n2, d_pts);
+    ctx->launches++;
+    VO_CHECK_LAUNCH();
+    return VO_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Host-side launchers (called from the C ABI in abi.cu)

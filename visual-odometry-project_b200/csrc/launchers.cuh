@@ -33,4 +33,7 @@ int vo_launch_p3p_select(vo_ctx* ctx, const double* d_landmarks, const double* d
                          double* d_best_model, cudaStream_t stream);
 // triangulation.cu
 int vo_launch_triangulate(vo_ctx* ctx, const double* d_p1, const double* d_p2, int n, const double* d_proj1,
-                          int proj1_per_point, const double* d_proj2, int mode, double* d_out, cudaStream_t stream);
+                          int proj1_per_point, const double* d_proj2, int proj2_group, int mode, double* d_out,
+                          cudaStream_t stream);
+// harris.cu: int32 (x, y) keypoints -> float32 points (the KLT input format)
+int vo_launch_kp_to_points(vo_ctx* ctx, const int* d_kp_xy, size_t n, float* d_pts, cudaStream_t stream);

@@ -79,14 +79,15 @@ __device__ __forceinline__ void jacobi_null_vector(double (&a)[6][4], double* x)
 
 __global__ void __launch_bounds__(128)
 triangulate_kernel(const double* __restrict__ p1, const double* __restrict__ p2, int n,
-                   const double* __restrict__ proj1, int per_point, const double* __restrict__ proj2, int mode,
-                   double* __restrict__ out) {
+                   const double* __restrict__ proj1, int per_point, const double* __restrict__ proj2, int group,
+                   int mode, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double c1[12], c2[12];
     const double* P1 = proj1 + (per_point ? (size_t)i * 12 : 0);
+    const double* P2 = proj2 + (group > 0 ? (size_t)(i / group) * 12 : 0);  // one end pose per sequence
 #pragma unroll
-    for (int k = 0; k < 12; k++) { c1[k] = P1[k]; c2[k] = proj2[k]; }
+    for (int k = 0; k < 12; k++) { c1[k] = P1[k]; c2[k] = P2[k]; }
     const double x1 = p1[2 * i], y1 = p1[2 * i + 1], x2 = p2[2 * i], y2 = p2[2 * i + 1];
     double a[6][4];
     double x[4];
@@ -121,11 +122,12 @@ triangulate_kernel(const double* __restrict__ p1, const double* __restrict__ p2,
 }  // namespace
 
 int vo_launch_triangulate(vo_ctx* ctx, const double* d_p1, const double* d_p2, int n, const double* d_proj1,
-                          int proj1_per_point, const double* d_proj2, int mode, double* d_out, cudaStream_t stream) {
+                          int proj1_per_point, const double* d_proj2, int proj2_group, int mode, double* d_out,
+                          cudaStream_t stream) {
     VO_REQUIRE(n >= 0 && (mode == 0 || mode == 1), "triangulate: bad n / mode");
     if (n == 0) return VO_OK;
-    triangulate_kernel<<<vo_div_up(n, 128), 128, 0, stream>>>(d_p1, d_p2, n, d_proj1, proj1_per_point, d_proj2, mode,
-                                                               d_out);
+    triangulate_kernel<<<vo_div_up(n, 128), 128, 0, stream>>>(d_p1, d_p2, n, d_proj1, proj1_per_point, d_proj2, proj2_group,
+                                                               mode, d_out);
     ctx->launches++;
     VO_CHECK_LAUNCH();
     return VO_OK;

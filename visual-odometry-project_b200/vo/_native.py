@@ -45,6 +45,7 @@ def lib():
         _sig(L.vo_ctx_launch_count, u64, [vp])
         _sig(L.vo_ctx_synchronize, i32, [vp])
         _sig(L.vo_ctx_stream, vp, [vp])
+        _sig(L.vo_copy_to_host, i32, [vp, vp, vp, sz])
         _sig(L.vo_harris_response_dev, i32, [vp, vp, i32, i32, i32, sz, sz, i32, dbl, vp, vp])
         _sig(L.vo_harris_nms_dev, i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, vp])
         _sig(L.vo_harris_detect_dev, i32, [vp, vp, i32, i32, i32, sz, sz, i32, dbl, i32, i32, vp, vp, vp])
@@ -63,6 +64,15 @@ def lib():
             "vo_triangulate_dev": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp, vp]),
             "vo_triangulate_host": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp]),
         }
+        _optional.update({
+            "vo_frontend_create": (i32, [vp, vp, C.POINTER(vp)]),
+            "vo_frontend_destroy": (None, [vp]),
+            "vo_frontend_outputs": (i32, [vp, vp]),
+            "vo_frontend_next_frame_slot": (vp, [vp, C.POINTER(sz), C.POINTER(sz)]),
+            "vo_frontend_step_dev": (i32, [vp, vp, sz, sz, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+            "vo_frontend_step_host": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp,
+                                            vp, vp, vp, vp, vp, vp, vp, vp]),
+        })
         for name, (rt, at) in _optional.items():
             if hasattr(L, name):  # all are present in a complete build; tests/test_abi.py checks that
                 _sig(getattr(L, name), rt, at)
@@ -97,6 +107,11 @@ class Context:
     def stream(self) -> int:
         return int(lib().vo_ctx_stream(self._h) or 0)
 
+    def copy_to_host(self, dst: np.ndarray, d_src: int) -> np.ndarray:
+        """Synchronous D2H copy of a resident result buffer into a contiguous numpy array."""
+        check(lib().vo_copy_to_host(self._h, ptr(dst), C.c_void_p(d_src), dst.nbytes), "vo_copy_to_host")
+        return dst
+
     def close(self):
         if self._h:
             lib().vo_ctx_destroy(self._h)
@@ -121,3 +136,21 @@ def default_context(device: int = 0) -> Context:
 
 def ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class FrontendParams(C.Structure):
+    """vo_frontend_params of include/vo_b200.h."""
+    _fields_ = [("n_seq", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("patch_size", C.c_int), ("kappa", C.c_double), ("nms_radius", C.c_int), ("num_keypoints", C.c_int),
+                ("klt_win", C.c_int), ("klt_max_level", C.c_int), ("klt_max_iters", C.c_int),
+                ("klt_epsilon", C.c_double), ("klt_min_eig", C.c_double),
+                ("n_corr", C.c_int), ("n_hyp", C.c_int), ("p3p_threshold", C.c_double),
+                ("n_tri", C.c_int), ("tri_mode", C.c_int)]
+
+
+class FrontendOutputs(C.Structure):
+    """vo_frontend_outputs_t of include/vo_b200.h (device pointers)."""
+    _fields_ = [("d_resp", C.c_void_p), ("d_kp_xy", C.c_void_p), ("d_tracked", C.c_void_p), ("d_status", C.c_void_p),
+                ("d_err", C.c_void_p), ("d_best4", C.c_void_p), ("d_inliers", C.c_void_p), ("d_pose", C.c_void_p),
+                ("d_tri_out", C.c_void_p), ("d_counts", C.c_void_p), ("d_cur_pyramid", C.c_void_p),
+                ("pyr_pitch0", C.c_size_t), ("pyr_frame_bytes", C.c_size_t)]
