@@ -273,7 +273,10 @@ def main():
     hostbuf["table"] = torch.from_numpy(table_h).pin_memory()
     devbuf = {k: v.to(dev) for k, v in hostbuf.items()}
     fe = Frontend(S, H, W, num_keypoints=KP, n_corr=N, n_hyp=Hn, p3p_threshold=P3P_THR, n_tri=T, tri_mode=1, ctx=ctx)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(device=dev)          # explicit stream: kernels and timing events share it
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step_dev(i):
         fr = pool_d[i % P]
@@ -303,10 +306,10 @@ def main():
         sampler.start()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    e0.record(tstream)
     for i in range(args.steps):
         step_dev(warmup + i)
-    e1.record()
+    e1.record(tstream)
     barrier()
     launches = ctx.launch_count() - l0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
@@ -335,10 +338,10 @@ def main():
         harris_only(i)
     torch.cuda.synchronize()
     n_rf = 20
-    e0.record()
+    e0.record(tstream)
     for i in range(n_rf):
         harris_only(3 + i)
-    e1.record()
+    e1.record(tstream)
     torch.cuda.synchronize()
     harris_ms = e0.elapsed_time(e1) / n_rf
     algo_bytes = S * H * W * (1 + 8)                 # uint8 pixel in, float64 score out

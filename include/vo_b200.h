@@ -63,6 +63,10 @@ int vo_harris_detect_host(vo_ctx* ctx, const uint8_t* h_img, int n_frames, int H
                           double kappa, int nms_radius, int num_keypoints, int desc_radius, double* h_resp,
                           int32_t* h_kp_xy, uint8_t* h_desc);
 
+/* harris.py:160-194 alone, host buffers: one tightly packed frame, int32 (x, y) keypoints [K][2].  */
+int vo_harris_descriptors_host(vo_ctx* ctx, const uint8_t* h_img, int H, int W, const int32_t* h_kp_xy, int K,
+                               int desc_radius, uint8_t* h_desc);
+
 /* ---- KLT: src/vo/features/klt.py:233-239 (cv2.calcOpticalFlowPyrLK) ------------------------- */
 /* Gaussian 5x5 pyramid (cv2.pyrDown, BORDER_REFLECT_101) of a batch of frames, frame-major: level l
  * of frame f lives at d_pyr + f * frame_bytes + level_offset[l] with row pitch level_pitch[l]

@@ -201,12 +201,61 @@ def make_triangulation():
     print("triangulation.npz", {k: np.shape(v) for k, v in out.items()})
 
 
+def make_bookkeeping():
+    """Matches / State bookkeeping of the reference on a mixed-state feature table."""
+    from vo.primitives import Features, Frame, Matches, State
+    from vo.sensors import Camera
+
+    rng = np.random.default_rng(11)
+    n1, n2 = 40, 36
+    kp1 = rng.uniform(0, 300, (n1, 2, 1))
+    kp2 = rng.uniform(0, 300, (n2, 2, 1))
+    f1 = Features(kp1.copy())
+    st = rng.integers(0, 3, n1).astype(float)
+    f1.state = st.copy()
+    lm = np.full((n1, 3, 1), np.nan)
+    lm[st == 2] = rng.uniform(-3, 3, (int((st == 2).sum()), 3, 1)) + np.array([[0], [0], [12.0]])
+    f1.landmarks = lm.copy()
+    tr = kp1.copy()
+    tr[st == 1] += rng.normal(0, 3, (int((st == 1).sum()), 2, 1))
+    f1.tracks = tr.copy()
+    poses = np.stack([np.eye(4)] * n1)
+    poses[:, :3, 3] = rng.normal(0, 0.1, (n1, 3))
+    f1.poses = poses.copy()
+    f1.descriptors = rng.integers(0, 255, (n1, 5)).astype(float)
+    f2 = Features(kp2.copy())
+    f2.descriptors = rng.integers(0, 255, (n2, 5)).astype(float)
+    m = np.stack([rng.permutation(n1)[:25], rng.permutation(n2)[:25]], 1)
+    out = dict(kp1=kp1, kp2=kp2, state1=st, land1=lm, tracks1=tr, poses1=poses, desc1=f1.descriptors.copy(),
+               desc2=f2.descriptors.copy(), matches=m)
+    K = np.array([[500, 0, 150], [0, 500, 150], [0, 0, 1.0]])
+    fr1, fr2 = Frame(None, features=f1, sensor=Camera(K)), Frame(None, features=f2, sensor=Camera(K))
+    mt = Matches(fr1, fr2, m)
+    for tag, f in (("a", mt.frame1.features), ("b", mt.frame2.features)):
+        out.update({f"{tag}_kp": f.keypoints.copy(), f"{tag}_state": f.state.copy(), f"{tag}_land": f.landmarks.copy(),
+                    f"{tag}_tracks": f.tracks.copy(), f"{tag}_poses": f.poses.copy(), f"{tag}_desc": f.descriptors.copy()})
+    state = State(fr1)
+    state.update_from_matches(mt)
+    pose_w2c = np.eye(4)
+    pose_w2c[:3, 3] = [0.3, -0.1, 0.2]
+    state.update_with_world_pose(pose_w2c[:3])
+    outl = np.zeros(mt.frame2.features.length, dtype=bool)
+    outl[::7] = True
+    state.reset_outliers(outl)
+    state.compute_candidates()
+    f = state.curr_frame.features
+    out.update(dict(s_pose=state.get_pose(), s_state=f.state, s_tracks=f.tracks, s_poses=f.poses, s_cand=f.candidate_mask,
+                    s_outliers=outl, s_pose_in=pose_w2c[:3]))
+    np.savez_compressed(os.path.join(OUT, "bookkeeping.npz"), **out)
+    print("bookkeeping.npz", {k: np.shape(v) for k, v in out.items()})
+
+
 def to_pixels(K, M, X):
     x = K @ (M[:, :3] @ X + M[:, 3:])
     return x[:2] / x[2:]
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["harris", "klt", "p3p", "triangulation"]
+    which = sys.argv[1:] or ["harris", "klt", "p3p", "triangulation", "bookkeeping"]
     for w in which:
         globals()["make_" + w]()

@@ -168,6 +168,27 @@ int vo_harris_detect_host(vo_ctx* ctx, const uint8_t* h_img, int n_frames, int H
     return VO_OK;
 }
 
+int vo_harris_descriptors_host(vo_ctx* ctx, const uint8_t* h_img, int H, int W, const int32_t* h_kp_xy, int K,
+                               int desc_radius, uint8_t* h_desc) {
+    VO_REQUIRE(ctx && h_img && h_kp_xy && h_desc && H > 0 && W > 0 && K >= 1, "vo_harris_descriptors_host: bad argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t pitch = ((size_t)W + 15) & ~(size_t)15;
+    const int d = 2 * desc_radius + 1;
+    const size_t db = (size_t)K * d * d;
+    int rc;
+    if ((rc = vo_buf_reserve(&ctx->scratch[1], pitch * H))) return rc;
+    if ((rc = vo_buf_reserve(&ctx->scratch[3], (size_t)K * 2 * sizeof(int32_t)))) return rc;
+    if ((rc = vo_buf_reserve(&ctx->scratch[4], db))) return rc;
+    VO_CUDA(cudaMemcpy2DAsync(ctx->scratch[1].p, pitch, h_img, W, W, H, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(ctx->scratch[3].p, h_kp_xy, (size_t)K * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if ((rc = vo_harris_descriptors_dev(ctx, (uint8_t*)ctx->scratch[1].p, 1, H, W, pitch, pitch * H,
+                                        (int32_t*)ctx->scratch[3].p, K, desc_radius, (uint8_t*)ctx->scratch[4].p, s))) return rc;
+    VO_CUDA(cudaMemcpyAsync(h_desc, ctx->scratch[4].p, db, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
+    return VO_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // KLT
 // ------------------------------------------------------------------------------------------

@@ -51,6 +51,7 @@ def lib():
         _sig(L.vo_harris_detect_dev, i32, [vp, vp, i32, i32, i32, sz, sz, i32, dbl, i32, i32, vp, vp, vp])
         _sig(L.vo_harris_descriptors_dev, i32, [vp, vp, i32, i32, i32, sz, sz, vp, i32, i32, vp, vp])
         _sig(L.vo_harris_detect_host, i32, [vp, vp, i32, i32, i32, i32, dbl, i32, i32, i32, vp, vp, vp])
+        _sig(L.vo_harris_descriptors_host, i32, [vp, vp, i32, i32, vp, i32, i32, vp])
         _optional = {
             "vo_klt_pyramid_layout": (i32, [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
             "vo_klt_build_pyramid_dev": (i32, [vp, vp, i32, i32, i32, sz, sz, i32, i32, vp, vp]),

@@ -97,7 +97,9 @@ def p3p_ransac(landmarks, keypoints, K, sample_idx, threshold, iters_for_count, 
     S = np.ascontiguousarray(np.asarray(sample_idx, dtype=np.int32).reshape(F, -1, 4))
     Hn = S.shape[1]
     K9 = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
-    table = np.ascontiguousarray(np.asarray(iters_for_count, dtype=np.int32).reshape(-1))
+    i32max = np.iinfo(np.int32).max
+    table = np.ascontiguousarray(np.minimum(np.asarray(iters_for_count).reshape(-1), i32max).astype(np.int32))
+    initial_iters = int(min(initial_iters, i32max))
     if table.shape[0] != N + 1:
         raise ValueError("p3p_ransac: iters_for_count must have N + 1 entries")
     best4 = np.zeros((F, 4), dtype=np.int32)
@@ -145,4 +147,20 @@ def triangulate(p1, p2, C1, C2, mode=0, ctx=None):
     rc = nat.lib().vo_triangulate_host(ctx.handle, nat.ptr(a), nat.ptr(b), n, nat.ptr(c1), per_point, nat.ptr(c2),
                                        int(mode), nat.ptr(out))
     nat.check(rc, "vo_triangulate_host")
+    return out
+
+
+def harris_descriptors(img, kp_xy, desc_radius=9, ctx=None):
+    """extractDescriptors alone (harris.py:160-194): uint8 (K, (2r+1)^2) patches for given keypoints."""
+    ctx = _ctx(ctx)
+    a = np.ascontiguousarray(img, dtype=np.uint8)
+    kp = np.ascontiguousarray(kp_xy, dtype=np.int32).reshape(-1, 2)
+    H, W = a.shape
+    d = 2 * int(desc_radius) + 1
+    out = np.empty((kp.shape[0], d * d), dtype=np.uint8)
+    if kp.shape[0] == 0:
+        return out
+    rc = nat.lib().vo_harris_descriptors_host(ctx.handle, nat.ptr(a), H, W, nat.ptr(kp), kp.shape[0], int(desc_radius),
+                                              nat.ptr(out))
+    nat.check(rc, "vo_harris_descriptors_host")
     return out

@@ -1,0 +1,99 @@
+"""P3P pose estimation (reference: src/vo/pose_estimation/p3p.py).
+
+estimate_pose runs the P3P minimal solver and the reprojection inlier count for whole batches of
+RANSAC hypotheses on the GPU (vo_p3p_ransac_* in include/vo_b200.h) and replays the reference's
+sequential, adaptive RANSAC loop over them, so the rng stream, the iteration count, the winning
+model and the inlier mask are those of the reference's `use_opencv=False` path.  With
+`use_opencv=True` the reference hands the whole problem to cv2.solvePnPRansac (its own RNG); here
+that flag only switches the inlier rule to OpenCV's (squared error <= reprojectionError^2)."""
+import numpy as np
+from scipy.optimize import least_squares
+
+from vo import _ops
+from vo.algorithms import RANSAC
+from vo.helpers import H_matrix_to_twist, twist_to_H_matrix
+
+__all__ = ["P3PPoseEstimator"]
+
+
+class P3PPoseEstimator:
+    FIRST_BATCH = 256      # hypotheses scored speculatively per GPU call
+    NEXT_BATCH = 2048
+
+    def __init__(self, intrinsic_matrix: np.ndarray, inlier_threshold: float, use_opencv: bool = True,
+                 outlier_ratio: float = 0.9, confidence: float = 0.99, max_iterations: int = 10000,
+                 nonlinear_refinement: bool = True) -> None:
+        self._use_opencv = use_opencv
+        self.intrinsic_matrix = intrinsic_matrix
+        self.inlier_threshold = inlier_threshold
+        self.outlier_ratio = outlier_ratio
+        self.confidence = confidence
+        self.max_iterations = max_iterations
+        self.nonlinear_refinement = nonlinear_refinement
+        # Same object the reference builds (p3p.py:110-121); its callables are never invoked here,
+        # the GPU evaluates model_fn / error_fn for whole batches of samples.
+        self.ransac = RANSAC(s_points=4, population=None, model_fn=None, error_fn=None,
+                             inlier_threshold=self.inlier_threshold, outlier_ratio=self.outlier_ratio,
+                             confidence=self.confidence, max_iterations=self.max_iterations, p3p=True)
+
+    def estimate_pose(self, features):
+        """((R 3x3, t 3x1) mapping world points into the camera, boolean inlier mask)  (p3p.py:123-186)."""
+        points_3d, points_2d = features.landmarks, features.keypoints
+        assert points_3d.shape[1] == 3 and points_2d.shape[1] == 2, "Invalid shape."
+        assert points_3d is not None and points_2d is not None, "3D landmarks and 2D keypoints must be provided."
+        model, inliers = self._gpu_ransac(points_3d, points_2d)
+        if self._use_opencv:
+            assert model is not None, "OpenCV P3P failed"                       # p3p.py:153
+        if model is not None and self.nonlinear_refinement:
+            model = self._nonlinear_refinement(points_3d[inliers], points_2d[inliers], model)
+        return model, inliers
+
+    def _gpu_ransac(self, points_3d, points_2d):
+        rs = self.ransac
+        N = points_3d.shape[0]
+        table = rs.iterations_table(N)
+        thr = self.inlier_threshold ** 2 if self._use_opencv else self.inlier_threshold
+        n, best_count, best = 0, -1, None
+        batch = self.FIRST_BATCH
+        while n < rs.n_iterations:
+            state0 = rs.rng.bit_generator.state
+            want = int(min(batch, max(1, rs.n_iterations - n)))
+            samples = np.stack([rs.draw(N) for _ in range(want)]).astype(np.int32)
+            r = _ops.p3p_ransac(points_3d, points_2d, self.intrinsic_matrix, samples, thr, table,
+                                rs.n_iterations, start_n=n, start_best=best_count)
+            n, consumed = int(r["n"]), int(r["consumed"])
+            if int(r["best"]) >= 0:
+                best_count = int(r["best_count"])
+                best = ((r["R"].copy(), r["t"].copy()), r["inliers"].copy())
+                # ransac.py:113-120 (adaptive update after an improvement)
+                rs.outlier_ratio = min(max(1 - np.int64(best_count) / N, 0.01), 0.99)
+                rs.n_iterations = int(r["n_iterations"])
+            if consumed < want:
+                # the loop stopped inside this batch: put the rng where the reference's would be
+                rs.rng.bit_generator.state = state0
+                for _ in range(consumed):
+                    rs.draw(N)
+                break
+            batch = self.NEXT_BATCH
+        if best is None:
+            return None, None
+        return best
+
+    def _nonlinear_refinement(self, points_3d, points_2d, best_model):
+        """Minimise the reprojection residuals over the 6-dof twist (p3p.py:188-213); host side,
+        scipy.optimize.least_squares as in the reference."""
+        K = np.asarray(self.intrinsic_matrix, dtype=np.float64)
+        P3 = np.asarray(points_3d, dtype=np.float64).reshape(-1, 3)
+        P2 = np.asarray(points_2d, dtype=np.float64).reshape(-1, 2)
+        H = np.eye(4)
+        H[:3, :3] = best_model[0]
+        H[:3, 3] = np.asarray(best_model[1]).squeeze()
+
+        def residuals(twist):
+            Hg = twist_to_H_matrix(twist)
+            cam = P3 @ Hg[:3, :3].T + Hg[:3, 3]
+            uv = cam @ K.T
+            return np.linalg.norm(P2 - uv[:, :2] / uv[:, 2:], axis=1)
+
+        Hg = twist_to_H_matrix(least_squares(residuals, x0=H_matrix_to_twist(H)).x)
+        return Hg[:3, :3], Hg[:3, 3:]
