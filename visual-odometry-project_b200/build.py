@@ -33,7 +33,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources() + ["-lcuda"]
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()   # the driver API (TMA descriptors) is resolved at run time
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(HERE, "build.log")
     with open(log, "w") as f:

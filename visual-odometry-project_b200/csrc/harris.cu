@@ -15,6 +15,8 @@
 // by (1) a dense local-maximum pass, (2) a per-frame threshold = K-th best local maximum (nothing
 // below it can be among the first K picks), (3) iterated local-maximum rounds over the still-alive
 // pixels above the threshold, (4) a final select + sort of the K best picks.
+#include <cuda.h>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -39,7 +41,7 @@ __device__ __forceinline__ double harris_score(int a, int b, int c, double kappa
 __global__ void __launch_bounds__(R_THREADS)
 harris_response_tiled(const uint8_t* __restrict__ img, size_t pitch, size_t frame_stride,
                       int H, int W, int pr, double kappa, double* __restrict__ resp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int pad = pr + 1;
     const int in_w = RT_W + 2 * pad, in_h = RT_H + 2 * pad;
     const int pw = RT_W + 2 * pr, ph = RT_H + 2 * pr;  // product region
@@ -126,6 +128,132 @@ harris_response_tiled(const uint8_t* __restrict__ img, size_t pitch, size_t fram
 }
 
 // ---------------------------------------------------------------------------------------------
+// Response kernel v2 (patch_size 9, TMA-legal image layout): 128x54 output tile per CTA.
+//   load   : one thread issues a 3-D TMA tile load (144 x 64 x 1 bytes, zero fill outside the image)
+//   phase H: thread = (product row, 32-column segment).  The 3 image rows it needs are pulled with
+//            conflict-free 128-bit shared loads into registers; it marches 42 columns, fully
+//            unrolled: Sobel -> 3 products -> sliding 9-sums with a register ring -> H[row][x].
+//   phase V: thread = (column, half tile).  Sliding vertical 9-sums over H with a register ring,
+//            float64 score, coalesced 8-byte stores (a warp writes 256 contiguous bytes).
+// Shared memory: 9.2 KB image + 3 x 62 x 129 x 4 B H-sums (row pitch 129 words: the row-per-lane
+// stores of phase H and the column-per-lane loads of phase V are both bank-conflict free).
+// ---------------------------------------------------------------------------------------------
+constexpr int FT_W = 128, FT_H = 54, FT_ROWS = FT_H + 8;   // 62 product rows
+constexpr int FT_IN_W = 144, FT_IN_H = 64;                 // TMA box
+constexpr int FT_HP = 129;                                 // H row pitch (words)
+constexpr int FT_THREADS = 256;
+constexpr int FT_IMG_BYTES = FT_IN_W * FT_IN_H;            // 9216
+constexpr int FT_SMEM = FT_IMG_BYTES + 3 * FT_ROWS * FT_HP * 4 + 16;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(FT_THREADS, 2)
+harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, double kappa, double* __restrict__ resp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint8_t* img = smem_raw;
+    int* hxx = reinterpret_cast<int*>(smem_raw + FT_IMG_BYTES);
+    int* hyy = hxx + FT_ROWS * FT_HP;
+    int* hxy = hyy + FT_ROWS * FT_HP;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + FT_IMG_BYTES + 3 * FT_ROWS * FT_HP * 4);
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H, f = blockIdx.z;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(FT_IMG_BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smem_u32(img)), "l"(&tmap), "r"(x0 - 5), "r"(y0 - 5), "r"(f), "r"(smem_u32(mbar)) : "memory");
+    }
+    {   // all threads wait for the tile
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(mbar)), "r"(0) : "memory");
+        }
+    }
+    // ---------------- phase H ----------------
+    {
+        const int g = tid >> 6, r = tid & 63;
+        if (r < FT_ROWS) {
+            uint32_t w[3][12];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const uint4* src = reinterpret_cast<const uint4*>(img + (r + k) * FT_IN_W + 32 * g);
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const uint4 v = src[q];
+                    w[k][4 * q] = v.x; w[k][4 * q + 1] = v.y; w[k][4 * q + 2] = v.z; w[k][4 * q + 3] = v.w;
+                }
+            }
+            int ring_xx[9], ring_yy[9], ring_xy[9];
+            int sxx = 0, syy = 0, sxy = 0;
+            int sv1 = 0, sv2 = 0, dv1 = 0, dv2 = 0;   // columns c-1, c-2
+            int* oxx = hxx + r * FT_HP + 32 * g;
+            int* oyy = hyy + r * FT_HP + 32 * g;
+            int* oxy = hxy + r * FT_HP + 32 * g;
+#pragma unroll
+            for (int c = 0; c < 42; c++) {
+                const int a = (int)__byte_perm(w[0][c >> 2], 0u, 0x4440u + (c & 3));
+                const int b = (int)__byte_perm(w[1][c >> 2], 0u, 0x4440u + (c & 3));
+                const int d = (int)__byte_perm(w[2][c >> 2], 0u, 0x4440u + (c & 3));
+                const int sv0 = a + 2 * b + d;
+                const int dv0 = a - d;
+                if (c >= 2) {
+                    const int m = c - 2;
+                    const int gx = sv2 - sv0;                 // left - right (sign cancels in the products)
+                    const int gy = dv2 + 2 * dv1 + dv0;       // top - bottom
+                    const int pxx = gx * gx, pyy = gy * gy, pxy = gx * gy;
+                    if (m >= 9) {
+                        sxx += pxx - ring_xx[m % 9]; syy += pyy - ring_yy[m % 9]; sxy += pxy - ring_xy[m % 9];
+                    } else {
+                        sxx += pxx; syy += pyy; sxy += pxy;
+                    }
+                    ring_xx[m % 9] = pxx; ring_yy[m % 9] = pyy; ring_xy[m % 9] = pxy;
+                    if (m >= 8) { oxx[m - 8] = sxx; oyy[m - 8] = syy; oxy[m - 8] = sxy; }
+                }
+                sv2 = sv1; sv1 = sv0; dv2 = dv1; dv1 = dv0;
+            }
+        }
+    }
+    __syncthreads();
+    // ---------------- phase V ----------------
+    {
+        const int col = tid & 127, half = tid >> 7;
+        const int base = 27 * half;
+        const int gx = x0 + col;
+        int rxx[9], ryy[9], rxy[9];
+        int vxx = 0, vyy = 0, vxy = 0;
+#pragma unroll
+        for (int k = 0; k < 9; k++) {
+            rxx[k] = hxx[(base + k) * FT_HP + col]; ryy[k] = hyy[(base + k) * FT_HP + col]; rxy[k] = hxy[(base + k) * FT_HP + col];
+            vxx += rxx[k]; vyy += ryy[k]; vxy += rxy[k];
+        }
+        const bool x_in = gx < W, x_interior = gx >= 5 && gx < W - 5;
+        double* dst = resp + (size_t)f * H * W + gx;
+#pragma unroll
+        for (int i = 0; i < 27; i++) {
+            const int gy = y0 + base + i;
+            if (x_in && gy < H) {
+                double s = 0.0;
+                if (x_interior && gy >= 5 && gy < H - 5) s = harris_score(vxx, vyy, vxy, kappa);
+                dst[(size_t)gy * W] = s;
+            }
+            if (i < 26) {
+                const int nxx = hxx[(base + i + 9) * FT_HP + col], nyy = hyy[(base + i + 9) * FT_HP + col],
+                          nxy = hxy[(base + i + 9) * FT_HP + col];
+                vxx += nxx - rxx[i % 9]; vyy += nyy - ryy[i % 9]; vxy += nxy - rxy[i % 9];
+                rxx[i % 9] = nxx; ryy[i % 9] = nyy; rxy[i % 9] = nxy;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // NMS step 1: dense local-maximum detection (window radius r, raster-order tie break).
 // ---------------------------------------------------------------------------------------------
 constexpr int LT_W = 64, LT_H = 16, L_THREADS = 256;
@@ -134,7 +262,7 @@ __global__ void __launch_bounds__(L_THREADS)
 harris_localmax(const double* __restrict__ resp, int H, int W, int r, unsigned int lm_cap,
                 unsigned long long* __restrict__ lm_key, unsigned int* __restrict__ lm_idx,
                 unsigned int* __restrict__ lm_count) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     double* tile = reinterpret_cast<double*>(smem_raw);
     const int tw = LT_W + 2 * r, th = LT_H + 2 * r;
     const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;
@@ -269,7 +397,7 @@ __device__ __forceinline__ void mark_window(unsigned char* st, int H, int W, int
 
 __global__ void __launch_bounds__(N_THREADS)
 harris_nms_frame(NmsArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_misc[4];
     __shared__ unsigned int s_cnt[4];  // 0: alive count, 1: picks count, 2: new picks, 3: next alive
@@ -471,6 +599,24 @@ int vo_launch_kp_to_points(vo_ctx* ctx, const int* d_kp_xy, size_t n, float* d_p
 // ---------------------------------------------------------------------------------------------
 // Host-side launchers (called from the C ABI in abi.cu)
 // ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled tmap_encoder() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tmapEncodeTiled)p;
+    }
+    return fn;
+}
+
 int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
                               size_t frame_stride, int patch_size, double kappa, double* d_resp,
                               cudaStream_t stream) {
@@ -479,6 +625,32 @@ int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, i
     const int pr = patch_size / 2, pad = pr + 1;
     VO_REQUIRE(H >= 2 * pad + 1 && W >= 2 * pad + 1, "harris: image %dx%d too small for patch_size %d", W, H, patch_size);
     VO_REQUIRE(n_frames >= 1 && pitch >= (size_t)W, "harris: bad n_frames/pitch");
+    // fast path: 9x9 patch, 16-byte aligned base / pitch / frame stride (what TMA requires)
+    const bool tma_ok = patch_size == 9 && ((uintptr_t)d_img % 16 == 0) && pitch % 16 == 0 &&
+                        (frame_stride % 16 == 0 || n_frames == 1) && n_frames <= 65535 && tmap_encoder() != nullptr &&
+                        !getenv("VO_HARRIS_NO_TMA");
+    if (tma_ok) {
+        CUtensorMap tmap;
+        const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_frames};
+        const cuuint64_t gstr[2] = {(cuuint64_t)pitch, (cuuint64_t)(n_frames == 1 ? pitch * H : frame_stride)};
+        const cuuint32_t box[3] = {FT_IN_W, FT_IN_H, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = tmap_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)d_img, gdim, gstr, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) {
+            static bool attr_fast = false;
+            if (!attr_fast) {
+                VO_CUDA(cudaFuncSetAttribute(harris_response_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+                attr_fast = true;
+            }
+            dim3 grid(vo_div_up(W, FT_W), vo_div_up(H, FT_H), n_frames);
+            harris_response_fast<<<grid, FT_THREADS, FT_SMEM, stream>>>(tmap, H, W, kappa, d_resp);
+            ctx->launches++;
+            VO_CHECK_LAUNCH();
+            return VO_OK;
+        }
+    }
     const int pw = RT_W + 2 * pr, ph = RT_H + 2 * pr;
     const size_t smem = (size_t)3 * ph * pw * 4 + (size_t)3 * ph * RT_W * 4 + (size_t)(RT_W + 2 * pad) * (RT_H + 2 * pad);
     static bool attr_set = false;
