@@ -142,6 +142,7 @@ constexpr int FT_W = 128, FT_H = 54, FT_ROWS = FT_H + 8;   // 62 product rows
 constexpr int FT_IN_W = 144, FT_IN_H = 64;                 // TMA box
 constexpr int FT_HP = 129;                                 // H row pitch (words)
 constexpr int FT_THREADS = 256;
+constexpr int FT_XSHIFT = 11;                              // (x0 - 5) % 16 == 0
 constexpr int FT_IMG_BYTES = FT_IN_W * FT_IN_H;            // 9216
 constexpr int FT_SMEM = FT_IMG_BYTES + 3 * FT_ROWS * FT_HP * 4 + 16;
 
@@ -156,7 +157,9 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
     int* hxy = hyy + FT_ROWS * FT_HP;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + FT_IMG_BYTES + 3 * FT_ROWS * FT_HP * 4);
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * FT_W, y0 = blockIdx.y * FT_H, f = blockIdx.z;
+    // Tiles start 11 columns left of a multiple of 128 so that the TMA box (which begins 5 columns
+    // further left) starts on a 16-byte boundary, as cp.async.bulk.tensor requires for 1-byte elements.
+    const int x0 = blockIdx.x * FT_W - FT_XSHIFT, y0 = blockIdx.y * FT_H, f = blockIdx.z;
 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
@@ -233,7 +236,7 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
             rxx[k] = hxx[(base + k) * FT_HP + col]; ryy[k] = hyy[(base + k) * FT_HP + col]; rxy[k] = hxy[(base + k) * FT_HP + col];
             vxx += rxx[k]; vyy += ryy[k]; vxy += rxy[k];
         }
-        const bool x_in = gx < W, x_interior = gx >= 5 && gx < W - 5;
+        const bool x_in = gx >= 0 && gx < W, x_interior = gx >= 5 && gx < W - 5;
         double* dst = resp + (size_t)f * H * W + gx;
 #pragma unroll
         for (int i = 0; i < 27; i++) {
@@ -644,7 +647,7 @@ int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, i
                 VO_CUDA(cudaFuncSetAttribute(harris_response_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
                 attr_fast = true;
             }
-            dim3 grid(vo_div_up(W, FT_W), vo_div_up(H, FT_H), n_frames);
+            dim3 grid(vo_div_up(W + FT_XSHIFT, FT_W), vo_div_up(H, FT_H), n_frames);
             harris_response_fast<<<grid, FT_THREADS, FT_SMEM, stream>>>(tmap, H, W, kappa, d_resp);
             ctx->launches++;
             VO_CHECK_LAUNCH();
