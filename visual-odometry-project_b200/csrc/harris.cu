@@ -236,16 +236,34 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
             rxx[k] = hxx[(base + k) * FT_HP + col]; ryy[k] = hyy[(base + k) * FT_HP + col]; rxy[k] = hxy[(base + k) * FT_HP + col];
             vxx += rxx[k]; vyy += ryy[k]; vxy += rxy[k];
         }
+        // Branch-free emission (one straight-line block, so the scheduler can overlap the float64 chains of
+        // neighbouring rows): the score is always evaluated; a single predicate folds the clamp (s > 0)
+        // with "inside the zero border"; the store itself is predicated on the row being in the image.
         const bool x_in = gx >= 0 && gx < W, x_interior = gx >= 5 && gx < W - 5;
-        double* dst = resp + (size_t)f * H * W + gx;
+        const int gy0 = y0 + base;
+        const int n_rows = x_in ? min(27, H - gy0) : 0;            // rows this thread may store
+        const int i_lo = 5 - gy0;                                  // interior rows: i_lo <= i < i_lo + i_span
+        const unsigned i_span = x_interior ? (unsigned)max(H - 10, 0) : 0u;
+        const size_t row_bytes = (size_t)W * sizeof(double);
+        char* dst = reinterpret_cast<char*>(resp + ((size_t)f * H + (size_t)max(gy0, 0)) * W + max(gx, 0));
 #pragma unroll
         for (int i = 0; i < 27; i++) {
-            const int gy = y0 + base + i;
-            if (x_in && gy < H) {
-                double s = 0.0;
-                if (x_interior && gy >= 5 && gy < H - 5) s = harris_score(vxx, vyy, vxy, kappa);
-                dst[(size_t)gy * W] = s;
-            }
+            const double sa = (double)vxx, sb = (double)vyy, sc = (double)vxy;
+            const double trace = __dadd_rn(sa, sb);
+            const double det = __dsub_rn(__dmul_rn(sa, sb), __dmul_rn(sc, sc));
+            const double sraw = __dsub_rn(det, __dmul_rn(kappa, __dmul_rn(trace, trace)));
+            // one predicate: inside the zero border (harris.py:129-137) AND s > 0 (harris.py:127); then a
+            // store predicated on the row being inside the image.  PTX keeps this at DSETP+ISETP+2 FSEL.
+            asm volatile(
+                "{\n\t.reg .pred p, q, r;\n\t.reg .f64 v;\n\t"
+                "setp.gt.f64 p, %1, 0d0000000000000000;\n\t"
+                "setp.lt.u32 q, %2, %3;\n\t"
+                "and.pred p, p, q;\n\t"
+                "selp.f64 v, %1, 0d0000000000000000, p;\n\t"
+                "setp.lt.s32 r, %4, %5;\n\t"
+                "@r st.global.f64 [%0], v;\n\t}"
+                ::"l"(dst), "d"(sraw), "r"((unsigned)(i - i_lo)), "r"(i_span), "r"(i), "r"(n_rows) : "memory");
+            dst += row_bytes;
             if (i < 26) {
                 const int nxx = hxx[(base + i + 9) * FT_HP + col], nyy = hyy[(base + i + 9) * FT_HP + col],
                           nxy = hxy[(base + i + 9) * FT_HP + col];
