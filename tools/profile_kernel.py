@@ -32,7 +32,18 @@ torch.cuda.set_stream(st)
 stream = st.cuda_stream
 resp = torch.empty((S, H, W), dtype=torch.float64, device=dev)
 kp = torch.empty((S, 1000, 2), dtype=torch.int32, device=dev)
-if what in ("harris", "nms"):
+if what == "harris_time":
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(2):
+        e0.record(st)
+        for i in range(20):
+            fr = pool[i % P]
+            nat.check(L.vo_harris_response_dev(ctx.handle, fr.data_ptr(), S, H, W, pitch, H * pitch, 9, C.c_double(0.09),
+                                               resp.data_ptr(), stream), "resp")
+        e1.record(st)
+        torch.cuda.synchronize()
+    print("harris_response ms/launch: %.4f" % (e0.elapsed_time(e1) / 20))
+elif what in ("harris", "nms"):
     for i in range(5):
         fr = pool[i % P]
         nat.check(L.vo_harris_response_dev(ctx.handle, fr.data_ptr(), S, H, W, pitch, H * pitch, 9, C.c_double(0.09),

@@ -149,7 +149,8 @@ constexpr int FT_SMEM = FT_IMG_BYTES + 3 * FT_ROWS * FT_HP * 4 + 16;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __global__ void __launch_bounds__(FT_THREADS, 2)
-harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, double kappa, double* __restrict__ resp) {
+harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, double kappa, double* __restrict__ resp,
+                     int tiles_x, int tiles_y, int n_tiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t* img = smem_raw;
     int* hxx = reinterpret_cast<int*>(smem_raw + FT_IMG_BYTES);
@@ -157,26 +158,32 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
     int* hxy = hyy + FT_ROWS * FT_HP;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + FT_IMG_BYTES + 3 * FT_ROWS * FT_HP * 4);
     const int tid = threadIdx.x;
-    // Tiles start 11 columns left of a multiple of 128 so that the TMA box (which begins 5 columns
-    // further left) starts on a 16-byte boundary, as cp.async.bulk.tensor requires for 1-byte elements.
-    const int x0 = blockIdx.x * FT_W - FT_XSHIFT, y0 = blockIdx.y * FT_H, f = blockIdx.z;
 
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
+    // Persistent CTA (grid = 2 x SM count): tile t -> (frame, tile row, tile column).  The image box of the
+    // next tile is requested as soon as phase H has consumed the current one, so its HBM latency hides
+    // behind phase V.  Tiles start 11 columns left of a multiple of 128 so that the TMA box (which begins
+    // 5 columns further left) starts on a 16-byte boundary, as cp.async.bulk.tensor needs for 1-byte data.
+    auto issue_load = [&](int t) {
+        const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, fr = t / (tiles_x * tiles_y);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(FT_IMG_BYTES) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-            ::"r"(smem_u32(img)), "l"(&tmap), "r"(x0 - 5), "r"(y0 - 5), "r"(f), "r"(smem_u32(mbar)) : "memory");
+            ::"r"(smem_u32(img)), "l"(&tmap), "r"(bx * FT_W - FT_XSHIFT - 5), "r"(by * FT_H - 5), "r"(fr), "r"(smem_u32(mbar)) : "memory");
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((int)blockIdx.x < n_tiles) issue_load(blockIdx.x);
     }
+    __syncthreads();
+    uint32_t parity = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1) {
+    const int x0 = (tile % tiles_x) * FT_W - FT_XSHIFT, y0 = ((tile / tiles_x) % tiles_y) * FT_H, f = tile / (tiles_x * tiles_y);
     {   // all threads wait for the tile
         uint32_t done = 0;
         while (!done) {
             asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(smem_u32(mbar)), "r"(0) : "memory");
+                         : "=r"(done) : "r"(smem_u32(mbar)), "r"(parity) : "memory");
         }
     }
     // ---------------- phase H ----------------
@@ -195,35 +202,45 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
             }
             int ring_xx[9], ring_yy[9], ring_xy[9];
             int sxx = 0, syy = 0, sxy = 0;
-            int sv1 = 0, sv2 = 0, dv1 = 0, dv2 = 0;   // columns c-1, c-2
             int* oxx = hxx + r * FT_HP + 32 * g;
             int* oyy = hyy + r * FT_HP + 32 * g;
             int* oxy = hxy + r * FT_HP + 32 * g;
+            // Sobel by 8-bit dot products on the packed pixels (no byte extraction): for product column m the
+            // word s_k = pixels (m, m+1, m+2, m+3) of image row k (funnel shift of two packed words);
+            //   gx = sum_k {1,2,1}[k] * (p_k[m] - p_k[m+2]),   gy = sum_j {1,2,1}[j] * (p_0[m+j] - p_2[m+j])
+            // (left - right, top - bottom: the signs cancel in the products, harris.py:103-113).
 #pragma unroll
-            for (int c = 0; c < 42; c++) {
-                const int a = (int)__byte_perm(w[0][c >> 2], 0u, 0x4440u + (c & 3));
-                const int b = (int)__byte_perm(w[1][c >> 2], 0u, 0x4440u + (c & 3));
-                const int d = (int)__byte_perm(w[2][c >> 2], 0u, 0x4440u + (c & 3));
-                const int sv0 = a + 2 * b + d;
-                const int dv0 = a - d;
-                if (c >= 2) {
-                    const int m = c - 2;
-                    const int gx = sv2 - sv0;                 // left - right (sign cancels in the products)
-                    const int gy = dv2 + 2 * dv1 + dv0;       // top - bottom
-                    const int pxx = gx * gx, pyy = gy * gy, pxy = gx * gy;
-                    if (m >= 9) {
-                        sxx += pxx - ring_xx[m % 9]; syy += pyy - ring_yy[m % 9]; sxy += pxy - ring_xy[m % 9];
-                    } else {
-                        sxx += pxx; syy += pyy; sxy += pxy;
-                    }
-                    ring_xx[m % 9] = pxx; ring_yy[m % 9] = pyy; ring_xy[m % 9] = pxy;
-                    if (m >= 8) { oxx[m - 8] = sxx; oyy[m - 8] = syy; oxy[m - 8] = sxy; }
+            for (int m = 0; m < 40; m++) {
+                const int q = m >> 2, sh = 8 * (m & 3);
+                uint32_t s0, s1, s2;
+                if (sh == 0) { s0 = w[0][q]; s1 = w[1][q]; s2 = w[2][q]; }
+                else {
+                    s0 = __funnelshift_r(w[0][q], w[0][q + 1], sh);
+                    s1 = __funnelshift_r(w[1][q], w[1][q + 1], sh);
+                    s2 = __funnelshift_r(w[2][q], w[2][q + 1], sh);
                 }
-                sv2 = sv1; sv1 = sv0; dv2 = dv1; dv1 = dv0;
+                int gx, gy;
+                asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s0), "r"(0x00FF0001), "r"(0));
+                asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s1), "r"(0x00FE0002), "r"(gx));
+                asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s2), "r"(0x00FF0001), "r"(gx));
+                asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gy) : "r"(s0), "r"(0x00010201), "r"(0));
+                asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gy) : "r"(s2), "r"(0x00FFFEFF), "r"(gy));
+                const int pxx = gx * gx, pyy = gy * gy, pxy = gx * gy;
+                if (m >= 9) {
+                    sxx += pxx - ring_xx[m % 9]; syy += pyy - ring_yy[m % 9]; sxy += pxy - ring_xy[m % 9];
+                } else {
+                    sxx += pxx; syy += pyy; sxy += pxy;
+                }
+                ring_xx[m % 9] = pxx; ring_yy[m % 9] = pyy; ring_xy[m % 9] = pxy;
+                if (m >= 8) { oxx[m - 8] = sxx; oyy[m - 8] = syy; oxy[m - 8] = sxy; }
             }
         }
     }
     __syncthreads();
+    if (tid == 0 && tile + (int)gridDim.x < n_tiles) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of img precede the async overwrite
+        issue_load(tile + gridDim.x);
+    }
     // ---------------- phase V ----------------
     {
         const int col = tid & 127, half = tid >> 7;
@@ -236,42 +253,70 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
             rxx[k] = hxx[(base + k) * FT_HP + col]; ryy[k] = hyy[(base + k) * FT_HP + col]; rxy[k] = hxy[(base + k) * FT_HP + col];
             vxx += rxx[k]; vyy += ryy[k]; vxy += rxy[k];
         }
-        // Branch-free emission (one straight-line block, so the scheduler can overlap the float64 chains of
-        // neighbouring rows): the score is always evaluated; a single predicate folds the clamp (s > 0)
-        // with "inside the zero border"; the store itself is predicated on the row being in the image.
+        // Branch-free emission (straight-line blocks, so the scheduler can overlap the float64 chains of
+        // neighbouring rows).  The score is always evaluated; one predicate folds the clamp (s > 0,
+        // harris.py:127) with "inside the zero border" (harris.py:129-137); the store is predicated on the
+        // pixel being inside the image.  Tiles that touch neither the top nor the bottom of the image
+        // (CTA-uniform test) take a variant whose predicates are per-thread constants.
         const bool x_in = gx >= 0 && gx < W, x_interior = gx >= 5 && gx < W - 5;
         const int gy0 = y0 + base;
-        const int n_rows = x_in ? min(27, H - gy0) : 0;            // rows this thread may store
-        const int i_lo = 5 - gy0;                                  // interior rows: i_lo <= i < i_lo + i_span
-        const unsigned i_span = x_interior ? (unsigned)max(H - 10, 0) : 0u;
-        const size_t row_bytes = (size_t)W * sizeof(double);
-        char* dst = reinterpret_cast<char*>(resp + ((size_t)f * H + (size_t)max(gy0, 0)) * W + max(gx, 0));
+        const unsigned int row_bytes = (unsigned int)W * (unsigned int)sizeof(double);
+        char* dst0 = reinterpret_cast<char*>(resp + ((size_t)f * H + (size_t)gy0) * W + max(gx, 0));
+        const bool y_interior_tile = (y0 >= 5) && (y0 + FT_H <= H - 5);
+        if (y_interior_tile) {
+            const unsigned int xi = x_interior ? 1u : 0u, xs = x_in ? 1u : 0u;
 #pragma unroll
-        for (int i = 0; i < 27; i++) {
-            const double sa = (double)vxx, sb = (double)vyy, sc = (double)vxy;
-            const double trace = __dadd_rn(sa, sb);
-            const double det = __dsub_rn(__dmul_rn(sa, sb), __dmul_rn(sc, sc));
-            const double sraw = __dsub_rn(det, __dmul_rn(kappa, __dmul_rn(trace, trace)));
-            // one predicate: inside the zero border (harris.py:129-137) AND s > 0 (harris.py:127); then a
-            // store predicated on the row being inside the image.  PTX keeps this at DSETP+ISETP+2 FSEL.
-            asm volatile(
-                "{\n\t.reg .pred p, q, r;\n\t.reg .f64 v;\n\t"
-                "setp.gt.f64 p, %1, 0d0000000000000000;\n\t"
-                "setp.lt.u32 q, %2, %3;\n\t"
-                "and.pred p, p, q;\n\t"
-                "selp.f64 v, %1, 0d0000000000000000, p;\n\t"
-                "setp.lt.s32 r, %4, %5;\n\t"
-                "@r st.global.f64 [%0], v;\n\t}"
-                ::"l"(dst), "d"(sraw), "r"((unsigned)(i - i_lo)), "r"(i_span), "r"(i), "r"(n_rows) : "memory");
-            dst += row_bytes;
-            if (i < 26) {
-                const int nxx = hxx[(base + i + 9) * FT_HP + col], nyy = hyy[(base + i + 9) * FT_HP + col],
-                          nxy = hxy[(base + i + 9) * FT_HP + col];
-                vxx += nxx - rxx[i % 9]; vyy += nyy - ryy[i % 9]; vxy += nxy - rxy[i % 9];
-                rxx[i % 9] = nxx; ryy[i % 9] = nyy; rxy[i % 9] = nxy;
+            for (int i = 0; i < 27; i++) {
+                const double sa = (double)vxx, sb = (double)vyy, sc = (double)vxy;
+                const double trace = __dadd_rn(sa, sb);
+                const double det = __dsub_rn(__dmul_rn(sa, sb), __dmul_rn(sc, sc));
+                const double sraw = __dsub_rn(det, __dmul_rn(kappa, __dmul_rn(trace, trace)));
+                char* dst = dst0 + (size_t)row_bytes * (unsigned int)i;
+                asm volatile(
+                    "{\n\t.reg .pred p, q, r;\n\t.reg .f64 v;\n\t"
+                    "setp.ne.u32 q, %2, 0;\n\t"
+                    "setp.gt.and.f64 p, %1, 0d0000000000000000, q;\n\t"
+                    "selp.f64 v, %1, 0d0000000000000000, p;\n\t"
+                    "setp.ne.u32 r, %3, 0;\n\t"
+                    "@r st.global.f64 [%0], v;\n\t}"
+                    ::"l"(dst), "d"(sraw), "r"(xi), "r"(xs) : "memory");
+                if (i < 26) {
+                    const int nxx = hxx[(base + i + 9) * FT_HP + col], nyy = hyy[(base + i + 9) * FT_HP + col],
+                              nxy = hxy[(base + i + 9) * FT_HP + col];
+                    vxx += nxx - rxx[i % 9]; vyy += nyy - ryy[i % 9]; vxy += nxy - rxy[i % 9];
+                    rxx[i % 9] = nxx; ryy[i % 9] = nyy; rxy[i % 9] = nxy;
+                }
+            }
+        } else {
+            const int n_rows = x_in ? min(27, H - gy0) : 0;           // rows this thread may store
+            const int i_lo = 5 - gy0;                                 // interior rows: i_lo <= i < i_lo + i_span
+            const unsigned i_span = x_interior ? (unsigned)max(H - 10, 0) : 0u;
+#pragma unroll
+            for (int i = 0; i < 27; i++) {
+                const double sa = (double)vxx, sb = (double)vyy, sc = (double)vxy;
+                const double trace = __dadd_rn(sa, sb);
+                const double det = __dsub_rn(__dmul_rn(sa, sb), __dmul_rn(sc, sc));
+                const double sraw = __dsub_rn(det, __dmul_rn(kappa, __dmul_rn(trace, trace)));
+                char* dst = dst0 + (size_t)row_bytes * (unsigned int)i;
+                asm volatile(
+                    "{\n\t.reg .pred p, q, r;\n\t.reg .f64 v;\n\t"
+                    "setp.lt.u32 q, %2, %3;\n\t"
+                    "setp.gt.and.f64 p, %1, 0d0000000000000000, q;\n\t"
+                    "selp.f64 v, %1, 0d0000000000000000, p;\n\t"
+                    "setp.lt.s32 r, %4, %5;\n\t"
+                    "@r st.global.f64 [%0], v;\n\t}"
+                    ::"l"(dst), "d"(sraw), "r"((unsigned)(i - i_lo)), "r"(i_span), "r"(i), "r"(n_rows) : "memory");
+                if (i < 26) {
+                    const int nxx = hxx[(base + i + 9) * FT_HP + col], nyy = hyy[(base + i + 9) * FT_HP + col],
+                              nxy = hxy[(base + i + 9) * FT_HP + col];
+                    vxx += nxx - rxx[i % 9]; vyy += nyy - ryy[i % 9]; vxy += nxy - rxy[i % 9];
+                    rxx[i % 9] = nxx; ryy[i % 9] = nyy; rxy[i % 9] = nxy;
+                }
             }
         }
     }
+    __syncthreads();   // the H sums are free for the next tile's phase H
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -665,8 +710,11 @@ int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, i
                 VO_CUDA(cudaFuncSetAttribute(harris_response_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
                 attr_fast = true;
             }
-            dim3 grid(vo_div_up(W + FT_XSHIFT, FT_W), vo_div_up(H, FT_H), n_frames);
-            harris_response_fast<<<grid, FT_THREADS, FT_SMEM, stream>>>(tmap, H, W, kappa, d_resp);
+            const int tiles_x = vo_div_up(W + FT_XSHIFT, FT_W), tiles_y = vo_div_up(H, FT_H);
+            const long long n_tiles = (long long)tiles_x * tiles_y * n_frames;
+            VO_REQUIRE(n_tiles < (1ll << 31), "harris: too many tiles");
+            const int grid = (int)((n_tiles < 2ll * ctx->sm_count) ? n_tiles : 2ll * ctx->sm_count);
+            harris_response_fast<<<grid, FT_THREADS, FT_SMEM, stream>>>(tmap, H, W, kappa, d_resp, tiles_x, tiles_y, (int)n_tiles);
             ctx->launches++;
             VO_CHECK_LAUNCH();
             return VO_OK;
