@@ -322,52 +322,67 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
 // ---------------------------------------------------------------------------------------------
 // NMS step 1: dense local-maximum detection (window radius r, raster-order tie break).
 // ---------------------------------------------------------------------------------------------
-constexpr int LT_W = 64, LT_H = 16, L_THREADS = 256;
+constexpr int LT_W = 64, LT_H = 32, L_THREADS = 256;
 
+// Scores are non-negative doubles, so their bit patterns order like unsigned 64-bit integers.  The tile
+// (+ halo r) is staged as two 32-bit planes; a pixel survives the cheap test if the high word of its
+// score is >= the high words of its 8 neighbours, and the (rare) survivors get the exact
+// (2r+1)^2 test, done by the whole warp (32 window positions per step, early exit by ballot).
 __global__ void __launch_bounds__(L_THREADS)
 harris_localmax(const double* __restrict__ resp, int H, int W, int r, unsigned int lm_cap,
                 unsigned long long* __restrict__ lm_key, unsigned int* __restrict__ lm_idx,
                 unsigned int* __restrict__ lm_count) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* tile = reinterpret_cast<double*>(smem_raw);
     const int tw = LT_W + 2 * r, th = LT_H + 2 * r;
+    unsigned int* hi = reinterpret_cast<unsigned int*>(smem_raw);
+    unsigned int* lo = hi + tw * th;
     const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;
     const int f = blockIdx.z;
     const double* src = resp + (size_t)f * H * W;
     for (int i = threadIdx.x; i < tw * th; i += L_THREADS) {
         const int ty = i / tw, tx = i - ty * tw;
         const int gy = y0 - r + ty, gx = x0 - r + tx;
-        double v = 0.0;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = src[(size_t)gy * W + gx];
-        tile[i] = v;
+        unsigned long long v = 0ull;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = (unsigned long long)__double_as_longlong(src[(size_t)gy * W + gx]);
+        hi[i] = (unsigned int)(v >> 32);
+        lo[i] = (unsigned int)v;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < LT_W * LT_H; i += L_THREADS) {
+    const int lane = threadIdx.x & 31;
+    const int win = 2 * r + 1, nwin = win * win;
+    for (int i = threadIdx.x; i < LT_W * LT_H; i += L_THREADS) {   // same trip count for every lane of a warp
         const int ly = i / LT_W, lx = i - ly * LT_W;
         const int gy = y0 + ly, gx = x0 + lx;
-        if (gy >= H || gx >= W) continue;
-        const double* c = tile + (ly + r) * tw + (lx + r);
-        const double s = *c;
-        if (!(s > 0.0)) continue;
-        // cheap reject on the 8-neighbourhood
-        bool ok = true;
-        if (r >= 1)
-            ok = s > c[-tw - 1] && s > c[-tw] && s > c[-tw + 1] && s > c[-1] &&
-                 s >= c[1] && s >= c[tw - 1] && s >= c[tw] && s >= c[tw + 1];
-        if (!ok) continue;
-        for (int dy = -r; dy <= r && ok; dy++) {
-            const double* row = c + dy * tw;
-            for (int dx = -r; dx <= r; dx++) {
-                const double q = row[dx];
-                const bool before = (dy < 0) || (dy == 0 && dx < 0);
-                if (before ? (q >= s) : (q > s)) { ok = false; break; }
-            }
+        const int c = (ly + r) * tw + (lx + r);
+        const unsigned int ch = hi[c];
+        bool cand = (gy < H && gx < W) && ((ch | lo[c]) != 0u);
+        if (cand && r >= 1) {
+            const unsigned int m0 = max(max(hi[c - tw - 1], hi[c - tw]), max(hi[c - tw + 1], hi[c - 1]));
+            const unsigned int m1 = max(max(hi[c + 1], hi[c + tw - 1]), max(hi[c + tw], hi[c + tw + 1]));
+            cand = ch >= max(m0, m1);
         }
-        if (ok) {
-            const unsigned int slot = atomicAdd(&lm_count[f], 1u);
-            if (slot < lm_cap) {
-                lm_key[(size_t)f * lm_cap + slot] = (unsigned long long)__double_as_longlong(s);
-                lm_idx[(size_t)f * lm_cap + slot] = (unsigned int)(gy * W + gx);
+        unsigned int mask = __ballot_sync(0xFFFFFFFFu, cand);
+        while (mask) {
+            const int src_lane = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int cc = __shfl_sync(0xFFFFFFFFu, c, src_lane);
+            const unsigned long long ck = ((unsigned long long)hi[cc] << 32) | lo[cc];
+            bool fail = false;
+            for (int j = lane; j < nwin; j += 32) {
+                const int dy = j / win - r, dx = j - (j / win) * win - r;
+                if (dy == 0 && dx == 0) continue;
+                const int q = cc + dy * tw + dx;
+                const unsigned long long qk = ((unsigned long long)hi[q] << 32) | lo[q];
+                const bool before = (dy < 0) || (dy == 0 && dx < 0);   // raster order: ties go to the earlier pixel
+                if (before ? (qk >= ck) : (qk > ck)) fail = true;
+            }
+            const bool is_lm = !__any_sync(0xFFFFFFFFu, fail);
+            if (is_lm && lane == src_lane) {
+                const unsigned int slot = atomicAdd(&lm_count[f], 1u);
+                if (slot < lm_cap) {
+                    lm_key[(size_t)f * lm_cap + slot] = ck;
+                    lm_idx[(size_t)f * lm_cap + slot] = (unsigned int)(gy * W + gx);
+                }
             }
         }
     }
@@ -443,119 +458,313 @@ struct NmsArgs {
     const unsigned int* lm_idx;
     const unsigned int* lm_count;      // [F]
     unsigned char* state;              // [F][H*W]  0 alive/unknown, 1 suppressed, 2 picked
-    unsigned int* alive_a;             // [F][H*W]
-    unsigned int* alive_b;             // [F][H*W]
+    uint4* alive_a;                    // [F][H*W] {pixel, blocker, key lo, key hi}
+    uint4* alive_b;                    // [F][H*W]
     unsigned long long* pick_key;      // [F][lm_cap]
     unsigned int* pick_idx;            // [F][lm_cap]
     unsigned int* new_idx;             // [F][lm_cap]
     int* kp_xy;                        // [F][K][2]
     unsigned int* stats;               // [F][4]: n_lm, n_alive0, n_rounds, n_picks
+    unsigned long long* thr_key;       // [F] threshold (score bits)
+    unsigned int* thr_idx;             // [F] threshold (tie-break index)
+    unsigned int* counters;            // [F][4]: alive count, picks count
 };
 
-__device__ __forceinline__ void mark_window(unsigned char* st, int H, int W, int r, unsigned int p) {
+// warp-cooperative: suppress the (2r+1)^2 box around p (state 1) and flag p itself as picked (state 2)
+__device__ __forceinline__ void mark_window_warp(unsigned char* st, int H, int W, int r, unsigned int p, int lane) {
     const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
-    const int ya = max(py - r, 0), yb = min(py + r, H - 1);
-    const int xa = max(px - r, 0), xb = min(px + r, W - 1);
-    for (int y = ya; y <= yb; y++)
-        for (int x = xa; x <= xb; x++) st[y * W + x] = 1;
-    st[p] = 2;
+    const int win = 2 * r + 1;
+    for (int j = lane; j < win * win; j += 32) {
+        const int y = py + j / win - r, x = px + j % win - r;
+        if (y >= 0 && y < H && x >= 0 && x < W) st[y * W + x] = (y == py && x == px) ? 2 : 1;
+    }
 }
+
+constexpr int NMS_MAX_WIN = 31 * 31;
+
+// ---- NMS step 2 (one CTA per frame): threshold = K-th best local maximum; maxima above it are picks and
+// ---- suppress their windows.
+__global__ void __launch_bounds__(N_THREADS)
+harris_nms_select(NmsArgs a) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_misc[4];
+    __shared__ unsigned int s_np;
+    const int f = blockIdx.x;
+    const int H = a.H, W = a.W, r = a.r, K = a.K;
+    const unsigned int npx = (unsigned int)H * W;
+    const unsigned long long* lmk = a.lm_key + (size_t)f * a.lm_cap;
+    const unsigned int* lmi = a.lm_idx + (size_t)f * a.lm_cap;
+    unsigned char* st = a.state + (size_t)f * npx;            // zeroed by the launcher
+    unsigned long long* pk = a.pick_key + (size_t)f * a.lm_cap;
+    unsigned int* pi = a.pick_idx + (size_t)f * a.lm_cap;
+    const unsigned int n_lm = min(a.lm_count[f], a.lm_cap);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long tk = 1ull;                             // "every positive score"
+    unsigned int ti = 0xFFFFFFFFu;
+    if (n_lm >= (unsigned)K && K > 0) block_select_kth(lmk, lmi, n_lm, (unsigned)K, hist, s_misc, &tk, &ti);
+    if (tid == 0) s_np = 0;
+    __syncthreads();
+    for (unsigned int j = warp; j < n_lm; j += N_THREADS / 32) {
+        const unsigned long long k = lmk[j];
+        const unsigned int i = lmi[j];
+        if (prio_ge(k, i, tk, ti)) {
+            if (lane == 0) {
+                const unsigned int s = atomicAdd(&s_np, 1u);
+                pk[s] = k; pi[s] = i;
+            }
+            mark_window_warp(st, H, W, r, i, lane);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        a.thr_key[f] = tk; a.thr_idx[f] = ti;
+        a.counters[f * 4 + 0] = 0;        // alive count (filled by the scan)
+        a.counters[f * 4 + 1] = s_np;     // picks so far
+    }
+}
+
+// ---- NMS step 3 (grid-wide, HBM speed): alive = score at or above the threshold and not suppressed.
+constexpr int SCAN_PER_THREAD = 8;
+constexpr unsigned int NMS_NONE = 0xFFFFFFFFu;
+
+// An alive-list entry is {pixel, blocker, score bits lo, hi}: blocker = a neighbour that is alive and has higher
+// priority (the pixel cannot be picked while that neighbour is alive), or NMS_NONE.
+__global__ void __launch_bounds__(256)
+harris_nms_scan(NmsArgs a) {
+    __shared__ unsigned int s_total, s_base;
+    __shared__ unsigned int s_warp[8];
+    const int f = blockIdx.y;
+    const int H = a.H, W = a.W;
+    const unsigned int npx = (unsigned int)H * W;
+    const double* resp = a.resp + (size_t)f * npx;
+    const unsigned char* st = a.state + (size_t)f * npx;
+    uint4* alive = a.alive_a + (size_t)f * npx;
+    const unsigned long long tk = a.thr_key[f];
+    const unsigned int ti = a.thr_idx[f];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int base = blockIdx.x * (256u * SCAN_PER_THREAD) + threadIdx.x;
+    unsigned long long k[SCAN_PER_THREAD];
+    unsigned char s8[SCAN_PER_THREAD];
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; j++) {            // all loads first (coalesced, 8 in flight per thread)
+        const unsigned int p = base + j * 256u;
+        k[j] = p < npx ? (unsigned long long)__double_as_longlong(resp[p]) : 0ull;
+        s8[j] = p < npx ? st[p] : (unsigned char)1;
+    }
+    unsigned int keep_mask = 0, cnt = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; j++) {
+        const unsigned int p = base + j * 256u;
+        if (k[j] != 0ull && s8[j] == 0 && prio_ge(k[j], p, tk, ti)) { keep_mask |= 1u << j; cnt++; }
+    }
+    // block-wide exclusive offsets: warp scan, then one global atomic per CTA
+    unsigned int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < 8; w++) { const unsigned int c = s_warp[w]; s_warp[w] = t; t += c; }
+        s_total = t;
+        s_base = t ? atomicAdd(&a.counters[f * 4 + 0], t) : 0u;
+    }
+    __syncthreads();
+    unsigned int off = s_base + s_warp[warp] + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; j++) {
+        if (!(keep_mask & (1u << j))) continue;
+        const unsigned int p = base + j * 256u;
+        const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
+        unsigned long long kq[8];
+        unsigned char sq[8];
+        unsigned int qi[8];
+#pragma unroll
+        for (int n = 0; n < 8; n++) {                      // the 8-neighbourhood, loads first
+            const int dy = (n < 3) ? -1 : (n < 6) ? 1 : 0;
+            const int dx = (n < 6) ? (n % 3) - 1 : (n == 6 ? -1 : 1);
+            const int y = py + dy, x = px + dx;
+            kq[n] = 0ull; sq[n] = 1; qi[n] = 0;
+            if (a.r >= 1 && y >= 0 && y < H && x >= 0 && x < W) {
+                qi[n] = (unsigned int)(y * W + x);
+                sq[n] = st[qi[n]];
+                kq[n] = (unsigned long long)__double_as_longlong(resp[qi[n]]);
+            }
+        }
+        unsigned int blocker = NMS_NONE;
+#pragma unroll
+        for (int n = 0; n < 8; n++)
+            if (sq[n] == 0 && prio_gt(kq[n], qi[n], k[j], p)) blocker = qi[n];
+        alive[off++] = make_uint4(p, blocker, (unsigned int)k[j], (unsigned int)(k[j] >> 32));
+    }
+}
+
+// ---- NMS step 4 (one CTA per frame): rounds + final selection.
+// A round: entries whose blocker is still alive are kept without further work; the others are re-tested,
+// rings 1-2 by one lane per candidate (all loads issued up front), rings 3..r by a whole warp for the
+// few that are 5x5 maxima among the alive.  Unbeaten candidates become picks and suppress their window.
+// Candidates that fall below the (tightening) threshold are dropped and flagged dead, so nothing stays
+// blocked behind them.
+constexpr int NMS_SMEM_PICKS = 4096;   // picks mirrored in shared memory for the per-round threshold selects
 
 __global__ void __launch_bounds__(N_THREADS)
 harris_nms_frame(NmsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_misc[4];
-    __shared__ unsigned int s_cnt[4];  // 0: alive count, 1: picks count, 2: new picks, 3: next alive
+    __shared__ unsigned int s_cnt[4];          // 0: survivors, 1: picks, 2: new picks, 3: next alive
+    __shared__ signed char s_wdy[NMS_MAX_WIN], s_wdx[NMS_MAX_WIN];   // window offsets, nearest ring first
     const int f = blockIdx.x;
     const int H = a.H, W = a.W, r = a.r, K = a.K;
     const unsigned int npx = (unsigned int)H * W;
     const double* resp = a.resp + (size_t)f * npx;
-    const unsigned long long* lmk = a.lm_key + (size_t)f * a.lm_cap;
-    const unsigned int* lmi = a.lm_idx + (size_t)f * a.lm_cap;
     unsigned char* st = a.state + (size_t)f * npx;
-    unsigned int* alive = a.alive_a + (size_t)f * npx;
-    unsigned int* alive_next = a.alive_b + (size_t)f * npx;
+    uint4* alive = a.alive_a + (size_t)f * npx;
+    uint4* alive_next = a.alive_b + (size_t)f * npx;
     unsigned long long* pk = a.pick_key + (size_t)f * a.lm_cap;
     unsigned int* pi = a.pick_idx + (size_t)f * a.lm_cap;
     unsigned int* newp = a.new_idx + (size_t)f * a.lm_cap;
-    const unsigned int n_lm = min(a.lm_count[f], a.lm_cap);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int N_WARPS = N_THREADS / 32;
+    const int win = 2 * r + 1, nwin = win * win, nnb = nwin - 1;
+    // shared-memory mirror of the picks (keys then indices); the final sort reuses the same storage
+    unsigned int P2 = 1;
+    while (P2 < (unsigned)max(K, 1)) P2 <<= 1;
+    const unsigned int cap_s = max(P2, (unsigned)NMS_SMEM_PICKS);
+    unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);
+    unsigned int* si = reinterpret_cast<unsigned int*>(sk + cap_s);
 
-    // ---- threshold = K-th best local maximum (or "everything positive" if fewer than K) ----
-    unsigned long long tk = 1ull;
-    unsigned int ti = 0xFFFFFFFFu;
-    if (n_lm >= (unsigned)K && K > 0) block_select_kth(lmk, lmi, n_lm, (unsigned)K, hist, s_misc, &tk, &ti);
-    if (tid < 4) s_cnt[tid] = 0;
-    for (unsigned int p = tid; p < npx; p += N_THREADS) st[p] = 0;
-    __syncthreads();
-    // ---- local maxima above the threshold are picks; suppress their windows ----
-    for (unsigned int j = tid; j < n_lm; j += N_THREADS) {
-        const unsigned long long k = lmk[j];
-        const unsigned int i = lmi[j];
-        if (prio_ge(k, i, tk, ti)) {
-            const unsigned int s = atomicAdd(&s_cnt[1], 1u);
-            pk[s] = k; pi[s] = i;
-            mark_window(st, H, W, r, i);
-        }
+    for (int j = tid; j < nwin; j += N_THREADS) {
+        const int dy = j / win - r, dx = j % win - r;
+        const int rho = max(abs(dy), abs(dx));
+        if (rho == 0) continue;
+        int local;
+        if (dy == -rho) local = dx + rho;
+        else if (dy == rho) local = 2 * rho + 1 + dx + rho;
+        else if (dx == -rho) local = 4 * rho + 2 + (dy + rho - 1);
+        else local = 4 * rho + 2 + (2 * rho - 1) + (dy + rho - 1);
+        const int slot = (2 * rho - 1) * (2 * rho - 1) - 1 + local;
+        s_wdy[slot] = (signed char)dy;
+        s_wdx[slot] = (signed char)dx;
     }
-    __syncthreads();
-    // ---- dense scan: alive = above threshold and not suppressed ----
-    for (unsigned int p = tid; p < npx; p += N_THREADS) {
-        const unsigned long long k = (unsigned long long)__double_as_longlong(resp[p]);
-        if (k != 0ull && prio_ge(k, p, tk, ti) && st[p] == 0) {
-            const unsigned int s = atomicAdd(&s_cnt[0], 1u);
-            alive[s] = p;
-        }
-    }
-    __syncthreads();
-    unsigned int n_alive = s_cnt[0];
+    unsigned long long tk = a.thr_key[f];
+    unsigned int ti = a.thr_idx[f];
+    unsigned int n_alive = a.counters[f * 4 + 0];
+    const unsigned int n_picks0 = a.counters[f * 4 + 1];
+    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = n_picks0; s_cnt[2] = 0; s_cnt[3] = 0; }
+    for (unsigned int j = tid; j < min(n_picks0, cap_s); j += N_THREADS) { sk[j] = pk[j]; si[j] = pi[j]; }
+    const unsigned int n_lm = min(a.lm_count[f], a.lm_cap);
     const unsigned int n_alive0 = n_alive;
     unsigned int rounds = 0;
-    // ---- rounds: local maxima among the alive pixels become picks ----
+    __syncthreads();
+    const int n_lane = min(24, nnb);           // rings 1-2: tested by one lane per candidate
     while (n_alive > 0) {
-        for (unsigned int j = tid; j < n_alive; j += N_THREADS) {
-            const unsigned int p = alive[j];
-            const unsigned long long k = (unsigned long long)__double_as_longlong(resp[p]);
+        // every pick found so far is a pick of the reference; with >= K of them, nothing below the K-th
+        // best can be among the first K any more: tighten the threshold and let the alive list shrink.
+        const unsigned int n_picks_now = s_cnt[1];
+        if (n_picks_now > (unsigned)K) {
+            if (n_picks_now <= cap_s) block_select_kth(sk, si, n_picks_now, (unsigned)K, hist, s_misc, &tk, &ti);
+            else block_select_kth(pk, pi, n_picks_now, (unsigned)K, hist, s_misc, &tk, &ti);
+        }
+        // pass A: one entry per lane
+        const unsigned int n_round = (n_alive + 31u) & ~31u;
+        for (unsigned int j = tid; j < n_round; j += N_THREADS) {
+            const bool valid = j < n_alive;
+            const uint4 e = valid ? alive[j] : make_uint4(0u, NMS_NONE, 0u, 0u);
+            const unsigned int p = e.x;
+            const unsigned long long k = ((unsigned long long)e.w << 32) | e.z;
+            const unsigned char sp = valid ? st[p] : (unsigned char)1;
+            const unsigned char sb = (valid && e.y != NMS_NONE) ? st[e.y] : (unsigned char)1;
+            bool live = valid && sp == 0;
+            if (live && !prio_ge(k, p, tk, ti)) { st[p] = 1; live = false; }   // below the threshold: irrelevant from now on
+            const bool blocked = live && sb == 0;          // its blocker is still alive: nothing to do
+            const bool test = live && !blocked;
             const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
-            const int ya = max(py - r, 0), yb = min(py + r, H - 1);
-            const int xa = max(px - r, 0), xb = min(px + r, W - 1);
-            bool is_max = true;
-            for (int y = ya; y <= yb && is_max; y++) {
-                for (int x = xa; x <= xb; x++) {
-                    const unsigned int q = (unsigned int)(y * W + x);
-                    if (q == p || st[q] != 0) continue;
-                    const unsigned long long kq = (unsigned long long)__double_as_longlong(resp[q]);
-                    if (prio_gt(kq, q, k, p)) { is_max = false; break; }
+            unsigned int blocker = blocked ? e.y : NMS_NONE;
+            for (int c0 = 0; c0 < n_lane && test && blocker == NMS_NONE; c0 += 8) {
+                unsigned long long kq[8];
+                unsigned char sq[8];
+                unsigned int qi[8];
+#pragma unroll
+                for (int n = 0; n < 8; n++) {
+                    kq[n] = 0ull; sq[n] = 1; qi[n] = 0;
+                    if (c0 + n < n_lane) {
+                        const int y = py + s_wdy[c0 + n], x = px + s_wdx[c0 + n];
+                        if (y >= 0 && y < H && x >= 0 && x < W) {
+                            qi[n] = (unsigned int)(y * W + x);
+                            sq[n] = st[qi[n]];
+                            kq[n] = (unsigned long long)__double_as_longlong(resp[qi[n]]);
+                        }
+                    }
                 }
+#pragma unroll
+                for (int n = 0; n < 8; n++)
+                    if (sq[n] == 0 && prio_gt(kq[n], qi[n], k, p)) blocker = qi[n];
             }
-            if (is_max) {
-                const unsigned int s = atomicAdd(&s_cnt[2], 1u);
-                newp[s] = p;
+            const bool keep = blocked || (test && blocker != NMS_NONE);
+            const bool surv = test && blocker == NMS_NONE;
+            const unsigned int mb = __ballot_sync(0xFFFFFFFFu, keep);
+            const unsigned int ms = __ballot_sync(0xFFFFFFFFu, surv);
+            unsigned int ob = 0, os = 0;
+            if (lane == 0) {
+                if (mb) ob = atomicAdd(&s_cnt[3], (unsigned int)__popc(mb));
+                if (ms) os = atomicAdd(&s_cnt[0], (unsigned int)__popc(ms));
+            }
+            ob = __shfl_sync(0xFFFFFFFFu, ob, 0);
+            os = __shfl_sync(0xFFFFFFFFu, os, 0);
+            const unsigned int below = (1u << lane) - 1u;
+            if (keep) alive_next[ob + __popc(mb & below)] = make_uint4(p, blocker, e.z, e.w);
+            if (surv) alive_next[npx - 1u - (os + __popc(ms & below))] = make_uint4(p, NMS_NONE, e.z, e.w);   // survivors grow from the end
+        }
+        __syncthreads();
+        // pass B: one warp per survivor, rings 3..r
+        const unsigned int n_surv = s_cnt[0];
+        for (unsigned int j = warp; j < n_surv; j += N_WARPS) {
+            const uint4 e = alive_next[npx - 1u - j];
+            const unsigned int p = e.x;
+            const unsigned long long k = ((unsigned long long)e.w << 32) | e.z;
+            const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
+            unsigned int hitmask = 0, myq = 0;
+            for (int base = n_lane; base < nnb && !hitmask; base += 32) {
+                const int j2 = base + lane;
+                bool hit = false;
+                if (j2 < nnb) {
+                    const int y = py + s_wdy[j2], x = px + s_wdx[j2];
+                    if (y >= 0 && y < H && x >= 0 && x < W) {
+                        myq = (unsigned int)(y * W + x);
+                        const unsigned char sq = st[myq];
+                        const unsigned long long kq = (unsigned long long)__double_as_longlong(resp[myq]);
+                        hit = (sq == 0) && prio_gt(kq, myq, k, p);
+                    }
+                }
+                hitmask = __ballot_sync(0xFFFFFFFFu, hit);
+            }
+            const unsigned int blocker = hitmask ? __shfl_sync(0xFFFFFFFFu, myq, __ffs(hitmask) - 1) : NMS_NONE;
+            if (lane == 0) {
+                if (hitmask) alive_next[atomicAdd(&s_cnt[3], 1u)] = make_uint4(p, blocker, e.z, e.w);
+                else newp[atomicAdd(&s_cnt[2], 1u)] = p;
             }
         }
         __syncthreads();
         const unsigned int n_new = s_cnt[2];
-        for (unsigned int j = tid; j < n_new; j += N_THREADS) {
+        for (unsigned int j = warp; j < n_new; j += N_WARPS) {
             const unsigned int p = newp[j];
-            const unsigned int s = atomicAdd(&s_cnt[1], 1u);
-            pk[s] = (unsigned long long)__double_as_longlong(resp[p]);
-            pi[s] = p;
-            mark_window(st, H, W, r, p);
-        }
-        __syncthreads();
-        for (unsigned int j = tid; j < n_alive; j += N_THREADS) {
-            const unsigned int p = alive[j];
-            if (st[p] == 0) {
-                const unsigned int s = atomicAdd(&s_cnt[3], 1u);
-                alive_next[s] = p;
+            if (lane == 0) {
+                const unsigned int s = atomicAdd(&s_cnt[1], 1u);
+                const unsigned long long k = (unsigned long long)__double_as_longlong(resp[p]);
+                pk[s] = k; pi[s] = p;
+                if (s < cap_s) { sk[s] = k; si[s] = p; }
             }
+            mark_window_warp(st, H, W, r, p, lane);
         }
         __syncthreads();
         n_alive = s_cnt[3];
         __syncthreads();
-        if (tid == 0) { s_cnt[2] = 0; s_cnt[3] = 0; }
-        unsigned int* t = alive; alive = alive_next; alive_next = t;
+        if (tid == 0) { s_cnt[0] = 0; s_cnt[2] = 0; s_cnt[3] = 0; }
+        uint4* t = alive; alive = alive_next; alive_next = t;
         rounds++;
         __syncthreads();
     }
@@ -569,11 +778,8 @@ harris_nms_frame(NmsArgs a) {
     unsigned int fi = 0xFFFFFFFFu;
     const unsigned int n_out = min(n_picks, (unsigned)K);
     if (n_picks > (unsigned)K) block_select_kth(pk, pi, n_picks, (unsigned)K, hist, s_misc, &fk, &fi);
-    // gather into shared memory, padded to a power of two
-    unsigned int P2 = 1;
-    while (P2 < (unsigned)max(K, 1)) P2 <<= 1;
-    unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);
-    unsigned int* si = reinterpret_cast<unsigned int*>(sk + P2);
+    // gather into shared memory, padded to a power of two (the mirror is not needed any more)
+    __syncthreads();
     for (unsigned int j = tid; j < P2; j += N_THREADS) { sk[j] = 0ull; si[j] = 0xFFFFFFFFu; }
     if (tid == 0) s_cnt[0] = 0;
     __syncthreads();
@@ -751,13 +957,15 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_lmk = carve(F * lm_cap * 8), o_lmi = carve(F * lm_cap * 4), o_cnt = carve(F * 4);
-    const size_t o_state = carve(F * npx), o_aa = carve(F * npx * 4), o_ab = carve(F * npx * 4);
+    const size_t o_state = carve(F * npx), o_aa = carve(F * npx * 16), o_ab = carve(F * npx * 16);
     const size_t o_pk = carve(F * lm_cap * 8), o_pi = carve(F * lm_cap * 4), o_new = carve(F * lm_cap * 4);
     const size_t o_stats = carve(F * 16);
+    const size_t o_tk = carve(F * 8), o_ti = carve(F * 4), o_ctr = carve(F * 16);
     int rc = vo_buf_reserve(&ctx->scratch[0], off);
     if (rc) return rc;
     unsigned char* base = (unsigned char*)ctx->scratch[0].p;
     VO_CUDA(cudaMemsetAsync(base + o_cnt, 0, F * 4, stream));
+    VO_CUDA(cudaMemsetAsync(base + o_state, 0, F * npx, stream));
 
     const size_t smem_lm = (size_t)(LT_W + 2 * radius) * (LT_H + 2 * radius) * 8;
     static bool attr_set = false;
@@ -776,14 +984,23 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     a.resp = d_resp; a.H = H; a.W = W; a.r = radius; a.K = num_keypoints; a.lm_cap = (unsigned)lm_cap;
     a.lm_key = (unsigned long long*)(base + o_lmk); a.lm_idx = (unsigned int*)(base + o_lmi);
     a.lm_count = (unsigned int*)(base + o_cnt);
-    a.state = base + o_state; a.alive_a = (unsigned int*)(base + o_aa); a.alive_b = (unsigned int*)(base + o_ab);
+    a.state = base + o_state; a.alive_a = (uint4*)(base + o_aa); a.alive_b = (uint4*)(base + o_ab);
     a.pick_key = (unsigned long long*)(base + o_pk); a.pick_idx = (unsigned int*)(base + o_pi);
     a.new_idx = (unsigned int*)(base + o_new);
     a.kp_xy = d_kp_xy;
     a.stats = d_stats_or_null ? d_stats_or_null : (unsigned int*)(base + o_stats);
+    a.thr_key = (unsigned long long*)(base + o_tk); a.thr_idx = (unsigned int*)(base + o_ti);
+    a.counters = (unsigned int*)(base + o_ctr);
     unsigned int P2 = 1;
     while (P2 < (unsigned)num_keypoints) P2 <<= 1;
-    const size_t smem_nms = (size_t)P2 * 12;
+    const size_t smem_nms = (size_t)(P2 > (unsigned)NMS_SMEM_PICKS ? P2 : (unsigned)NMS_SMEM_PICKS) * 12;
+    harris_nms_select<<<n_frames, N_THREADS, 0, stream>>>(a);
+    ctx->launches++;
+    VO_CHECK_LAUNCH();
+    dim3 g3(vo_div_up((int)npx, 256 * SCAN_PER_THREAD), n_frames);
+    harris_nms_scan<<<g3, 256, 0, stream>>>(a);
+    ctx->launches++;
+    VO_CHECK_LAUNCH();
     harris_nms_frame<<<n_frames, N_THREADS, smem_nms, stream>>>(a);
     ctx->launches++;
     VO_CHECK_LAUNCH();

@@ -9,6 +9,8 @@
 // point is staged in shared memory, lanes stride over the win^2 window pixels, the Gram matrix
 // and mismatch vector are reduced with warp shuffles as exact integers, and every lane carries
 // the (uniform) float32 iteration state in OpenCV's operation order (--fmad=false).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -255,6 +257,244 @@ klt_track_kernel(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path: window size known at compile time.  Same arithmetic as klt_track_kernel (the tests
+// compare both with the oracle bit for bit); what changes is how the warp gets there:
+//   * window values (I, Ix, Iy) live in registers, WIN*WIN/32 (+1) pixels per lane, static indexing;
+//   * staging is division-free (compile-time divisors) with a branch-free single reflection
+//     (pyramid levels are larger than the window, so one reflection is enough);
+//   * warp sums use the REDUX unit on 16-bit halves (exact) instead of 64-bit shuffle trees;
+//   * the J patch is re-staged only when the integer window position moves.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect1(int i, int n) {   // reflect-101 for |overshoot| <= n + 1 (levels are wider than the window)
+    i = i < 0 ? -i : i;
+    i = i >= n ? 2 * n - 2 - i : i;
+    return i < 0 ? -i : i;
+}
+
+__device__ __forceinline__ long long warp_sum_exact(int v) {
+    const int lo = v & 0xFFFF, hi = v >> 16;               // v == hi * 65536 + lo, also for negative v
+    const int slo = __reduce_add_sync(0xFFFFFFFFu, lo);
+    const int shi = __reduce_add_sync(0xFFFFFFFFu, hi);
+    return (long long)shi * 65536ll + (long long)slo;
+}
+
+template <int N>
+__device__ __forceinline__ void stage_patch_fast(const uint8_t* __restrict__ img, int rows, int cols, size_t pitch,
+                                                 int x0, int y0, uint8_t* sm, int lane) {
+    const bool inside = x0 >= 0 && y0 >= 0 && x0 + N <= cols && y0 + N <= rows;   // warp-uniform
+    if (inside) {
+        const uint8_t* base = img + (size_t)y0 * pitch + x0;
+#pragma unroll
+        for (int i0 = 0; i0 < N * N; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < N * N) { const int py = i / N, px = i - py * N; sm[i] = base[(size_t)py * pitch + px]; }
+        }
+    } else {
+#pragma unroll
+        for (int i0 = 0; i0 < N * N; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < N * N) {
+                const int py = i / N, px = i - py * N;
+                sm[i] = img[(size_t)reflect1(y0 + py, rows) * pitch + reflect1(x0 + px, cols)];
+            }
+        }
+    }
+}
+
+template <int WIN>
+__global__ void __launch_bounds__(KLT_WARPS * 32, 4)
+klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__ pyr_next, PyrLayout lay,
+               int max_iters, double eps2, double min_eig, const float* __restrict__ prev_pts, int n_pts,
+               float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
+    constexpr int W2 = WIN * WIN, PN = WIN + 3, DN = WIN + 1;
+    constexpr int PPL = (W2 + 31) / 32;                        // window pixels per lane
+    constexpr int PATCH_BYTES = (PN * PN + 15) & ~15;
+    constexpr int PER_WARP = (PATCH_BYTES + DN * DN * 4 + 15) & ~15;
+    __shared__ __align__(16) unsigned char smem[KLT_WARPS * PER_WARP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pt = blockIdx.x * KLT_WARPS + warp;
+    const int f = blockIdx.y;
+    if (pt >= n_pts) return;
+    uint8_t* patch = smem + warp * PER_WARP;                                  // I (PN^2), later J (DN^2)
+    short* dpatch = reinterpret_cast<short*>(patch + PATCH_BYTES);             // [DN*DN][2]
+
+    const uint8_t* Ip = pyr_prev + (size_t)f * lay.frame_bytes;
+    const uint8_t* Jp = pyr_next + (size_t)f * lay.frame_bytes;
+    const size_t pidx = (size_t)f * n_pts + pt;
+    const float px0 = prev_pts[2 * pidx], py0 = prev_pts[2 * pidx + 1];
+    const float half = (float)(WIN - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    const int top = lay.n_levels - 1;
+    bool st = true;
+    float e_out = 0.f;
+    float outx = 0.f, outy = 0.f;
+
+    for (int level = top; level >= 0; level--) {
+        const int cols = lay.w[level], rows = lay.h[level];
+        const size_t pitch = lay.pitch[level];
+        const uint8_t* I = Ip + lay.offset[level];
+        const uint8_t* J = Jp + lay.offset[level];
+        const float sc = (float)(1. / (1 << level));
+        float prx = px0 * sc, pry = py0 * sc;
+        float nx, ny;
+        if (level == top) { nx = prx; ny = pry; }
+        else { nx = outx * 2.f; ny = outy * 2.f; }
+        outx = nx; outy = ny;
+        prx -= half; pry -= half;
+        const int ipx = (int)floorf(prx), ipy = (int)floorf(pry);
+        if (ipx < -WIN || ipx >= cols || ipy < -WIN || ipy >= rows) {
+            if (level == 0) { st = false; e_out = 0.f; }
+            continue;
+        }
+        float a = prx - ipx, b = pry - ipy;
+        int iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS));
+        int iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
+        int iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
+        int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+
+        __syncwarp();
+        stage_patch_fast<PN>(I, rows, cols, pitch, ipx - 1, ipy - 1, patch, lane);
+        __syncwarp();
+#pragma unroll
+        for (int i0 = 0; i0 < DN * DN; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < DN * DN) {
+                const int qy = i / DN, qx = i - qy * DN;
+                const int gx = ipx + qx, gy = ipy + qy;
+                int dx = 0, dy = 0;
+                if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
+                    const uint8_t* r0 = patch + qy * PN + qx;
+                    const uint8_t* r1 = r0 + PN;
+                    const uint8_t* r2 = r1 + PN;
+                    const int t0m = ((int)r0[0] + (int)r2[0]) * 3 + (int)r1[0] * 10;
+                    const int t0p = ((int)r0[2] + (int)r2[2]) * 3 + (int)r1[2] * 10;
+                    const int t1m = (int)r2[0] - (int)r0[0], t1c = (int)r2[1] - (int)r0[1], t1p = (int)r2[2] - (int)r0[2];
+                    dx = t0p - t0m;
+                    dy = (t1p + t1m) * 3 + t1c * 10;
+                }
+                dpatch[2 * i] = (short)dx;
+                dpatch[2 * i + 1] = (short)dy;
+            }
+        }
+        __syncwarp();
+        int Iv[PPL], Ix[PPL], Iy[PPL];
+        int sA11 = 0, sA12 = 0, sA22 = 0;
+#pragma unroll
+        for (int k = 0; k < PPL; k++) {
+            const int i = k * 32 + lane;
+            Iv[k] = 0; Ix[k] = 0; Iy[k] = 0;
+            if (i < W2) {
+                const int y = i / WIN, x = i - y * WIN;
+                const uint8_t* s0 = patch + (y + 1) * PN + (x + 1);
+                Iv[k] = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[PN] * iw10 + (int)s0[PN + 1] * iw11, W_BITS - 5);
+                const short* d0 = dpatch + 2 * (y * DN + x);
+                const short* d1 = d0 + 2 * DN;
+                Ix[k] = descale((int)d0[0] * iw00 + (int)d0[2] * iw01 + (int)d1[0] * iw10 + (int)d1[2] * iw11, W_BITS);
+                Iy[k] = descale((int)d0[1] * iw00 + (int)d0[3] * iw01 + (int)d1[1] * iw10 + (int)d1[3] * iw11, W_BITS);
+                sA11 += Ix[k] * Ix[k];
+                sA12 += Ix[k] * Iy[k];
+                sA22 += Iy[k] * Iy[k];
+            }
+        }
+        const long long iA11 = warp_sum_exact(sA11), iA12 = warp_sum_exact(sA12), iA22 = warp_sum_exact(sA22);
+        const float A11 = (float)iA11 * FLT_SCALE, A12 = (float)iA12 * FLT_SCALE, A22 = (float)iA22 * FLT_SCALE;
+        float D = A11 * A22 - A12 * A12;
+        const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
+        if ((double)minEig < min_eig || D < 1.1920928955078125e-07f) {
+            if (level == 0) st = false;
+            continue;
+        }
+        D = 1.f / D;
+        nx -= half; ny -= half;
+        float pdx = 0.f, pdy = 0.f;
+        int sx = 0x7fffffff, sy = 0x7fffffff;                 // integer position of the staged J patch
+        for (int j = 0; j < max_iters; j++) {
+            const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+            if (inx < -WIN || inx >= cols || iny < -WIN || iny >= rows) {
+                if (level == 0) st = false;
+                break;
+            }
+            a = nx - inx; b = ny - iny;
+            iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS));
+            iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
+            iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
+            iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+            if (inx != sx || iny != sy) {
+                __syncwarp();
+                stage_patch_fast<DN>(J, rows, cols, pitch, inx, iny, patch, lane);
+                __syncwarp();
+                sx = inx; sy = iny;
+            }
+            int sb1 = 0, sb2 = 0;
+#pragma unroll
+            for (int k = 0; k < PPL; k++) {
+                const int i = k * 32 + lane;
+                if (i < W2) {
+                    const int y = i / WIN, x = i - y * WIN;
+                    const uint8_t* s0 = patch + y * DN + x;
+                    const int diff = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[DN] * iw10 + (int)s0[DN + 1] * iw11,
+                                             W_BITS - 5) - Iv[k];
+                    sb1 += diff * Ix[k];
+                    sb2 += diff * Iy[k];
+                }
+            }
+            const long long ib1 = warp_sum_exact(sb1), ib2 = warp_sum_exact(sb2);
+            const float b1 = (float)ib1 * FLT_SCALE, b2 = (float)ib2 * FLT_SCALE;
+            const float dx = (float)((A12 * b2 - A22 * b1) * D);
+            const float dy = (float)((A12 * b1 - A11 * b2) * D);
+            nx += dx; ny += dy;
+            outx = nx + half; outy = ny + half;
+            if ((double)dx * dx + (double)dy * dy <= eps2) break;
+            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
+                outx -= dx * 0.5f;
+                outy -= dy * 0.5f;
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+        if (st && level == 0) {
+            const float fx = outx - half, fy = outy - half;
+            const int inx = (int)floorf(fx), iny = (int)floorf(fy);
+            if (inx < -WIN || inx >= cols || iny < -WIN || iny >= rows) {
+                st = false;
+                continue;
+            }
+            const float aa = fx - inx, bb = fy - iny;
+            iw00 = __float2int_rn((1.f - aa) * (1.f - bb) * (1 << W_BITS));
+            iw01 = __float2int_rn(aa * (1.f - bb) * (1 << W_BITS));
+            iw10 = __float2int_rn((1.f - aa) * bb * (1 << W_BITS));
+            iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+            if (inx != sx || iny != sy) {
+                __syncwarp();
+                stage_patch_fast<DN>(J, rows, cols, pitch, inx, iny, patch, lane);
+                __syncwarp();
+            }
+            int se = 0;
+#pragma unroll
+            for (int k = 0; k < PPL; k++) {
+                const int i = k * 32 + lane;
+                if (i < W2) {
+                    const int y = i / WIN, x = i - y * WIN;
+                    const uint8_t* s0 = patch + y * DN + x;
+                    const int diff = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[DN] * iw10 + (int)s0[DN + 1] * iw11,
+                                             W_BITS - 5) - Iv[k];
+                    se += diff < 0 ? -diff : diff;
+                }
+            }
+            const long long e = warp_sum_exact(se);
+            e_out = (float)e * 1.f / (float)(32 * WIN * WIN);
+        }
+    }
+    if (lane == 0) {
+        next_pts[2 * pidx] = outx;
+        next_pts[2 * pidx + 1] = outy;
+        status[pidx] = st ? 1 : 0;
+        err[pidx] = e_out;
+    }
+}
+
 }  // namespace
 
 static int klt_layout(int H, int W, int max_level, int win, PyrLayout* L) {
@@ -338,6 +578,17 @@ int vo_launch_klt_track(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d
         attr_set = true;
     }
     dim3 g(vo_div_up(n_pts, KLT_WARPS), n_frames);
+    if ((win == 17 || win == 21) && !getenv("VO_KLT_GENERIC")) {
+        if (win == 17)
+            klt_track_fast<17><<<g, KLT_WARPS * 32, 0, stream>>>(d_pyr_prev, d_pyr_next, L, max_iters, epsilon * epsilon, min_eig,
+                                                                  d_prev_pts, n_pts, d_next_pts, d_status, d_err);
+        else
+            klt_track_fast<21><<<g, KLT_WARPS * 32, 0, stream>>>(d_pyr_prev, d_pyr_next, L, max_iters, epsilon * epsilon, min_eig,
+                                                                  d_prev_pts, n_pts, d_next_pts, d_status, d_err);
+        ctx->launches++;
+        VO_CHECK_LAUNCH();
+        return VO_OK;
+    }
     klt_track_kernel<<<g, KLT_WARPS * 32, smem, stream>>>(d_pyr_prev, d_pyr_next, L, win, max_iters, epsilon * epsilon,
                                                           min_eig, d_prev_pts, n_pts, d_next_pts, d_status, d_err);
     ctx->launches++;
