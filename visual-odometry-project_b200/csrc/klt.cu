@@ -283,24 +283,30 @@ __device__ __forceinline__ long long warp_sum_exact(int v) {
 template <int N>
 __device__ __forceinline__ void stage_patch_fast(const uint8_t* __restrict__ img, int rows, int cols, size_t pitch,
                                                  int x0, int y0, uint8_t* sm, int lane) {
+    // element i = lane + 32 t -> (py, px), advanced without division; loads are batched (all issued, then stored)
+    constexpr int T = (N * N + 31) / 32;
+    int py = lane / N, px = lane - py * N;
     const bool inside = x0 >= 0 && y0 >= 0 && x0 + N <= cols && y0 + N <= rows;   // warp-uniform
+    uint8_t v[T];
     if (inside) {
         const uint8_t* base = img + (size_t)y0 * pitch + x0;
 #pragma unroll
-        for (int i0 = 0; i0 < N * N; i0 += 32) {
-            const int i = i0 + lane;
-            if (i < N * N) { const int py = i / N, px = i - py * N; sm[i] = base[(size_t)py * pitch + px]; }
+        for (int t = 0; t < T; t++) {
+            v[t] = (t * 32 + lane < N * N) ? base[(size_t)py * pitch + px] : (uint8_t)0;
+            px += 32 % N; py += 32 / N;
+            if (px >= N) { px -= N; py++; }
         }
     } else {
 #pragma unroll
-        for (int i0 = 0; i0 < N * N; i0 += 32) {
-            const int i = i0 + lane;
-            if (i < N * N) {
-                const int py = i / N, px = i - py * N;
-                sm[i] = img[(size_t)reflect1(y0 + py, rows) * pitch + reflect1(x0 + px, cols)];
-            }
+        for (int t = 0; t < T; t++) {
+            v[t] = (t * 32 + lane < N * N) ? img[(size_t)reflect1(y0 + py, rows) * pitch + reflect1(x0 + px, cols)] : (uint8_t)0;
+            px += 32 % N; py += 32 / N;
+            if (px >= N) { px -= N; py++; }
         }
     }
+#pragma unroll
+    for (int t = 0; t < T; t++)
+        if (t * 32 + lane < N * N) sm[t * 32 + lane] = v[t];
 }
 
 template <int WIN>
@@ -330,6 +336,15 @@ klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__
     bool st = true;
     float e_out = 0.f;
     float outx = 0.f, outy = 0.f;
+    // window pixel k of this lane: offsets into the J patch (DN wide) and the I patch (PN wide); -1 = none
+    int offJ[PPL], offI[PPL];
+#pragma unroll
+    for (int k = 0; k < PPL; k++) {
+        const int i = k * 32 + lane;
+        const int y = i / WIN, x = i - y * WIN;
+        offJ[k] = i < W2 ? y * DN + x : -1;
+        offI[k] = (y + 1) * PN + (x + 1);
+    }
 
     for (int level = top; level >= 0; level--) {
         const int cols = lay.w[level], rows = lay.h[level];
@@ -357,11 +372,10 @@ klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__
         __syncwarp();
         stage_patch_fast<PN>(I, rows, cols, pitch, ipx - 1, ipy - 1, patch, lane);
         __syncwarp();
-#pragma unroll
-        for (int i0 = 0; i0 < DN * DN; i0 += 32) {
-            const int i = i0 + lane;
-            if (i < DN * DN) {
-                const int qy = i / DN, qx = i - qy * DN;
+        {
+            int qy = lane / DN, qx = lane - qy * DN;
+#pragma unroll 2
+            for (int i = lane; i < DN * DN; i += 32) {
                 const int gx = ipx + qx, gy = ipy + qy;
                 int dx = 0, dy = 0;
                 if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
@@ -376,6 +390,8 @@ klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__
                 }
                 dpatch[2 * i] = (short)dx;
                 dpatch[2 * i + 1] = (short)dy;
+                qx += 32 % DN; qy += 32 / DN;
+                if (qx >= DN) { qx -= DN; qy++; }
             }
         }
         __syncwarp();
@@ -383,13 +399,11 @@ klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__
         int sA11 = 0, sA12 = 0, sA22 = 0;
 #pragma unroll
         for (int k = 0; k < PPL; k++) {
-            const int i = k * 32 + lane;
             Iv[k] = 0; Ix[k] = 0; Iy[k] = 0;
-            if (i < W2) {
-                const int y = i / WIN, x = i - y * WIN;
-                const uint8_t* s0 = patch + (y + 1) * PN + (x + 1);
+            if (offJ[k] >= 0) {
+                const uint8_t* s0 = patch + offI[k];
                 Iv[k] = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[PN] * iw10 + (int)s0[PN + 1] * iw11, W_BITS - 5);
-                const short* d0 = dpatch + 2 * (y * DN + x);
+                const short* d0 = dpatch + 2 * offJ[k];
                 const short* d1 = d0 + 2 * DN;
                 Ix[k] = descale((int)d0[0] * iw00 + (int)d0[2] * iw01 + (int)d1[0] * iw10 + (int)d1[2] * iw11, W_BITS);
                 Iy[k] = descale((int)d0[1] * iw00 + (int)d0[3] * iw01 + (int)d1[1] * iw10 + (int)d1[3] * iw11, W_BITS);
@@ -430,10 +444,8 @@ klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__
             int sb1 = 0, sb2 = 0;
 #pragma unroll
             for (int k = 0; k < PPL; k++) {
-                const int i = k * 32 + lane;
-                if (i < W2) {
-                    const int y = i / WIN, x = i - y * WIN;
-                    const uint8_t* s0 = patch + y * DN + x;
+                if (offJ[k] >= 0) {
+                    const uint8_t* s0 = patch + offJ[k];
                     const int diff = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[DN] * iw10 + (int)s0[DN + 1] * iw11,
                                              W_BITS - 5) - Iv[k];
                     sb1 += diff * Ix[k];
@@ -474,10 +486,8 @@ klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__
             int se = 0;
 #pragma unroll
             for (int k = 0; k < PPL; k++) {
-                const int i = k * 32 + lane;
-                if (i < W2) {
-                    const int y = i / WIN, x = i - y * WIN;
-                    const uint8_t* s0 = patch + y * DN + x;
+                if (offJ[k] >= 0) {
+                    const uint8_t* s0 = patch + offJ[k];
                     const int diff = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[DN] * iw10 + (int)s0[DN + 1] * iw11,
                                              W_BITS - 5) - Iv[k];
                     se += diff < 0 ? -diff : diff;
