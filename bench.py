@@ -117,49 +117,54 @@ def initial_iters():
 # clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Polls NVML every few ms from a thread while the timed region runs (nvidia-smi -lms is too coarse for
+    a region of tens of ms); falls back to one nvidia-smi query."""
 
     def __init__(self, gpu_index):
-        self.idx, self.samples, self.proc = gpu_index, [], None
+        self.idx, self.sm, self.reasons, self.max_mhz, self._stop, self.th = gpu_index, [], set(), None, False, None
+
+    def _poll(self):
+        import pynvml as nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+        while not self._stop:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.th = threading.Thread(target=self._poll, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.th = None
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        self._stop = True
+        if self.th is not None:
+            self.th.join(timeout=1)
+        if self.sm:
+            return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(self.max_mhz), "reasons": sorted(self.reasons),
+                    "samples": len(self.sm), "source": "NVML polled every 4 ms during the timed region"}
         try:
-            self.proc.wait(timeout=2)
+            out = subprocess.run(["nvidia-smi", f"--id={self.idx}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            a, b = [float(x) for x in out.strip().split(",")]
+            return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "source": "nvidia-smi after the timed region"}
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.samples:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -373,11 +378,18 @@ def main():
     hb = {k: v.numpy() for k, v in hostbuf.items()}
     pool_np = pool_pinned.numpy()
 
+    def prefetch(i):
+        fe2.prefetch_host(pool_np[i % P], hb["landmarks"], hb["kp2d"], hb["samples"], hb["table"], hb["tri_p1"],
+                          hb["tri_p2"], hb["tri_proj1"], hb["tri_proj2"])
+
     def step_host(i):
-        fe2.step_host(pool_np[i % P], hb["landmarks"], hb["kp2d"], K9, hb["samples"], hb["table"], init, hb["tri_p1"],
-                      hb["tri_p2"], hb["tri_proj1"], hb["tri_proj2"], outs)
+        # documented call order: the upload of step i+1 is queued on the copy stream, then step i (whose inputs
+        # were uploaded during step i-1) runs and its results are read back; every step moves h2d + d2h bytes.
+        prefetch(i + 1)
+        fe2.step_host(None, None, None, K9, None, None, init, None, None, None, None, outs)
 
     e2e_steps = args.e2e_steps or args.steps
+    prefetch(0)
     for i in range(warmup):
         step_host(i)
     barrier()
@@ -414,7 +426,7 @@ def main():
                                     f"({P * S * H * pitch / 1e6:.0f} MB) + {S * H * W * 8 / 1e6:.0f} MB score maps per step",
                        "parallelism": f"{world} x independent sequence shards, no collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "vo_frontend_step_host (pinned host buffers in, results out, per step)"},
+                    "steps": e2e_steps, "api": "vo_frontend_prefetch_host + vo_frontend_step_host (pinned host buffers in, results out, every step; the upload of step t+1 overlaps the compute of step t)"},
             "gpu_launches": int(launches) * world,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }))

@@ -161,6 +161,13 @@ int vo_frontend_step_dev(vo_frontend* fe, const uint8_t* d_frames, size_t pitch,
                          const int32_t* d_sample_idx, const int32_t* d_iters_table, int initial_iters,
                          const double* d_tri_p1, const double* d_tri_p2, const double* d_tri_proj1,
                          const double* d_tri_proj2, void* stream);
+/* Optional: start uploading the inputs of the NEXT step on the context's copy stream (double-buffered
+ * staging) so that the transfer overlaps the step that is computing now.  Up to two uploads may be pending;
+ * step_host consumes the oldest one (its h_* input pointers are then ignored and may be NULL).  Call order:
+ * prefetch(step 0); then per step t: prefetch(step t+1); step_host(step t).                          */
+int vo_frontend_prefetch_host(vo_frontend* fe, const uint8_t* h_frames, const double* h_landmarks, const double* h_kp2d,
+                              const int32_t* h_sample_idx, const int32_t* h_iters_table, const double* h_tri_p1,
+                              const double* h_tri_p2, const double* h_tri_proj1, const double* h_tri_proj2);
 /* Host-buffer step: uploads the frames (tightly packed) and the P3P / triangulation inputs, runs
  * the step, downloads keypoints int32 [n_seq][K][2], tracked points / status / err of the previous
  * keypoints, best4 / inlier masks / poses [n_seq][12] and landmarks [n_seq * n_tri][3]; returns when

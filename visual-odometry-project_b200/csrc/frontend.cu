@@ -29,6 +29,13 @@ struct vo_frontend {
     // staging for the host entry point
     double *s_landmarks, *s_kp2d, *s_tri_p1, *s_tri_p2, *s_tri_proj1, *s_tri_proj2;
     int32_t *s_samples, *s_table;
+    uint8_t* s_frames;        // tightly packed upload target of the host entry point
+    unsigned char* stage[2];  // two staging sets (frames + P3P + triangulation inputs) for upload / compute overlap
+    size_t so_fr, so_l, so_k, so_s, so_tb, so_t1, so_t2, so_tp1, so_tp2, stage_bytes;
+    int stage_next;           // set the next prefetch / upload writes (sets alternate)
+    int prefetched;           // number of uploaded-but-not-yet-consumed steps (0..2), oldest first
+    cudaStream_t copy_stream;  // uploads / downloads of the host entry point overlap compute on the main stream
+    cudaEvent_t ev_up[8], ev_done[8];
 };
 
 extern "C" {
@@ -55,6 +62,7 @@ int vo_frontend_create(vo_ctx* ctx, const vo_frontend_params* prm, vo_frontend**
     const size_t o_b4 = carve(S * 16), o_con = carve(S * 4), o_it = carve(S * 4), o_in = carve(S * N), o_pose = carve(S * 96);
     const size_t o_to = carve(S * T * 24 + 256);
     const size_t o_sl = carve(S * N * 24), o_sk = carve(S * N * 16), o_ss = carve(S * Hn * 16), o_stb = carve((N + 1) * 4);
+    const size_t o_fr = carve(S * npx + 256);
     const size_t o_t1 = carve(S * T * 16 + 256), o_t2 = carve(S * T * 16 + 256), o_tp1 = carve(S * T * 96 + 256), o_tp2 = carve(S * 96);
     cudaError_t e = cudaMalloc(&fe->base, off);
     if (e != cudaSuccess) {
@@ -73,6 +81,22 @@ int vo_frontend_create(vo_ctx* ctx, const vo_frontend_params* prm, vo_frontend**
     fe->s_landmarks = (double*)(b + o_sl); fe->s_kp2d = (double*)(b + o_sk); fe->s_samples = (int32_t*)(b + o_ss);
     fe->s_table = (int32_t*)(b + o_stb); fe->s_tri_p1 = (double*)(b + o_t1); fe->s_tri_p2 = (double*)(b + o_t2);
     fe->s_tri_proj1 = (double*)(b + o_tp1); fe->s_tri_proj2 = (double*)(b + o_tp2);
+    fe->s_frames = b + o_fr;
+    {
+        size_t o = 0;
+        auto cv = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+        fe->so_fr = cv(S * npx + 256); fe->so_l = cv(S * N * 24); fe->so_k = cv(S * N * 16); fe->so_s = cv(S * Hn * 16);
+        fe->so_tb = cv((N + 1) * 4); fe->so_t1 = cv(S * T * 16 + 256); fe->so_t2 = cv(S * T * 16 + 256);
+        fe->so_tp1 = cv(S * T * 96 + 256); fe->so_tp2 = cv(S * 96);
+        fe->stage_bytes = o;
+        for (int i = 0; i < 2; i++) VO_CUDA(cudaMalloc(&fe->stage[i], o));
+        fe->stage_next = 0; fe->prefetched = 0;
+    }
+    VO_CUDA(cudaStreamCreateWithFlags(&fe->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; i++) {
+        VO_CUDA(cudaEventCreateWithFlags(&fe->ev_up[i], cudaEventDisableTiming));
+        VO_CUDA(cudaEventCreateWithFlags(&fe->ev_done[i], cudaEventDisableTiming));
+    }
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = fe;
     return VO_OK;
@@ -82,6 +106,10 @@ void vo_frontend_destroy(vo_frontend* fe) {
     if (!fe) return;
     cudaSetDevice(fe->ctx->device);
     cudaStreamSynchronize(fe->ctx->stream);
+    cudaStreamSynchronize(fe->copy_stream);
+    for (int i = 0; i < 8; i++) { cudaEventDestroy(fe->ev_up[i]); cudaEventDestroy(fe->ev_done[i]); }
+    cudaStreamDestroy(fe->copy_stream);
+    cudaFree(fe->stage[0]); cudaFree(fe->stage[1]);
     cudaFree(fe->base);
     delete fe;
 }
@@ -103,6 +131,55 @@ uint8_t* vo_frontend_next_frame_slot(vo_frontend* fe, size_t* pitch, size_t* fra
     return fe->pyr[1 - fe->cur];
 }
 
+// All stages for sequences [s0, s0 + n) on stream s.  Inputs are indexed from sequence 0.
+static int frontend_run_range(vo_frontend* fe, int s0, int n, const uint8_t* d_frames, size_t pitch, size_t frame_stride,
+                              const double* d_landmarks, const double* d_kp2d, const double* K9,
+                              const int32_t* d_sample_idx, const int32_t* d_iters_table, int initial_iters,
+                              const double* d_tri_p1, const double* d_tri_p2, const double* d_tri_proj1,
+                              const double* d_tri_proj2, cudaStream_t s) {
+    vo_ctx* ctx = fe->ctx;
+    const vo_frontend_params& p = fe->p;
+    const int nxt = 1 - fe->cur;
+    const size_t K = p.num_keypoints, N = p.n_corr, Hn = p.n_hyp, T = p.n_tri, npx = (size_t)p.H * p.W;
+    uint8_t* pyr_new = fe->pyr[nxt] + (size_t)s0 * fe->frame_bytes;
+    const uint8_t* pyr_old = fe->pyr[fe->cur] + (size_t)s0 * fe->frame_bytes;
+    int rc;
+    // 1. pyramid of the new frames (level 0 copied unless already uploaded into the slot)
+    if ((rc = vo_launch_klt_pyramid(ctx, d_frames + (size_t)s0 * frame_stride, n, p.H, p.W, pitch, frame_stride,
+                                    p.klt_max_level, p.klt_win, pyr_new, s))) return rc;
+    // 2. KLT: last frame's keypoints into the new frame (klt.py:233-239)
+    if (fe->steps > 0) {
+        if ((rc = vo_launch_klt_track(ctx, pyr_old, pyr_new, n, p.H, p.W, p.klt_max_level, p.klt_win, p.klt_max_iters,
+                                      p.klt_epsilon, p.klt_min_eig, fe->pts_prev + (size_t)s0 * K * 2, p.num_keypoints,
+                                      fe->pts_next + (size_t)s0 * K * 2, fe->status + (size_t)s0 * K,
+                                      fe->err + (size_t)s0 * K, s))) return rc;
+    }
+    // 3. Harris on the new frame (harris.py:86-158); its keypoints seed the next step's tracking
+    if ((rc = vo_launch_harris_response(ctx, pyr_new, n, p.H, p.W, fe->pitch0, fe->frame_bytes, p.patch_size, p.kappa,
+                                        fe->resp + (size_t)s0 * npx, s))) return rc;
+    if ((rc = vo_launch_harris_nms(ctx, fe->resp + (size_t)s0 * npx, n, p.H, p.W, p.nms_radius, p.num_keypoints,
+                                   fe->kp + (size_t)s0 * K * 2, nullptr, s))) return rc;
+    if ((rc = vo_launch_kp_to_points(ctx, fe->kp + (size_t)s0 * K * 2, (size_t)n * K, fe->pts_prev + (size_t)s0 * K * 2, s))) return rc;
+    // 4. P3P + RANSAC (p3p.py:123-186 with use_opencv=False)
+    if ((rc = vo_launch_p3p_score(ctx, d_landmarks + (size_t)s0 * N * 3, d_kp2d + (size_t)s0 * N * 2, n, p.n_corr, K9,
+                                  d_sample_idx + (size_t)s0 * Hn * 4, p.n_hyp, p.p3p_threshold,
+                                  fe->models + (size_t)s0 * Hn * 12, fe->valid + (size_t)s0 * Hn,
+                                  fe->counts + (size_t)s0 * Hn, s))) return rc;
+    if ((rc = vo_launch_p3p_select(ctx, d_landmarks + (size_t)s0 * N * 3, d_kp2d + (size_t)s0 * N * 2, n, p.n_corr, K9,
+                                   fe->models + (size_t)s0 * Hn * 12, fe->valid + (size_t)s0 * Hn,
+                                   fe->counts + (size_t)s0 * Hn, p.n_hyp, p.p3p_threshold, d_iters_table, initial_iters, 0, -1,
+                                   fe->best4 + (size_t)s0 * 4, fe->consumed + s0, fe->iters_out + s0,
+                                   fe->inliers + (size_t)s0 * N, fe->pose + (size_t)s0 * 12, s))) return rc;
+    // 5. triangulation of new landmarks (triangulation.py:38-86)
+    if (p.n_tri > 0) {
+        VO_REQUIRE(d_tri_p1 && d_tri_p2 && d_tri_proj1 && d_tri_proj2, "vo_frontend_step: null triangulation input");
+        if ((rc = vo_launch_triangulate(ctx, d_tri_p1 + (size_t)s0 * T * 2, d_tri_p2 + (size_t)s0 * T * 2, n * p.n_tri,
+                                        d_tri_proj1 + (size_t)s0 * T * 12, 1, d_tri_proj2 + (size_t)s0 * 12, p.n_tri,
+                                        p.tri_mode, fe->tri_out + (size_t)s0 * T * 3, s))) return rc;
+    }
+    return VO_OK;
+}
+
 int vo_frontend_step_dev(vo_frontend* fe, const uint8_t* d_frames, size_t pitch, size_t frame_stride,
                          const double* d_landmarks, const double* d_kp2d, const double* K9,
                          const int32_t* d_sample_idx, const int32_t* d_iters_table, int initial_iters,
@@ -110,41 +187,54 @@ int vo_frontend_step_dev(vo_frontend* fe, const uint8_t* d_frames, size_t pitch,
                          const double* d_tri_proj2, void* stream) {
     VO_REQUIRE(fe && d_frames && d_landmarks && d_kp2d && K9 && d_sample_idx && d_iters_table,
                "vo_frontend_step_dev: null argument");
-    vo_ctx* ctx = fe->ctx;
-    VO_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
-    const vo_frontend_params& p = fe->p;
-    const int S = p.n_seq;
-    const int nxt = 1 - fe->cur;
-    int rc;
-    // 1. pyramid of the new frames (level 0 copied unless already uploaded into the slot)
-    if ((rc = vo_launch_klt_pyramid(ctx, d_frames, S, p.H, p.W, pitch, frame_stride, p.klt_max_level, p.klt_win,
-                                    fe->pyr[nxt], s))) return rc;
-    // 2. KLT: last frame's keypoints into the new frame (klt.py:233-239)
-    if (fe->steps > 0) {
-        if ((rc = vo_launch_klt_track(ctx, fe->pyr[fe->cur], fe->pyr[nxt], S, p.H, p.W, p.klt_max_level, p.klt_win,
-                                      p.klt_max_iters, p.klt_epsilon, p.klt_min_eig, fe->pts_prev, p.num_keypoints,
-                                      fe->pts_next, fe->status, fe->err, s))) return rc;
-    }
-    // 3. Harris on the new frame (harris.py:86-158); its keypoints seed the next step's tracking
-    if ((rc = vo_launch_harris_response(ctx, fe->pyr[nxt], S, p.H, p.W, fe->pitch0, fe->frame_bytes, p.patch_size,
-                                        p.kappa, fe->resp, s))) return rc;
-    if ((rc = vo_launch_harris_nms(ctx, fe->resp, S, p.H, p.W, p.nms_radius, p.num_keypoints, fe->kp, nullptr, s))) return rc;
-    if ((rc = vo_launch_kp_to_points(ctx, fe->kp, (size_t)S * p.num_keypoints, fe->pts_prev, s))) return rc;
-    // 4. P3P + RANSAC (p3p.py:123-186 with use_opencv=False)
-    if ((rc = vo_launch_p3p_score(ctx, d_landmarks, d_kp2d, S, p.n_corr, K9, d_sample_idx, p.n_hyp, p.p3p_threshold,
-                                  fe->models, fe->valid, fe->counts, s))) return rc;
-    if ((rc = vo_launch_p3p_select(ctx, d_landmarks, d_kp2d, S, p.n_corr, K9, fe->models, fe->valid, fe->counts, p.n_hyp,
-                                   p.p3p_threshold, d_iters_table, initial_iters, 0, -1, fe->best4, fe->consumed,
-                                   fe->iters_out, fe->inliers, fe->pose, s))) return rc;
-    // 5. triangulation of new landmarks (triangulation.py:38-86)
-    if (p.n_tri > 0) {
-        VO_REQUIRE(d_tri_p1 && d_tri_p2 && d_tri_proj1 && d_tri_proj2, "vo_frontend_step_dev: null triangulation input");
-        if ((rc = vo_launch_triangulate(ctx, d_tri_p1, d_tri_p2, S * p.n_tri, d_tri_proj1, 1, d_tri_proj2, p.n_tri,
-                                        p.tri_mode, fe->tri_out, s))) return rc;
-    }
-    fe->cur = nxt;
+    VO_CUDA(cudaSetDevice(fe->ctx->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : fe->ctx->stream;
+    int rc = frontend_run_range(fe, 0, fe->p.n_seq, d_frames, pitch, frame_stride, d_landmarks, d_kp2d, K9, d_sample_idx,
+                                d_iters_table, initial_iters, d_tri_p1, d_tri_p2, d_tri_proj1, d_tri_proj2, s);
+    if (rc) return rc;
+    fe->cur = 1 - fe->cur;
     fe->steps++;
+    return VO_OK;
+}
+
+// enqueue the upload of one step's inputs into staging set `set` on the copy stream
+static int frontend_upload(vo_frontend* fe, int set, const uint8_t* h_frames, const double* h_landmarks,
+                           const double* h_kp2d, const int32_t* h_sample_idx, const int32_t* h_iters_table,
+                           const double* h_tri_p1, const double* h_tri_p2, const double* h_tri_proj1,
+                           const double* h_tri_proj2) {
+    const vo_frontend_params& p = fe->p;
+    const size_t S = p.n_seq, N = p.n_corr, Hn = p.n_hyp, T = p.n_tri, npx = (size_t)p.H * p.W;
+    unsigned char* b = fe->stage[set];
+    cudaStream_t cs = fe->copy_stream;
+    // one contiguous copy per array (a pitched 2-D copy of 1241-byte rows is several times slower over PCIe);
+    // the pyramid builder re-pitches the frames into the level-0 slots on the device.
+    VO_CUDA(cudaMemcpyAsync(b + fe->so_fr, h_frames, S * npx, cudaMemcpyHostToDevice, cs));
+    VO_CUDA(cudaMemcpyAsync(b + fe->so_l, h_landmarks, S * N * 24, cudaMemcpyHostToDevice, cs));
+    VO_CUDA(cudaMemcpyAsync(b + fe->so_k, h_kp2d, S * N * 16, cudaMemcpyHostToDevice, cs));
+    VO_CUDA(cudaMemcpyAsync(b + fe->so_s, h_sample_idx, S * Hn * 16, cudaMemcpyHostToDevice, cs));
+    VO_CUDA(cudaMemcpyAsync(b + fe->so_tb, h_iters_table, (N + 1) * 4, cudaMemcpyHostToDevice, cs));
+    if (T > 0) {
+        VO_CUDA(cudaMemcpyAsync(b + fe->so_t1, h_tri_p1, S * T * 16, cudaMemcpyHostToDevice, cs));
+        VO_CUDA(cudaMemcpyAsync(b + fe->so_t2, h_tri_p2, S * T * 16, cudaMemcpyHostToDevice, cs));
+        VO_CUDA(cudaMemcpyAsync(b + fe->so_tp1, h_tri_proj1, S * T * 96, cudaMemcpyHostToDevice, cs));
+        VO_CUDA(cudaMemcpyAsync(b + fe->so_tp2, h_tri_proj2, S * 96, cudaMemcpyHostToDevice, cs));
+    }
+    VO_CUDA(cudaEventRecord(fe->ev_up[set], cs));
+    return VO_OK;
+}
+
+int vo_frontend_prefetch_host(vo_frontend* fe, const uint8_t* h_frames, const double* h_landmarks, const double* h_kp2d,
+                              const int32_t* h_sample_idx, const int32_t* h_iters_table, const double* h_tri_p1,
+                              const double* h_tri_p2, const double* h_tri_proj1, const double* h_tri_proj2) {
+    VO_REQUIRE(fe && h_frames && h_landmarks && h_kp2d && h_sample_idx && h_iters_table, "vo_frontend_prefetch_host: null argument");
+    VO_REQUIRE(fe->prefetched < 2, "vo_frontend_prefetch_host: two prefetched steps are already pending");
+    if (fe->p.n_tri > 0) VO_REQUIRE(h_tri_p1 && h_tri_p2 && h_tri_proj1 && h_tri_proj2, "vo_frontend_prefetch_host: null triangulation buffer");
+    VO_CUDA(cudaSetDevice(fe->ctx->device));
+    const int set = fe->stage_next;
+    int rc = frontend_upload(fe, set, h_frames, h_landmarks, h_kp2d, h_sample_idx, h_iters_table, h_tri_p1, h_tri_p2,
+                             h_tri_proj1, h_tri_proj2);
+    if (rc) return rc;
+    fe->prefetched++; fe->stage_next = 1 - set;
     return VO_OK;
 }
 
@@ -154,32 +244,38 @@ int vo_frontend_step_host(vo_frontend* fe, const uint8_t* h_frames, const double
                           const double* h_tri_proj1, const double* h_tri_proj2, int32_t* h_kp_xy, float* h_tracked,
                           uint8_t* h_status, float* h_err, int32_t* h_best4, uint8_t* h_inliers, double* h_pose,
                           double* h_tri_out) {
-    VO_REQUIRE(fe && h_frames && h_landmarks && h_kp2d && K9 && h_sample_idx && h_iters_table && h_kp_xy && h_pose,
-               "vo_frontend_step_host: null argument");
+    VO_REQUIRE(fe && K9 && h_kp_xy && h_pose, "vo_frontend_step_host: null argument");
     vo_ctx* ctx = fe->ctx;
     VO_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream;
+    cudaStream_t s = ctx->stream, cs = fe->copy_stream;
     const vo_frontend_params& p = fe->p;
-    const size_t S = p.n_seq, K = p.num_keypoints, N = p.n_corr, Hn = p.n_hyp, T = p.n_tri;
-    uint8_t* slot = fe->pyr[1 - fe->cur];
-    for (size_t f = 0; f < S; f++)   // frames land directly in the level-0 slots (pitched, TMA-legal rows)
-        VO_CUDA(cudaMemcpy2DAsync(slot + f * fe->frame_bytes, fe->pitch0, h_frames + f * (size_t)p.H * p.W, p.W, p.W, p.H,
-                                  cudaMemcpyHostToDevice, s));
-    VO_CUDA(cudaMemcpyAsync(fe->s_landmarks, h_landmarks, S * N * 24, cudaMemcpyHostToDevice, s));
-    VO_CUDA(cudaMemcpyAsync(fe->s_kp2d, h_kp2d, S * N * 16, cudaMemcpyHostToDevice, s));
-    VO_CUDA(cudaMemcpyAsync(fe->s_samples, h_sample_idx, S * Hn * 16, cudaMemcpyHostToDevice, s));
-    VO_CUDA(cudaMemcpyAsync(fe->s_table, h_iters_table, (N + 1) * 4, cudaMemcpyHostToDevice, s));
-    if (T > 0) {
-        VO_REQUIRE(h_tri_p1 && h_tri_p2 && h_tri_proj1 && h_tri_proj2 && h_tri_out, "vo_frontend_step_host: null triangulation buffer");
-        VO_CUDA(cudaMemcpyAsync(fe->s_tri_p1, h_tri_p1, S * T * 16, cudaMemcpyHostToDevice, s));
-        VO_CUDA(cudaMemcpyAsync(fe->s_tri_p2, h_tri_p2, S * T * 16, cudaMemcpyHostToDevice, s));
-        VO_CUDA(cudaMemcpyAsync(fe->s_tri_proj1, h_tri_proj1, S * T * 96, cudaMemcpyHostToDevice, s));
-        VO_CUDA(cudaMemcpyAsync(fe->s_tri_proj2, h_tri_proj2, S * 96, cudaMemcpyHostToDevice, s));
+    const size_t S = p.n_seq, K = p.num_keypoints, N = p.n_corr, T = p.n_tri, npx = (size_t)p.H * p.W;
+    if (T > 0) VO_REQUIRE(h_tri_out, "vo_frontend_step_host: null triangulation output");
+    int set;
+    if (fe->prefetched) {                 // inputs were uploaded by vo_frontend_prefetch_host (host pointers may be NULL)
+        set = (fe->stage_next + 2 - fe->prefetched) & 1;     // oldest pending set
+        fe->prefetched--;
+    } else {
+        VO_REQUIRE(h_frames && h_landmarks && h_kp2d && h_sample_idx && h_iters_table, "vo_frontend_step_host: null input");
+        if (T > 0) VO_REQUIRE(h_tri_p1 && h_tri_p2 && h_tri_proj1 && h_tri_proj2, "vo_frontend_step_host: null triangulation buffer");
+        set = fe->stage_next;
+        int rc = frontend_upload(fe, set, h_frames, h_landmarks, h_kp2d, h_sample_idx, h_iters_table, h_tri_p1, h_tri_p2,
+                                 h_tri_proj1, h_tri_proj2);
+        if (rc) return rc;
+        fe->stage_next = 1 - set;
     }
     const bool had_prev = fe->steps > 0;
-    int rc = vo_frontend_step_dev(fe, slot, fe->pitch0, fe->frame_bytes, fe->s_landmarks, fe->s_kp2d, K9, fe->s_samples,
-                                  fe->s_table, initial_iters, fe->s_tri_p1, fe->s_tri_p2, fe->s_tri_proj1, fe->s_tri_proj2, s);
+    unsigned char* b = fe->stage[set];
+    VO_CUDA(cudaStreamWaitEvent(s, fe->ev_up[set], 0));
+    int rc = frontend_run_range(fe, 0, (int)S, b + fe->so_fr, (size_t)p.W, npx, (const double*)(b + fe->so_l),
+                                (const double*)(b + fe->so_k), K9, (const int32_t*)(b + fe->so_s),
+                                (const int32_t*)(b + fe->so_tb), initial_iters, (const double*)(b + fe->so_t1),
+                                (const double*)(b + fe->so_t2), (const double*)(b + fe->so_tp1),
+                                (const double*)(b + fe->so_tp2), s);
     if (rc) return rc;
+    fe->cur = 1 - fe->cur;
+    fe->steps++;
+    // results come back on the compute stream (a prefetch for the following step may be using the copy stream)
     VO_CUDA(cudaMemcpyAsync(h_kp_xy, fe->kp, S * K * 8, cudaMemcpyDeviceToHost, s));
     if (had_prev && h_tracked) VO_CUDA(cudaMemcpyAsync(h_tracked, fe->pts_next, S * K * 8, cudaMemcpyDeviceToHost, s));
     if (had_prev && h_status) VO_CUDA(cudaMemcpyAsync(h_status, fe->status, S * K, cudaMemcpyDeviceToHost, s));

@@ -71,6 +71,7 @@ def lib():
             "vo_frontend_outputs": (i32, [vp, vp]),
             "vo_frontend_next_frame_slot": (vp, [vp, C.POINTER(sz), C.POINTER(sz)]),
             "vo_frontend_step_dev": (i32, [vp, vp, sz, sz, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+            "vo_frontend_prefetch_host": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
             "vo_frontend_step_host": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp,
                                             vp, vp, vp, vp, vp, vp, vp, vp]),
         })

@@ -51,6 +51,14 @@ class Frontend:
             hp(out.get("tri_out")))
         nat.check(rc, "vo_frontend_step_host")
 
+    def prefetch_host(self, frames, landmarks, kp2d, samples, table, tri_p1, tri_p2, tri_proj1, tri_proj2):
+        """Start uploading the NEXT step's inputs while the current step computes (see vo_frontend_prefetch_host)."""
+        def hp(a):
+            return a.ctypes.data_as(C.c_void_p) if a is not None else None
+        rc = nat.lib().vo_frontend_prefetch_host(self._h, hp(frames), hp(landmarks), hp(kp2d), hp(samples), hp(table),
+                                                 hp(tri_p1), hp(tri_p2), hp(tri_proj1), hp(tri_proj2))
+        nat.check(rc, "vo_frontend_prefetch_host")
+
     def close(self):
         if self._h:
             nat.lib().vo_frontend_destroy(self._h)
