@@ -412,6 +412,7 @@ __device__ __forceinline__ unsigned int comp_byte(unsigned long long k, unsigned
 __device__ void block_select_kth(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ idxs,
                                  unsigned int n, unsigned int kth, unsigned int* hist /*smem[256]*/,
                                  unsigned int* s_misc /*smem[4]*/, unsigned long long* tk_out, unsigned int* ti_out) {
+    __shared__ unsigned int s_wsum[8];
     unsigned long long pk = 0;  // chosen prefix of key
     unsigned int pi = 0;        // chosen prefix of ~idx
     unsigned int remaining = kth;
@@ -429,15 +430,29 @@ __device__ void block_select_kth(const unsigned long long* __restrict__ keys, co
             if (match) atomicAdd(&hist[comp_byte(k, ~ni, b)], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned int acc = 0;
-            int d = 255;
-            for (; d > 0; d--) {
-                if (acc + hist[d] >= remaining) break;
-                acc += hist[d];
+        // which digit holds the `remaining`-th entry counting from the top?  parallel scan over the 256 bins
+        // (thread t looks at digit 255 - t); s_misc[2..] carries the per-warp totals.
+        {
+            const unsigned int t = threadIdx.x, ln = t & 31u, wp = t >> 5;
+            unsigned int v = 0, incl = 0;
+            if (t < 256u) {
+                v = hist[255u - t];
+                incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (ln >= (unsigned)o) incl += u;
+                }
+                if (ln == 31u) s_wsum[wp] = incl;
             }
-            s_misc[0] = (unsigned int)d;
-            s_misc[1] = remaining - acc;
+            __syncthreads();
+            if (t < 256u) {
+                unsigned int off = 0;
+                for (unsigned int w = 0; w < wp; w++) off += s_wsum[w];
+                incl += off;
+                const unsigned int excl = incl - v;
+                if (excl < remaining && incl >= remaining) { s_misc[0] = 255u - t; s_misc[1] = remaining - excl; }
+            }
         }
         __syncthreads();
         const unsigned int d = s_misc[0];
@@ -481,6 +496,7 @@ __device__ __forceinline__ void mark_window_warp(unsigned char* st, int H, int W
 }
 
 constexpr int NMS_MAX_WIN = 31 * 31;
+constexpr int NMS_SELECT_SMEM = 3584;   // local maxima staged in shared memory for the threshold select (42 KB)
 
 // ---- NMS step 2 (one CTA per frame): threshold = K-th best local maximum; maxima above it are picks and
 // ---- suppress their windows.
@@ -501,12 +517,23 @@ harris_nms_select(NmsArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long tk = 1ull;                             // "every positive score"
     unsigned int ti = 0xFFFFFFFFu;
-    if (n_lm >= (unsigned)K && K > 0) block_select_kth(lmk, lmi, n_lm, (unsigned)K, hist, s_misc, &tk, &ti);
+    // the list of local maxima is staged in shared memory when it fits: the 12 radix passes and the marking
+    // loop then run at shared-memory latency instead of one dependent global load per step
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned long long* kk = lmk;
+    const unsigned int* ii = lmi;
+    if (n_lm <= (unsigned)NMS_SELECT_SMEM) {
+        unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);
+        unsigned int* si = reinterpret_cast<unsigned int*>(sk + NMS_SELECT_SMEM);
+        for (unsigned int j = tid; j < n_lm; j += N_THREADS) { sk[j] = lmk[j]; si[j] = lmi[j]; }
+        kk = sk; ii = si;
+    }
     if (tid == 0) s_np = 0;
     __syncthreads();
+    if (n_lm >= (unsigned)K && K > 0) block_select_kth(kk, ii, n_lm, (unsigned)K, hist, s_misc, &tk, &ti);
     for (unsigned int j = warp; j < n_lm; j += N_THREADS / 32) {
-        const unsigned long long k = lmk[j];
-        const unsigned int i = lmi[j];
+        const unsigned long long k = kk[j];
+        const unsigned int i = ii[j];
         if (prio_ge(k, i, tk, ti)) {
             if (lane == 0) {
                 const unsigned int s = atomicAdd(&s_np, 1u);
@@ -994,7 +1021,7 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     unsigned int P2 = 1;
     while (P2 < (unsigned)num_keypoints) P2 <<= 1;
     const size_t smem_nms = (size_t)(P2 > (unsigned)NMS_SMEM_PICKS ? P2 : (unsigned)NMS_SMEM_PICKS) * 12;
-    harris_nms_select<<<n_frames, N_THREADS, 0, stream>>>(a);
+    harris_nms_select<<<n_frames, N_THREADS, NMS_SELECT_SMEM * 12, stream>>>(a);
     ctx->launches++;
     VO_CHECK_LAUNCH();
     dim3 g3(vo_div_up((int)npx, 256 * SCAN_PER_THREAD), n_frames);

@@ -50,11 +50,31 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch, si
     dst[(size_t)blockIdx.z * dframe + (size_t)dy * dpitch + dx] = (uint8_t)((acc + 128) >> 8);
 }
 
-__global__ void copy_level0_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch, size_t sframe,
-                                   uint8_t* __restrict__ dst, size_t dpitch, size_t dframe) {
-    const int x = blockIdx.x * 256 + threadIdx.x;
+// frame -> level-0 slot.  Destination rows are 16-byte aligned (pitch % 16 == 0); each thread assembles one
+// 16-byte store from byte loads when the source row is not aligned the same way (tightly packed 1241-byte rows).
+__global__ void __launch_bounds__(256)
+copy_level0_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch, size_t sframe,
+                   uint8_t* __restrict__ dst, size_t dpitch, size_t dframe) {
+    const int x = (blockIdx.x * 256 + threadIdx.x) * 16;
     const int y = blockIdx.y;
-    if (x < W) dst[(size_t)blockIdx.z * dframe + (size_t)y * dpitch + x] = src[(size_t)blockIdx.z * sframe + (size_t)y * spitch + x];
+    if (x >= W) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * sframe + (size_t)y * spitch + x;
+    uint8_t* d = dst + (size_t)blockIdx.z * dframe + (size_t)y * dpitch + x;
+    if (x + 16 <= W) {
+        uint4 v;
+        if ((reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+            v = *reinterpret_cast<const uint4*>(s);
+        } else {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                w[k] = (uint32_t)s[4 * k] | ((uint32_t)s[4 * k + 1] << 8) | ((uint32_t)s[4 * k + 2] << 16) | ((uint32_t)s[4 * k + 3] << 24);
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        *reinterpret_cast<uint4*>(d) = v;
+    } else {
+        for (int k = 0; x + k < W; k++) d[k] = s[k];
+    }
 }
 
 struct PyrLayout {
@@ -549,7 +569,7 @@ int vo_launch_klt_pyramid(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H
     VO_REQUIRE(klt_layout(H, W, max_level, win, &L) == 0, "klt: max_level must be in [0, %d)", KLT_MAX_LEVELS);
     // level 0: copy unless the caller already placed the frames in the pyramid's level-0 slots
     if (!(d_img == d_pyr && pitch == L.pitch[0] && frame_stride == L.frame_bytes)) {
-        dim3 g(vo_div_up(W, 256), H, n_frames);
+        dim3 g(vo_div_up(vo_div_up(W, 16), 256), H, n_frames);
         copy_level0_kernel<<<g, 256, 0, stream>>>(d_img, H, W, pitch, frame_stride, d_pyr, L.pitch[0], L.frame_bytes);
         ctx->launches++;
         VO_CHECK_LAUNCH();
