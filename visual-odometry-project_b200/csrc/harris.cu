@@ -328,11 +328,13 @@ constexpr int LT_W = 64, LT_H = 32, L_THREADS = 256;
 // (+ halo r) is staged as two 32-bit planes; a pixel survives the cheap test if the high word of its
 // score is >= the high words of its 8 neighbours, and the (rare) survivors get the exact
 // (2r+1)^2 test, done by the whole warp (32 window positions per step, early exit by ballot).
+template <int R>
 __global__ void __launch_bounds__(L_THREADS)
-harris_localmax(const double* __restrict__ resp, int H, int W, int r, unsigned int lm_cap,
+harris_localmax(const double* __restrict__ resp, int H, int W, int r_rt, unsigned int lm_cap,
                 unsigned long long* __restrict__ lm_key, unsigned int* __restrict__ lm_idx,
                 unsigned int* __restrict__ lm_count) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int r = R > 0 ? R : r_rt;                   // compile-time radius: the index divisions below become multiplies
     const int tw = LT_W + 2 * r, th = LT_H + 2 * r;
     unsigned int* hi = reinterpret_cast<unsigned int*>(smem_raw);
     unsigned int* lo = hi + tw * th;
@@ -560,6 +562,8 @@ __global__ void __launch_bounds__(256)
 harris_nms_scan(NmsArgs a) {
     __shared__ unsigned int s_total, s_base;
     __shared__ unsigned int s_warp[8];
+    __shared__ unsigned int s_p[256 * SCAN_PER_THREAD];
+    __shared__ unsigned long long s_k[256 * SCAN_PER_THREAD];
     const int f = blockIdx.y;
     const int H = a.H, W = a.W;
     const unsigned int npx = (unsigned int)H * W;
@@ -600,11 +604,19 @@ harris_nms_scan(NmsArgs a) {
         s_base = t ? atomicAdd(&a.counters[f * 4 + 0], t) : 0u;
     }
     __syncthreads();
-    unsigned int off = s_base + s_warp[warp] + incl - cnt;
+    // compact the kept pixels of this CTA (position + score bits) so that the 8-neighbour test below runs with
+    // dense lanes instead of once per sparse (thread, j) slot
+    const unsigned int total = s_total;
+    {
+        unsigned int o = s_warp[warp] + incl - cnt;
 #pragma unroll
-    for (int j = 0; j < SCAN_PER_THREAD; j++) {
-        if (!(keep_mask & (1u << j))) continue;
-        const unsigned int p = base + j * 256u;
+        for (int j = 0; j < SCAN_PER_THREAD; j++)
+            if (keep_mask & (1u << j)) { s_p[o] = base + j * 256u; s_k[o] = k[j]; o++; }
+    }
+    __syncthreads();
+    for (unsigned int t = threadIdx.x; t < total; t += 256u) {
+        const unsigned int p = s_p[t];
+        const unsigned long long kp = s_k[t];
         const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
         unsigned long long kq[8];
         unsigned char sq[8];
@@ -624,8 +636,8 @@ harris_nms_scan(NmsArgs a) {
         unsigned int blocker = NMS_NONE;
 #pragma unroll
         for (int n = 0; n < 8; n++)
-            if (sq[n] == 0 && prio_gt(kq[n], qi[n], k[j], p)) blocker = qi[n];
-        alive[off++] = make_uint4(p, blocker, (unsigned int)k[j], (unsigned int)(k[j] >> 32));
+            if (sq[n] == 0 && prio_gt(kq[n], qi[n], kp, p)) blocker = qi[n];
+        alive[s_base + t] = make_uint4(p, blocker, (unsigned int)kp, (unsigned int)(kp >> 32));
     }
 }
 
@@ -997,14 +1009,20 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     const size_t smem_lm = (size_t)(LT_W + 2 * radius) * (LT_H + 2 * radius) * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        VO_CUDA(cudaFuncSetAttribute(harris_localmax, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        VO_CUDA(cudaFuncSetAttribute(harris_localmax<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        VO_CUDA(cudaFuncSetAttribute(harris_localmax<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         VO_CUDA(cudaFuncSetAttribute(harris_nms_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         attr_set = true;
     }
     dim3 g1(vo_div_up(W, LT_W), vo_div_up(H, LT_H), n_frames);
-    harris_localmax<<<g1, L_THREADS, smem_lm, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap,
-                                                        (unsigned long long*)(base + o_lmk),
-                                                        (unsigned int*)(base + o_lmi), (unsigned int*)(base + o_cnt));
+    if (radius == 5)
+        harris_localmax<5><<<g1, L_THREADS, smem_lm, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap,
+                                                               (unsigned long long*)(base + o_lmk),
+                                                               (unsigned int*)(base + o_lmi), (unsigned int*)(base + o_cnt));
+    else
+        harris_localmax<0><<<g1, L_THREADS, smem_lm, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap,
+                                                               (unsigned long long*)(base + o_lmk),
+                                                               (unsigned int*)(base + o_lmi), (unsigned int*)(base + o_cnt));
     ctx->launches++;
     VO_CHECK_LAUNCH();
     NmsArgs a;
