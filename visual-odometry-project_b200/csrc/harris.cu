@@ -987,7 +987,7 @@ size_t vo_harris_lm_cap(int H, int W, int r) {
 int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H, int W, int radius,
                          int num_keypoints, int* d_kp_xy, unsigned int* d_stats_or_null, cudaStream_t stream) {
     VO_REQUIRE(radius >= 0 && radius <= 15, "harris nms: radius must be in [0, 15] (got %d)", radius);
-    VO_REQUIRE(num_keypoints >= 1 && num_keypoints <= 8192, "harris nms: num_keypoints must be in [1, 8192]");
+    VO_REQUIRE(num_keypoints >= 1 && num_keypoints <= 16384, "harris nms: num_keypoints must be in [1, 16384]");
     VO_REQUIRE(H >= 2 * radius + 1 && W >= 2 * radius + 1, "harris nms: image smaller than the suppression box");
     const size_t npx = (size_t)H * W;
     const size_t lm_cap = vo_harris_lm_cap(H, W, radius);
@@ -1011,7 +1011,7 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     if (!attr_set) {
         VO_CUDA(cudaFuncSetAttribute(harris_localmax<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         VO_CUDA(cudaFuncSetAttribute(harris_localmax<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        VO_CUDA(cudaFuncSetAttribute(harris_nms_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        VO_CUDA(cudaFuncSetAttribute(harris_nms_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
     dim3 g1(vo_div_up(W, LT_W), vo_div_up(H, LT_H), n_frames);
