@@ -28,26 +28,39 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-// cv2.pyrDown (uint8, 1 channel): thread per output pixel
+// cv2.pyrDown (uint8, 1 channel, BORDER_REFLECT_101): separable [1 4 6 4 1] in shared memory.
+// CTA = 64 x 16 outputs: the (2*64+3) x (2*16+3) input region is staged once (reflected at the image
+// border), the horizontal pass writes 35 x 64 row sums (<= 4080, int16), the vertical pass rounds
+// (sum + 128) >> 8 exactly like OpenCV's integer path.
+constexpr int PD_W = 64, PD_H = 16, PD_IW = 2 * PD_W + 3, PD_IH = 2 * PD_H + 3, PD_IP = 132;
 __global__ void __launch_bounds__(256)
 pyr_down_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch, size_t sframe,
                 uint8_t* __restrict__ dst, int dh, int dw, size_t dpitch, size_t dframe) {
-    const int dx = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int dy = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (dx >= dw || dy >= dh) return;
+    __shared__ uint8_t tile[PD_IH * PD_IP];
+    __shared__ short hs[PD_IH * PD_W];
+    const int ox = blockIdx.x * PD_W, oy = blockIdx.y * PD_H;
     const uint8_t* s = src + (size_t)blockIdx.z * sframe;
-    int xs[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) xs[k] = reflect101(2 * dx + k - 2, W);
-    const int wts[5] = {1, 4, 6, 4, 1};
-    int acc = 0;
-#pragma unroll
-    for (int j = 0; j < 5; j++) {
-        const uint8_t* r = s + (size_t)reflect101(2 * dy + j - 2, H) * spitch;
-        const int rowsum = (int)r[xs[0]] + (int)r[xs[4]] + 4 * ((int)r[xs[1]] + (int)r[xs[3]]) + 6 * (int)r[xs[2]];
-        acc += wts[j] * rowsum;
+    const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
+    for (int i = threadIdx.x; i < PD_IH * PD_IW; i += 256) {
+        const int ty = i / PD_IW, tx = i - ty * PD_IW;
+        tile[ty * PD_IP + tx] = s[(size_t)reflect101(iy0 + ty, H) * spitch + reflect101(ix0 + tx, W)];
     }
-    dst[(size_t)blockIdx.z * dframe + (size_t)dy * dpitch + dx] = (uint8_t)((acc + 128) >> 8);
+    __syncthreads();
+    for (int i = threadIdx.x; i < PD_IH * PD_W; i += 256) {
+        const int ty = i / PD_W, x = i - ty * PD_W;
+        const uint8_t* r = tile + ty * PD_IP + 2 * x;
+        hs[i] = (short)((int)r[0] + (int)r[4] + 4 * ((int)r[1] + (int)r[3]) + 6 * (int)r[2]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PD_H * PD_W; i += 256) {
+        const int y = i / PD_W, x = i - y * PD_W;
+        const int dx = ox + x, dy = oy + y;
+        if (dx < dw && dy < dh) {
+            const short* c = hs + (2 * y) * PD_W + x;
+            const int acc = (int)c[0] + (int)c[4 * PD_W] + 4 * ((int)c[PD_W] + (int)c[3 * PD_W]) + 6 * (int)c[2 * PD_W];
+            dst[(size_t)blockIdx.z * dframe + (size_t)dy * dpitch + dx] = (uint8_t)((acc + 128) >> 8);
+        }
+    }
 }
 
 // frame -> level-0 slot.  Destination rows are 16-byte aligned (pitch % 16 == 0); each thread assembles one
@@ -764,7 +777,7 @@ int vo_launch_klt_pyramid(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H
         VO_CHECK_LAUNCH();
     }
     for (int l = 1; l < L.n_levels; l++) {
-        dim3 g(vo_div_up(L.w[l], 32), vo_div_up(L.h[l], 8), n_frames);
+        dim3 g(vo_div_up(L.w[l], PD_W), vo_div_up(L.h[l], PD_H), n_frames);
         pyr_down_kernel<<<g, 256, 0, stream>>>(d_pyr + L.offset[l - 1], L.h[l - 1], L.w[l - 1], L.pitch[l - 1],
                                                L.frame_bytes, d_pyr + L.offset[l], L.h[l], L.w[l], L.pitch[l],
                                                L.frame_bytes);
