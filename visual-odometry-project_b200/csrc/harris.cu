@@ -153,9 +153,8 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
                      int tiles_x, int tiles_y, int n_tiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t* img = smem_raw;
-    int* hxx = reinterpret_cast<int*>(smem_raw + FT_IMG_BYTES);
-    int* hyy = hxx + FT_ROWS * FT_HP;
-    int* hxy = hyy + FT_ROWS * FT_HP;
+    int2* hab = reinterpret_cast<int2*>(smem_raw + FT_IMG_BYTES);          // (sum Ix^2, sum Iy^2): one 64-bit access
+    int* hxy = reinterpret_cast<int*>(hab + FT_ROWS * FT_HP);              // sum Ix*Iy
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + FT_IMG_BYTES + 3 * FT_ROWS * FT_HP * 4);
     const int tid = threadIdx.x;
 
@@ -202,8 +201,7 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
             }
             int ring_xx[9], ring_yy[9], ring_xy[9];
             int sxx = 0, syy = 0, sxy = 0;
-            int* oxx = hxx + r * FT_HP + 32 * g;
-            int* oyy = hyy + r * FT_HP + 32 * g;
+            int2* oab = hab + r * FT_HP + 32 * g;
             int* oxy = hxy + r * FT_HP + 32 * g;
             // Sobel by 8-bit dot products on the packed pixels (no byte extraction): for product column m the
             // word s_k = pixels (m, m+1, m+2, m+3) of image row k (funnel shift of two packed words);
@@ -232,7 +230,7 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
                     sxx += pxx; syy += pyy; sxy += pxy;
                 }
                 ring_xx[m % 9] = pxx; ring_yy[m % 9] = pyy; ring_xy[m % 9] = pxy;
-                if (m >= 8) { oxx[m - 8] = sxx; oyy[m - 8] = syy; oxy[m - 8] = sxy; }
+                if (m >= 8) { oab[m - 8] = make_int2(sxx, syy); oxy[m - 8] = sxy; }
             }
         }
     }
@@ -250,7 +248,8 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
         int vxx = 0, vyy = 0, vxy = 0;
 #pragma unroll
         for (int k = 0; k < 9; k++) {
-            rxx[k] = hxx[(base + k) * FT_HP + col]; ryy[k] = hyy[(base + k) * FT_HP + col]; rxy[k] = hxy[(base + k) * FT_HP + col];
+            const int2 ab = hab[(base + k) * FT_HP + col];
+            rxx[k] = ab.x; ryy[k] = ab.y; rxy[k] = hxy[(base + k) * FT_HP + col];
             vxx += rxx[k]; vyy += ryy[k]; vxy += rxy[k];
         }
         // Branch-free emission (straight-line blocks, so the scheduler can overlap the float64 chains of
@@ -281,8 +280,8 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
                     "@r st.global.f64 [%0], v;\n\t}"
                     ::"l"(dst), "d"(sraw), "r"(xi), "r"(xs) : "memory");
                 if (i < 26) {
-                    const int nxx = hxx[(base + i + 9) * FT_HP + col], nyy = hyy[(base + i + 9) * FT_HP + col],
-                              nxy = hxy[(base + i + 9) * FT_HP + col];
+                    const int2 nab = hab[(base + i + 9) * FT_HP + col];
+                    const int nxx = nab.x, nyy = nab.y, nxy = hxy[(base + i + 9) * FT_HP + col];
                     vxx += nxx - rxx[i % 9]; vyy += nyy - ryy[i % 9]; vxy += nxy - rxy[i % 9];
                     rxx[i % 9] = nxx; ryy[i % 9] = nyy; rxy[i % 9] = nxy;
                 }
@@ -307,8 +306,8 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
                     "@r st.global.f64 [%0], v;\n\t}"
                     ::"l"(dst), "d"(sraw), "r"((unsigned)(i - i_lo)), "r"(i_span), "r"(i), "r"(n_rows) : "memory");
                 if (i < 26) {
-                    const int nxx = hxx[(base + i + 9) * FT_HP + col], nyy = hyy[(base + i + 9) * FT_HP + col],
-                              nxy = hxy[(base + i + 9) * FT_HP + col];
+                    const int2 nab = hab[(base + i + 9) * FT_HP + col];
+                    const int nxx = nab.x, nyy = nab.y, nxy = hxy[(base + i + 9) * FT_HP + col];
                     vxx += nxx - rxx[i % 9]; vyy += nyy - ryy[i % 9]; vxy += nxy - rxy[i % 9];
                     rxx[i % 9] = nxx; ryy[i % 9] = nyy; rxy[i % 9] = nxy;
                 }
