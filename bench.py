@@ -368,6 +368,28 @@ def main():
                 "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": harris_ms,
                 "note": "9 B/pixel (uint8 in, float64 score out) x S frames per launch"}
 
+    # ---- one sequence alone (latency-bound): device-resident steps of a single 1241x376 stream -----
+    single = None
+    if rank == 0:
+        fe1 = Frontend(1, H, W, num_keypoints=KP, n_corr=N, n_hyp=Hn, p3p_threshold=P3P_THR, n_tri=T, tri_mode=1, ctx=ctx)
+        def step_one(i):
+            fr = pool_d[i % P][0:1]
+            fe1.step_dev(fr.data_ptr(), pitch, H * pitch, devbuf["landmarks"].data_ptr(), devbuf["kp2d"].data_ptr(), K9,
+                         devbuf["samples"].data_ptr(), devbuf["table"].data_ptr(), init, devbuf["tri_p1"].data_ptr(),
+                         devbuf["tri_p2"].data_ptr(), devbuf["tri_proj1"].data_ptr(), devbuf["tri_proj2"].data_ptr(), stream)
+        for i in range(5):
+            step_one(i)
+        torch.cuda.synchronize()
+        n1 = 50
+        e0.record(tstream)
+        for i in range(n1):
+            step_one(5 + i)
+        e1.record(tstream)
+        torch.cuda.synchronize()
+        ms1 = e0.elapsed_time(e1) / n1
+        single = {"frames_per_s": 1e3 / ms1, "ms_per_frame": ms1, "note": "S = 1: one sequence, back-to-back device-resident steps"}
+        fe1.close()
+
     # ---- end-to-end arm through the host-buffer C ABI ------------------------------------------
     fe2 = Frontend(S, H, W, num_keypoints=KP, n_corr=N, n_hyp=Hn, p3p_threshold=P3P_THR, n_tri=T, tri_mode=1, ctx=ctx)
     outs = {"kp_xy": np.empty((S, KP, 2), np.int32), "tracked": np.empty((S, KP, 2), np.float32),
@@ -428,7 +450,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "vo_frontend_prefetch_host + vo_frontend_step_host (pinned host buffers in, results out, every step; the upload of step t+1 overlaps the compute of step t)"},
             "gpu_launches": int(launches) * world,
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "single_sequence": single,
         }))
     if world > 1:
         dist.destroy_process_group()
