@@ -67,6 +67,15 @@ int vo_harris_detect_host(vo_ctx* ctx, const uint8_t* h_img, int n_frames, int H
 int vo_harris_descriptors_host(vo_ctx* ctx, const uint8_t* h_img, int H, int W, const int32_t* h_kp_xy, int K,
                                int desc_radius, uint8_t* h_desc);
 
+/* harris.py:196-264  matchDescriptor for 8-bit descriptors: cv2.BFMatcher().knnMatch(k=2) (L2), the ratio
+ * test m.distance < ratio * n.distance (0.85 in the reference) and first-come uniqueness of the train index.
+ * desc uint8 [n_frames][Q|T][D]; pairs int32 [n_frames][Q][2] = (query, train) in query order, the first
+ * n_pairs[f] rows valid.                                                                            */
+int vo_match_descriptors_dev(vo_ctx* ctx, const uint8_t* d_desc1, const uint8_t* d_desc2, int n_frames, int Q, int T,
+                             int D, double ratio, int32_t* d_pairs, int32_t* d_n_pairs, void* stream);
+int vo_match_descriptors_host(vo_ctx* ctx, const uint8_t* h_desc1, const uint8_t* h_desc2, int n_frames, int Q, int T,
+                              int D, double ratio, int32_t* h_pairs, int32_t* h_n_pairs);
+
 /* ---- KLT: src/vo/features/klt.py:233-239 (cv2.calcOpticalFlowPyrLK) ------------------------- */
 /* Gaussian 5x5 pyramid (cv2.pyrDown, BORDER_REFLECT_101) of a batch of frames, frame-major: level l
  * of frame f lives at d_pyr + f * frame_bytes + level_offset[l] with row pitch level_pitch[l]

@@ -73,6 +73,26 @@ def harris_descriptors(img: np.ndarray, kp_xy: np.ndarray, r: int = 9) -> np.nda
     return out
 
 
+def match_descriptors(desc1, desc2, ratio=0.85):
+    """matchDescriptor of harris.py:196-264 for 8-bit descriptors: cv2.BFMatcher().knnMatch(k=2) with the L2 norm
+    (exact integer squared distances, float32 sqrt), neighbours ordered by (distance, train index) as cv2's
+    batchDistance does, the ratio test in double, and first-come uniqueness of the train index."""
+    a = np.asarray(desc1).reshape(len(desc1), -1).astype(np.int64)
+    b = np.asarray(desc2).reshape(len(desc2), -1).astype(np.int64)
+    d2 = (a * a).sum(1)[:, None] + (b * b).sum(1)[None, :] - 2 * (a @ b.T)
+    order = np.lexsort((np.broadcast_to(np.arange(b.shape[0]), d2.shape), d2), axis=1)[:, :2]
+    used = np.zeros(b.shape[0], dtype=bool)
+    good = []
+    for q in range(a.shape[0]):
+        m, n = order[q]
+        dm = float(np.sqrt(np.float32(d2[q, m])))
+        dn = float(np.sqrt(np.float32(d2[q, n])))
+        if dm < ratio * dn and not used[m]:
+            good.append([q, m])
+            used[m] = True
+    return np.array(good, dtype=np.int64).reshape(-1, 2)
+
+
 # ----------------------------------------------------------------------------
 # P3P + RANSAC  (reference: src/vo/pose_estimation/p3p.py, src/vo/algorithms/ransac.py)
 # ----------------------------------------------------------------------------

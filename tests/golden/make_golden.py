@@ -68,8 +68,26 @@ def make_harris():
     fr = det.extractKeypoints(Frame(blank.copy()))
     out["blank"] = blank
     out["blank_kp40"] = fr.features.keypoints.reshape(-1, 2).astype(np.int32)
+    # matchDescriptor of the reference on two consecutive KITTI crops (harris.py:196-264)
+    crop2 = np.ascontiguousarray(kitti_gray(1)[100:292, 400:720])
+    det = HarrisCornerDetector(num_keypoints=300)
+    fa = det.extractDescriptors(det.extractKeypoints(Frame(crop.copy())))
+    fb = det.extractDescriptors(det.extractKeypoints(Frame(crop2.copy())))
+    out["crop2"] = crop2
+    out["match_desc1"] = fa.features.descriptors.reshape(300, -1).astype(np.uint8)
+    out["match_desc2"] = fb.features.descriptors.reshape(300, -1).astype(np.uint8)
+    bf = cv2.BFMatcher()
+    used = np.zeros(300)
+    good = []
+    for m, n in bf.knnMatch(out["match_desc1"].astype(np.float32), out["match_desc2"].astype(np.float32), k=2):
+        if m.distance < 0.85 * n.distance and used[m.trainIdx] == 0:
+            good.append([m.queryIdx, m.trainIdx])
+            used[m.trainIdx] = 1
+    out["match_pairs"] = np.array(good, np.int32)
+    mt = det.matchDescriptor(fa, fb)
+    out["match_n_matched"] = int((mt.frame1.features.state == 1).sum())
     np.savez_compressed(os.path.join(OUT, "harris.npz"), **out)
-    print("harris.npz", {k: v.shape for k, v in out.items()})
+    print("harris.npz", {k: np.shape(v) for k, v in out.items()})
 
 
 def make_klt():

@@ -75,3 +75,19 @@ def test_errors(ctx):
         _detect(ctx, np.zeros((8, 8), np.uint8), 10)       # smaller than the patch
     with pytest.raises(VoNativeError):
         _detect(ctx, np.zeros((64, 64), np.uint8), 10, ps=8)  # even patch size
+
+
+def test_match_descriptors(ctx, golden):
+    """GPU matcher vs the reference's cv2.BFMatcher run (golden) and vs the oracle on random 8-bit descriptors."""
+    from vo import _ops
+    g = golden("harris")
+    pairs = _ops.match_descriptors(g["match_desc1"], g["match_desc2"], ctx=ctx)
+    assert np.array_equal(pairs, g["match_pairs"])
+    rng = np.random.default_rng(3)
+    for Q, T, D in [(57, 133, 361), (1000, 1000, 361), (40, 2, 9), (300, 70, 25)]:
+        base = rng.integers(0, 256, (max(Q, T), D))
+        d1 = np.clip(base[:Q] + rng.integers(-6, 7, (Q, D)), 0, 255).astype(np.uint8)
+        d2 = np.clip(base[rng.permutation(max(Q, T))[:T]] + rng.integers(-6, 7, (T, D)), 0, 255).astype(np.uint8)
+        d2[T // 2] = d2[0]                                   # exact duplicates: ties broken by train index
+        got = _ops.match_descriptors(d1, d2, ctx=ctx)
+        assert np.array_equal(got, oracle.match_descriptors(d1, d2)), (Q, T, D)

@@ -124,3 +124,10 @@ def test_triangulation_vs_reference(golden):
         X1 = oracle.triangulate(g[f"{tag}_cand_tracks"], g[f"{tag}_p2"], proj1, proj2, mode=1)
         assert np.allclose(X0, g[f"{tag}_cand_cv0"], rtol=0, atol=1e-9)
         assert np.allclose(X1, g[f"{tag}_cand_cv1"], rtol=1e-7, atol=1e-7)   # cv2's float64 SVD
+
+
+def test_match_descriptors_vs_reference(golden):
+    g = golden("harris")
+    pairs = oracle.match_descriptors(g["match_desc1"], g["match_desc2"])
+    assert np.array_equal(pairs, g["match_pairs"])          # cv2.BFMatcher + the reference's loop
+    assert len(pairs) == int(g["match_n_matched"])

@@ -189,6 +189,35 @@ int vo_harris_descriptors_host(vo_ctx* ctx, const uint8_t* h_img, int H, int W, 
     return VO_OK;
 }
 
+int vo_match_descriptors_dev(vo_ctx* ctx, const uint8_t* d_desc1, const uint8_t* d_desc2, int n_frames, int Q, int T,
+                             int D, double ratio, int32_t* d_pairs, int32_t* d_n_pairs, void* stream) {
+    VO_REQUIRE(ctx && d_desc1 && d_desc2 && d_pairs && d_n_pairs, "vo_match_descriptors_dev: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_launch_match(ctx, d_desc1, d_desc2, n_frames, Q, T, D, ratio, d_pairs, d_n_pairs, pick_stream(ctx, stream));
+}
+
+int vo_match_descriptors_host(vo_ctx* ctx, const uint8_t* h_desc1, const uint8_t* h_desc2, int n_frames, int Q, int T,
+                              int D, double ratio, int32_t* h_pairs, int32_t* h_n_pairs) {
+    VO_REQUIRE(ctx && h_desc1 && h_desc2 && h_pairs && h_n_pairs, "vo_match_descriptors_host: null argument");
+    VO_REQUIRE(n_frames >= 1 && Q >= 1 && T >= 1 && D >= 1, "vo_match_descriptors_host: bad sizes");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t F = n_frames;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_a = carve(F * Q * D), o_b = carve(F * T * D), o_p = carve(F * Q * 8), o_n = carve(F * 4);
+    int rc = vo_buf_reserve(&ctx->scratch[11], off);
+    if (rc) return rc;
+    unsigned char* b = (unsigned char*)ctx->scratch[11].p;
+    VO_CUDA(cudaMemcpyAsync(b + o_a, h_desc1, F * Q * D, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(b + o_b, h_desc2, F * T * D, cudaMemcpyHostToDevice, s));
+    if ((rc = vo_launch_match(ctx, b + o_a, b + o_b, n_frames, Q, T, D, ratio, (int*)(b + o_p), (int*)(b + o_n), s))) return rc;
+    VO_CUDA(cudaMemcpyAsync(h_pairs, b + o_p, F * Q * 8, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_n_pairs, b + o_n, F * 4, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
+    return VO_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // KLT
 // ------------------------------------------------------------------------------------------

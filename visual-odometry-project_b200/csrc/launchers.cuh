@@ -37,3 +37,6 @@ int vo_launch_triangulate(vo_ctx* ctx, const double* d_p1, const double* d_p2, i
                           cudaStream_t stream);
 // harris.cu: int32 (x, y) keypoints -> float32 points (the KLT input format)
 int vo_launch_kp_to_points(vo_ctx* ctx, const int* d_kp_xy, size_t n, float* d_pts, cudaStream_t stream);
+// match.cu
+int vo_launch_match(vo_ctx* ctx, const uint8_t* d_q, const uint8_t* d_t, int n_frames, int Q, int T, int D, double ratio,
+                    int* d_pairs, int* d_n_pairs, cudaStream_t stream);

@@ -66,6 +66,8 @@ def lib():
             "vo_triangulate_host": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp]),
         }
         _optional.update({
+            "vo_match_descriptors_dev": (i32, [vp, vp, vp, i32, i32, i32, i32, dbl, vp, vp, vp]),
+            "vo_match_descriptors_host": (i32, [vp, vp, vp, i32, i32, i32, i32, dbl, vp, vp]),
             "vo_frontend_create": (i32, [vp, vp, C.POINTER(vp)]),
             "vo_frontend_destroy": (None, [vp]),
             "vo_frontend_outputs": (i32, [vp, vp]),

@@ -164,3 +164,21 @@ def harris_descriptors(img, kp_xy, desc_radius=9, ctx=None):
                                               nat.ptr(out))
     nat.check(rc, "vo_harris_descriptors_host")
     return out
+
+
+def match_descriptors(desc1, desc2, ratio=0.85, ctx=None):
+    """matchDescriptor for 8-bit descriptors (harris.py:196-264): (M, 2) int array of (query, train) pairs."""
+    ctx = _ctx(ctx)
+    a = np.ascontiguousarray(desc1, dtype=np.uint8)
+    b = np.ascontiguousarray(desc2, dtype=np.uint8)
+    a = a.reshape(a.shape[0], -1)
+    b = b.reshape(b.shape[0], -1)
+    if a.shape[1] != b.shape[1]:
+        raise ValueError("match_descriptors: descriptor lengths differ")
+    Q, T, D = a.shape[0], b.shape[0], a.shape[1]
+    pairs = np.zeros((Q, 2), dtype=np.int32)
+    n = np.zeros(1, dtype=np.int32)
+    rc = nat.lib().vo_match_descriptors_host(ctx.handle, nat.ptr(a), nat.ptr(b), 1, Q, T, D, C.c_double(ratio),
+                                             nat.ptr(pairs), nat.ptr(n))
+    nat.check(rc, "vo_match_descriptors_host")
+    return pairs[: int(n[0])].astype(np.int64)

@@ -67,18 +67,31 @@ class HarrisCornerDetector:
 
     def matchDescriptor(self, frame1: Frame, frame2: Frame) -> Matches:
         """2-NN brute-force matching with a 0.85 ratio test, one match per train descriptor
-        (harris.py:196-264)."""
+        (harris.py:196-264).  8-bit descriptors (what extractDescriptors produces) are matched on the GPU
+        with exact integer distances; anything else takes the reference's OpenCV path on the host."""
+        d1, d2 = frame1.features.descriptors, frame2.features.descriptors
+        if _is_u8_valued(d1) and _is_u8_valued(d2) and len(d2) >= 2:
+            pairs = _ops.match_descriptors(d1.reshape(len(d1), -1), d2.reshape(len(d2), -1), 0.85)
+            if len(pairs) == 0:
+                pairs = np.empty(shape=(0, 2), dtype=int)
+            return Matches(frame1, frame2, pairs)
         import cv2
-        d1 = frame1.features.descriptors.astype(np.float32)
-        d2 = frame2.features.descriptors.astype(np.float32)
-        used = np.zeros(len(d1))
+        f1, f2 = d1.astype(np.float32), d2.astype(np.float32)
+        used = np.zeros(len(f1))
         good = []
-        for m, n in cv2.BFMatcher().knnMatch(d1, d2, k=2):
+        for m, n in cv2.BFMatcher().knnMatch(f1, f2, k=2):
             if m.distance < 0.85 * n.distance and used[m.trainIdx] == 0:
                 good.append([m.queryIdx, m.trainIdx])
                 used[m.trainIdx] = 1
         pairs = np.stack(good) if len(good) > 0 else np.empty(shape=(0, 2), dtype=int)
         return Matches(frame1, frame2, pairs)
+
+
+def _is_u8_valued(d):
+    d = np.asarray(d)
+    if d.dtype == np.uint8:
+        return True
+    return bool(np.all((d >= 0) & (d <= 255) & (d == np.floor(d))))
 
 
 def _as_u8(image):
