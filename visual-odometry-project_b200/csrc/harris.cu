@@ -321,70 +321,151 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
 // ---------------------------------------------------------------------------------------------
 // NMS step 1: dense local-maximum detection (window radius r, raster-order tie break).
 // ---------------------------------------------------------------------------------------------
-constexpr int LT_W = 64, LT_H = 32, L_THREADS = 256;
+constexpr int L_THREADS = 256;     // 8 warps = 8 adjacent column strips
+constexpr int L_ROWS = 96;         // rows per warp (plus one block row above and below); multiple of 1, 2 and 3
+constexpr int L_CHUNK = 4;         // block rows loaded ahead
 
-// Scores are non-negative doubles, so their bit patterns order like unsigned 64-bit integers.  The tile
-// (+ halo r) is staged as two 32-bit planes; a pixel survives the cheap test if the high word of its
-// score is >= the high words of its 8 neighbours, and the (rare) survivors get the exact
-// (2r+1)^2 test, done by the whole warp (32 window positions per step, early exit by ballot).
+// Scores are non-negative doubles, so their bit patterns order like unsigned 64-bit integers.
+// A warp streams down a strip of 32 columns, one coalesced 256-byte row per load, nothing staged in shared
+// memory.  The strip is cut into BxB blocks (B = 3 for r >= 5): a local maximum of the (2r+1)^2 window must be
+// the maximum of its own block and of the 8 blocks around it (all nine lie inside the window when r >= 2B-1).
+// Block maxima of a 32-bit monotone image of the score (high word) cost one max3 per B rows down the column and
+// four shuffles across it, so the dense pass is a handful of instructions per pixel and rejects all but a
+// fraction of a percent.  Survivors are queued and get the exact (2r+1)^2 test with full keys and the
+// raster-order tie break, done by the whole warp on data that is L1/L2 resident.
+// exact window test, one candidate per lane: window rows from the outside in (a candidate that survived the
+// block test can only lose to the part of the window the nine blocks do not cover), a whole row of loads in
+// flight, early exit per lane
 template <int R>
+__device__ __forceinline__ bool localmax_exact_lane(const double* __restrict__ src, int H, int W, int r_rt, int yc, int xc,
+                                                    unsigned long long ck) {
+    const int r = R > 0 ? R : r_rt;
+    bool ok = true;
+    for (int a = 0; a <= 2 * r && ok; a++) {
+        const int dy = ((a & 1) ? 1 : -1) * (r - (a >> 1));
+        const int y = yc + dy;
+        if (y < 0 || y >= H) continue;
+        const double* row = src + (size_t)y * W + xc;
+        if (R > 0) {
+            unsigned long long qk[2 * R + 1];
+#pragma unroll
+            for (int dx = -R; dx <= R; dx++)
+                qk[dx + R] = (xc + dx >= 0 && xc + dx < W) ? (unsigned long long)__double_as_longlong(__ldg(row + dx)) : 0ull;
+#pragma unroll
+            for (int dx = -R; dx <= R; dx++) {
+                const bool before = (dy < 0) || (dy == 0 && dx < 0);   // raster order: ties go to the earlier pixel
+                if (!(dy == 0 && dx == 0) && (before ? (qk[dx + R] >= ck) : (qk[dx + R] > ck))) ok = false;
+            }
+        } else {
+            for (int dx = -r; dx <= r; dx++) {
+                const unsigned long long qk = (xc + dx >= 0 && xc + dx < W) ? (unsigned long long)__double_as_longlong(__ldg(row + dx)) : 0ull;
+                const bool before = (dy < 0) || (dy == 0 && dx < 0);
+                if (!(dy == 0 && dx == 0) && (before ? (qk >= ck) : (qk > ck))) ok = false;
+            }
+        }
+    }
+    return ok;
+}
+
+template <int R, int B>
 __global__ void __launch_bounds__(L_THREADS)
 harris_localmax(const double* __restrict__ resp, int H, int W, int r_rt, unsigned int lm_cap,
                 unsigned long long* __restrict__ lm_key, unsigned int* __restrict__ lm_idx,
                 unsigned int* __restrict__ lm_count) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int r = R > 0 ? R : r_rt;                   // compile-time radius: the index divisions below become multiplies
-    const int tw = LT_W + 2 * r, th = LT_H + 2 * r;
-    unsigned int* hi = reinterpret_cast<unsigned int*>(smem_raw);
-    unsigned int* lo = hi + tw * th;
-    const int x0 = blockIdx.x * LT_W, y0 = blockIdx.y * LT_H;
+    constexpr unsigned int FULL = 0xFFFFFFFFu;
+    constexpr int NBLK = 32 / B, LANES = NBLK * B, OUT_W = (NBLK - 2) * B;   // the outer blocks are halo
+    __shared__ unsigned int s_queue[L_THREADS / 32][L_CHUNK * B * OUT_W + 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * (L_THREADS / 32) + warp;
+    if (strip * OUT_W >= W) return;                    // warp-uniform
     const int f = blockIdx.z;
     const double* src = resp + (size_t)f * H * W;
-    for (int i = threadIdx.x; i < tw * th; i += L_THREADS) {
-        const int ty = i / tw, tx = i - ty * tw;
-        const int gy = y0 - r + ty, gx = x0 - r + tx;
-        unsigned long long v = 0ull;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = (unsigned long long)__double_as_longlong(src[(size_t)gy * W + gx]);
-        hi[i] = (unsigned int)(v >> 32);
-        lo[i] = (unsigned int)v;
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int win = 2 * r + 1, nwin = win * win;
-    for (int i = threadIdx.x; i < LT_W * LT_H; i += L_THREADS) {   // same trip count for every lane of a warp
-        const int ly = i / LT_W, lx = i - ly * LT_W;
-        const int gy = y0 + ly, gx = x0 + lx;
-        const int c = (ly + r) * tw + (lx + r);
-        const unsigned int ch = hi[c];
-        bool cand = (gy < H && gx < W) && ((ch | lo[c]) != 0u);
-        if (cand && r >= 1) {
-            const unsigned int m0 = max(max(hi[c - tw - 1], hi[c - tw]), max(hi[c - tw + 1], hi[c - 1]));
-            const unsigned int m1 = max(max(hi[c + 1], hi[c + tw - 1]), max(hi[c + tw], hi[c + tw + 1]));
-            cand = ch >= max(m0, m1);
-        }
-        unsigned int mask = __ballot_sync(0xFFFFFFFFu, cand);
-        while (mask) {
-            const int src_lane = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const int cc = __shfl_sync(0xFFFFFFFFu, c, src_lane);
-            const unsigned long long ck = ((unsigned long long)hi[cc] << 32) | lo[cc];
-            bool fail = false;
-            for (int j = lane; j < nwin; j += 32) {
-                const int dy = j / win - r, dx = j - (j / win) * win - r;
-                if (dy == 0 && dx == 0) continue;
-                const int q = cc + dy * tw + dx;
-                const unsigned long long qk = ((unsigned long long)hi[q] << 32) | lo[q];
-                const bool before = (dy < 0) || (dy == 0 && dx < 0);   // raster order: ties go to the earlier pixel
-                if (before ? (qk >= ck) : (qk > ck)) fail = true;
+    const int xs = strip * OUT_W - B + lane;
+    const bool col_in = lane < LANES && xs >= 0 && xs < W;
+    const bool decides = lane >= B && lane < LANES - B && xs < W;
+    const int leader = lane - lane % B;
+    const bool reject = (R > 0 ? R : r_rt) >= 2 * B - 1;   // the nine blocks lie inside the window (false only for r = 0)
+    const int y0 = blockIdx.y * L_ROWS, y1 = min(H, y0 + L_ROWS);
+    const int n_brows = (y1 - y0 + B - 1) / B + 2;     // block row k covers rows y0 - B + k*B ...
+    unsigned int* queue = s_queue[warp];
+    int n_q = 0;
+    unsigned int nb1 = 0u, nb2 = 0u;                   // 3-block row maxima of the two previous block rows
+    unsigned int gprev[B];
+#pragma unroll
+    for (int i = 0; i < B; i++) gprev[i] = 0u;
+    for (int k0 = 0; k0 < n_brows; k0 += L_CHUNK) {
+        unsigned long long v[L_CHUNK * B];
+        const int yf = y0 - B + k0 * B;                // first row of the chunk
+        if (yf >= 0 && yf + L_CHUNK * B <= H && k0 + L_CHUNK <= n_brows) {   // interior chunk: no per-row tests
+            const double* pr = src + (yf * W + xs);    // running row pointer: one 64-bit add per load
+#pragma unroll
+            for (int j = 0; j < L_CHUNK * B; j++) {
+                v[j] = col_in ? (unsigned long long)__double_as_longlong(__ldg(pr)) : 0ull;
+                pr += W;
             }
-            const bool is_lm = !__any_sync(0xFFFFFFFFu, fail);
-            if (is_lm && lane == src_lane) {
-                const unsigned int slot = atomicAdd(&lm_count[f], 1u);
-                if (slot < lm_cap) {
-                    lm_key[(size_t)f * lm_cap + slot] = ck;
-                    lm_idx[(size_t)f * lm_cap + slot] = (unsigned int)(gy * W + gx);
+        } else {
+#pragma unroll
+            for (int j = 0; j < L_CHUNK * B; j++) {
+                const int y = yf + j;
+                v[j] = 0ull;
+                if (k0 + j / B < n_brows && y >= 0 && y < H && col_in)
+                    v[j] = (unsigned long long)__double_as_longlong(__ldg(src + (y * W + xs)));
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < L_CHUNK; c++) {
+            if (k0 + c >= n_brows) break;              // warp-uniform
+            unsigned int g[B];
+            unsigned int cm = 0u;
+#pragma unroll
+            for (int i = 0; i < B; i++) {
+                // ceil(key / 2^32): a 32-bit monotone image of the key that is zero only for a zero key
+                g[i] = (unsigned int)((v[c * B + i] + 0xFFFFFFFFull) >> 32);
+                cm = max(cm, g[i]);
+            }
+            unsigned int t = cm;                       // block maximum, valid on the block's first lane
+#pragma unroll
+            for (int d = 1; d < B; d++) t = max(t, __shfl_down_sync(FULL, cm, d));
+            const unsigned int nb = max(t, max(__shfl_up_sync(FULL, t, B), __shfl_down_sync(FULL, t, B)));
+            const unsigned int m9 = __shfl_sync(FULL, max(nb, max(nb1, nb2)), leader);   // 3x3 blocks around block row k-1
+            // m9 >= every gprev[i], so equality means "not beaten by the nine blocks".  Cheap test first; the
+            // exact candidate bits (with the segment's row range) only when some lane has a hit.
+            bool hit = false;
+#pragma unroll
+            for (int i = 0; i < B; i++) hit = hit || (reject ? (gprev[i] == m9) : (gprev[i] != 0u));
+            hit = hit && decides && (m9 != 0u || !reject);
+            if (__any_sync(FULL, hit)) {
+                const int yp = yf + (c - 1) * B;       // first row of the block row being decided
+#pragma unroll
+                for (int i = 0; i < B; i++) {
+                    const bool cnd = hit && yp + i >= y0 && yp + i < y1 && (reject ? (gprev[i] == m9) : (gprev[i] != 0u));
+                    const unsigned int mask = __ballot_sync(FULL, cnd);
+                    if (cnd) queue[n_q + __popc(mask & ((1u << lane) - 1u))] = (unsigned int)((yp + i) * W + xs);
+                    n_q += __popc(mask);
                 }
             }
+            nb2 = nb1; nb1 = nb;
+#pragma unroll
+            for (int i = 0; i < B; i++) gprev[i] = g[i];
+        }
+        __syncwarp();
+        const bool last = k0 + L_CHUNK >= n_brows;
+        while (n_q >= 32 || (last && n_q > 0)) {       // batches of 32 queued candidates, one per lane
+            const int m = min(32, n_q);
+            n_q -= m;
+            if (lane < m) {
+                const unsigned int p = queue[n_q + lane];
+                const int yc = (int)(p / (unsigned)W), xc = (int)(p - (unsigned)yc * W);
+                const unsigned long long k = (unsigned long long)__double_as_longlong(__ldg(src + p));
+                if (localmax_exact_lane<R>(src, H, W, r_rt, yc, xc, k)) {
+                    const unsigned int slot = atomicAdd(&lm_count[f], 1u);
+                    if (slot < lm_cap) {
+                        lm_key[(size_t)f * lm_cap + slot] = k;
+                        lm_idx[(size_t)f * lm_cap + slot] = p;
+                    }
+                }
+            }
+            __syncwarp();
         }
     }
 }
@@ -1005,23 +1086,23 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     VO_CUDA(cudaMemsetAsync(base + o_cnt, 0, F * 4, stream));
     VO_CUDA(cudaMemsetAsync(base + o_state, 0, F * npx, stream));
 
-    const size_t smem_lm = (size_t)(LT_W + 2 * radius) * (LT_H + 2 * radius) * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        VO_CUDA(cudaFuncSetAttribute(harris_localmax<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        VO_CUDA(cudaFuncSetAttribute(harris_localmax<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         VO_CUDA(cudaFuncSetAttribute(harris_nms_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    dim3 g1(vo_div_up(W, LT_W), vo_div_up(H, LT_H), n_frames);
-    if (radius == 5)
-        harris_localmax<5><<<g1, L_THREADS, smem_lm, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap,
-                                                               (unsigned long long*)(base + o_lmk),
-                                                               (unsigned int*)(base + o_lmi), (unsigned int*)(base + o_cnt));
-    else
-        harris_localmax<0><<<g1, L_THREADS, smem_lm, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap,
-                                                               (unsigned long long*)(base + o_lmk),
-                                                               (unsigned int*)(base + o_lmi), (unsigned int*)(base + o_cnt));
+    {
+        unsigned long long* lmk = (unsigned long long*)(base + o_lmk);
+        unsigned int* lmi = (unsigned int*)(base + o_lmi);
+        unsigned int* lmc = (unsigned int*)(base + o_cnt);
+        const int bs = radius >= 5 ? 3 : (radius >= 3 ? 2 : 1);      // block size: the 3x3 blocks must fit the window
+        const int out_w = (32 / bs - 2) * bs;
+        dim3 g1(vo_div_up(vo_div_up(W, out_w), L_THREADS / 32), vo_div_up(H, L_ROWS), n_frames);
+        if (radius == 5) harris_localmax<5, 3><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc);
+        else if (bs == 3) harris_localmax<0, 3><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc);
+        else if (bs == 2) harris_localmax<0, 2><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc);
+        else harris_localmax<0, 1><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc);
+    }
     ctx->launches++;
     VO_CHECK_LAUNCH();
     NmsArgs a;
