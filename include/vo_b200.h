@@ -46,7 +46,7 @@ int vo_harris_response_dev(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int 
                            size_t frame_stride, int patch_size, double kappa, double* d_resp, void* stream);
 /* harris.py:139-152  greedy non-maximum suppression -> int32 [n_frames][num_keypoints][2] = (x, y),
  * in the reference's selection order.  d_stats (optional, may be NULL): uint32 [n_frames][4] =
- * {local maxima, alive after round 0, rounds, picks}.                                           */
+ * {local maxima, entries above the threshold outside all boxes, rounds, picks}.                  */
 int vo_harris_nms_dev(vo_ctx* ctx, const double* d_resp, int n_frames, int H, int W, int nms_radius,
                       int num_keypoints, int32_t* d_kp_xy, uint32_t* d_stats, void* stream);
 /* harris.py:86-158  HarrisCornerDetector.extractKeypoints = response + NMS.                     */

@@ -91,3 +91,53 @@ def test_match_descriptors(ctx, golden):
         d2[T // 2] = d2[0]                                   # exact duplicates: ties broken by train index
         got = _ops.match_descriptors(d1, d2, ctx=ctx)
         assert np.array_equal(got, oracle.match_descriptors(d1, d2)), (Q, T, D)
+
+
+def _nms_dev(ctx, resp, K, r):
+    import ctypes as C
+    import torch
+    from vo import _native as nat
+    a = np.ascontiguousarray(resp, np.float64)
+    if a.ndim == 2:
+        a = a[None]
+    F, H, W = a.shape
+    d = torch.from_numpy(a).cuda()
+    kp = torch.empty((F, K, 2), dtype=torch.int32, device="cuda")
+    st = torch.zeros((F, 4), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    nat.check(nat.lib().vo_harris_nms_dev(ctx.handle, d.data_ptr(), F, H, W, r, K, kp.data_ptr(), st.data_ptr(), None), "nms")
+    ctx.synchronize()
+    return kp.cpu().numpy(), st.cpu().numpy()
+
+
+@pytest.mark.parametrize("r", [0, 1, 2, 3, 4, 5, 7])
+def test_nms_arbitrary_maps(ctx, r):
+    """vo_harris_nms_dev on score maps that do not come from the response kernel: plateaus (ties), huge dynamic
+    range, denormals, fewer local maxima than K -- against the literal argmax loop."""
+    rng = np.random.default_rng(100 + r)
+    H, W = 90, 140
+    maps = []
+    m = rng.random((H, W)) * (rng.random((H, W)) > 0.3)
+    maps.append((m, 200))
+    maps.append((rng.integers(0, 4, (H, W)).astype(np.float64), 150))          # plateaus: ties everywhere
+    maps.append((10.0 ** rng.uniform(-200, 200, (H, W)) * (rng.random((H, W)) > 0.5), 300))
+    maps.append((rng.integers(0, 50, (H, W)).astype(np.float64) * 5e-324, 100))  # denormals: high word is zero
+    yy, xx = np.mgrid[0:H, 0:W]
+    maps.append((np.exp(-((yy - 40) ** 2 + (xx - 60) ** 2) / 300.0) + 0.5 * np.exp(-((yy - 70) ** 2 + (xx - 20) ** 2) / 80.0), 120))
+    maps.append((np.full((H, W), 3.0), 40))                                    # one plateau
+    for i, (m, K) in enumerate(maps):
+        if r == 0 and i in (1, 5):
+            K = 30
+        kp, _ = _nms_dev(ctx, m, K, r)
+        assert np.array_equal(kp[0], oracle.harris_nms(np.ascontiguousarray(m), K, r)), (r, i)
+
+
+def test_nms_large_frame_global_bitmaps(ctx):
+    """a frame whose two bitmaps do not fit in shared memory takes the global-memory bitmaps"""
+    rng = np.random.default_rng(5)
+    H, W = 1000, 1900
+    m = rng.random((H, W)) ** 8
+    from scipy.ndimage import uniform_filter
+    m = uniform_filter(m, 7) * (rng.random((H, W)) > 0.2)
+    kp, st = _nms_dev(ctx, m, 700, 5)
+    assert np.array_equal(kp[0], oracle.harris_nms(np.ascontiguousarray(m), 700, 5))

@@ -554,34 +554,39 @@ struct NmsArgs {
     const unsigned long long* lm_key;  // [F][lm_cap]
     const unsigned int* lm_idx;
     const unsigned int* lm_count;      // [F]
-    unsigned char* state;              // [F][H*W]  0 alive/unknown, 1 suppressed, 2 picked
-    uint4* alive_a;                    // [F][H*W] {pixel, blocker, key lo, key hi}
-    uint4* alive_b;                    // [F][H*W]
+    unsigned int* sup;                 // [F][bm_words] bitmap: pixel lies in the box of a pick
+    unsigned int* mem;                 // [F][bm_words] bitmap: undecided entry of the current band (global fallback only)
+    unsigned int bm_words;             // words per frame bitmap (H*W/32 + 2: the range helpers read one word ahead)
+    uint4* ent_a;                      // [F][H*W] entries {pixel, key lo, key hi, -} in scan order
+    uint4* ent_b;                      // [F][H*W] the same entries ordered by priority bin
     unsigned long long* pick_key;      // [F][lm_cap]
     unsigned int* pick_idx;            // [F][lm_cap]
-    unsigned int* new_idx;             // [F][lm_cap]
     int* kp_xy;                        // [F][K][2]
-    unsigned int* stats;               // [F][4]: n_lm, n_alive0, n_rounds, n_picks
+    unsigned int* stats;               // [F][4]: n_lm, n_entries, n_rounds, n_picks
     unsigned long long* thr_key;       // [F] threshold (score bits)
     unsigned int* thr_idx;             // [F] threshold (tie-break index)
-    unsigned int* counters;            // [F][4]: alive count, picks count
+    unsigned int* counters;            // [F][4]: entries, picks, min / max high word of the entries' keys
+    int bitmaps_in_smem;
 };
 
-// warp-cooperative: suppress the (2r+1)^2 box around p (state 1) and flag p itself as picked (state 2)
-__device__ __forceinline__ void mark_window_warp(unsigned char* st, int H, int W, int r, unsigned int p, int lane) {
-    const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
-    const int win = 2 * r + 1;
-    for (int j = lane; j < win * win; j += 32) {
-        const int y = py + j / win - r, x = px + j % win - r;
-        if (y >= 0 && y < H && x >= 0 && x < W) st[y * W + x] = (y == py && x == px) ? 2 : 1;
-    }
+// ---- bitmaps: bit p = pixel p (row-major, no row padding) ----
+__device__ __forceinline__ bool bm_test(const unsigned int* bm, unsigned int p) { return (bm[p >> 5] >> (p & 31u)) & 1u; }
+// set bits [b0, b0 + len), 1 <= len <= 31
+__device__ __forceinline__ void bm_set_range(unsigned int* bm, unsigned int b0, int len) {
+    const unsigned long long m = ((1ull << len) - 1ull) << (b0 & 31u);
+    atomicOr(&bm[b0 >> 5], (unsigned int)m);
+    if (m >> 32) atomicOr(&bm[(b0 >> 5) + 1], (unsigned int)(m >> 32));
+}
+// bits [b0, b0 + len) as the low bits of a word, 1 <= len <= 31
+__device__ __forceinline__ unsigned int bm_get_range(const unsigned int* bm, unsigned int b0, int len) {
+    const unsigned int w = b0 >> 5;
+    return __funnelshift_r(bm[w], bm[w + 1], b0 & 31u) & ((1u << len) - 1u);
 }
 
-constexpr int NMS_MAX_WIN = 31 * 31;
 constexpr int NMS_SELECT_SMEM = 3584;   // local maxima staged in shared memory for the threshold select (42 KB)
 
-// ---- NMS step 2 (one CTA per frame): threshold = K-th best local maximum; maxima above it are picks and
-// ---- suppress their windows.
+// ---- NMS step 2 (one CTA per frame): threshold = K-th best local maximum; the maxima at or above it are picks
+// ---- (a local maximum beats its whole window, so nothing can suppress it) and their boxes go into the bitmap.
 __global__ void __launch_bounds__(N_THREADS)
 harris_nms_select(NmsArgs a) {
     __shared__ unsigned int hist[256];
@@ -589,18 +594,17 @@ harris_nms_select(NmsArgs a) {
     __shared__ unsigned int s_np;
     const int f = blockIdx.x;
     const int H = a.H, W = a.W, r = a.r, K = a.K;
-    const unsigned int npx = (unsigned int)H * W;
     const unsigned long long* lmk = a.lm_key + (size_t)f * a.lm_cap;
     const unsigned int* lmi = a.lm_idx + (size_t)f * a.lm_cap;
-    unsigned char* st = a.state + (size_t)f * npx;            // zeroed by the launcher
+    unsigned int* sup = a.sup + (size_t)f * a.bm_words;       // zeroed by the launcher
     unsigned long long* pk = a.pick_key + (size_t)f * a.lm_cap;
     unsigned int* pi = a.pick_idx + (size_t)f * a.lm_cap;
     const unsigned int n_lm = min(a.lm_count[f], a.lm_cap);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     unsigned long long tk = 1ull;                             // "every positive score"
     unsigned int ti = 0xFFFFFFFFu;
-    // the list of local maxima is staged in shared memory when it fits: the 12 radix passes and the marking
-    // loop then run at shared-memory latency instead of one dependent global load per step
+    // the list of local maxima is staged in shared memory when it fits: the 12 radix passes then run at
+    // shared-memory latency instead of one dependent global load per step
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned long long* kk = lmk;
     const unsigned int* ii = lmi;
@@ -613,60 +617,69 @@ harris_nms_select(NmsArgs a) {
     if (tid == 0) s_np = 0;
     __syncthreads();
     if (n_lm >= (unsigned)K && K > 0) block_select_kth(kk, ii, n_lm, (unsigned)K, hist, s_misc, &tk, &ti);
-    for (unsigned int j = warp; j < n_lm; j += N_THREADS / 32) {
+    for (unsigned int j = tid; j < n_lm; j += N_THREADS) {
         const unsigned long long k = kk[j];
         const unsigned int i = ii[j];
         if (prio_ge(k, i, tk, ti)) {
-            if (lane == 0) {
-                const unsigned int s = atomicAdd(&s_np, 1u);
-                pk[s] = k; pi[s] = i;
-            }
-            mark_window_warp(st, H, W, r, i, lane);
+            const unsigned int s = atomicAdd(&s_np, 1u);
+            pk[s] = k; pi[s] = i;
         }
     }
     __syncthreads();
+    const unsigned int n_p = s_np;
+    const int win = 2 * r + 1;
+    for (unsigned int it = tid; it < n_p * (unsigned)win; it += N_THREADS) {   // one box row per thread
+        const unsigned int j = it / (unsigned)win;
+        const int dy = (int)(it - j * (unsigned)win) - r;
+        const unsigned int p = pi[j];
+        const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
+        const int y = py + dy;
+        if (y < 0 || y >= H) continue;
+        const int x0 = max(px - r, 0), x1 = min(px + r, W - 1);
+        bm_set_range(sup, (unsigned int)(y * W + x0), x1 - x0 + 1);
+    }
     if (tid == 0) {
         a.thr_key[f] = tk; a.thr_idx[f] = ti;
-        a.counters[f * 4 + 0] = 0;        // alive count (filled by the scan)
-        a.counters[f * 4 + 1] = s_np;     // picks so far
+        a.counters[f * 4 + 0] = 0;               // entries (filled by the scan)
+        a.counters[f * 4 + 1] = n_p;             // picks so far
+        a.counters[f * 4 + 2] = 0xFFFFFFFFu;     // min / max high word of the entries' keys
+        a.counters[f * 4 + 3] = 0u;
     }
 }
 
-// ---- NMS step 3 (grid-wide, HBM speed): alive = score at or above the threshold and not suppressed.
+// ---- NMS step 3 (grid-wide, one read of the score map): entries = pixels at or above the threshold outside
+// ---- every box.  Only these can still become picks.
 constexpr int SCAN_PER_THREAD = 8;
-constexpr unsigned int NMS_NONE = 0xFFFFFFFFu;
 
-// An alive-list entry is {pixel, blocker, score bits lo, hi}: blocker = a neighbour that is alive and has higher
-// priority (the pixel cannot be picked while that neighbour is alive), or NMS_NONE.
 __global__ void __launch_bounds__(256)
 harris_nms_scan(NmsArgs a) {
-    __shared__ unsigned int s_total, s_base;
-    __shared__ unsigned int s_warp[8];
-    __shared__ unsigned int s_p[256 * SCAN_PER_THREAD];
-    __shared__ unsigned long long s_k[256 * SCAN_PER_THREAD];
+    __shared__ unsigned int s_base;
+    __shared__ unsigned int s_warp[8], s_min[8], s_max[8];
     const int f = blockIdx.y;
-    const int H = a.H, W = a.W;
-    const unsigned int npx = (unsigned int)H * W;
+    const unsigned int npx = (unsigned int)a.H * a.W;
     const double* resp = a.resp + (size_t)f * npx;
-    const unsigned char* st = a.state + (size_t)f * npx;
-    uint4* alive = a.alive_a + (size_t)f * npx;
+    const unsigned int* sup = a.sup + (size_t)f * a.bm_words;
+    uint4* ent = a.ent_a + (size_t)f * npx;
     const unsigned long long tk = a.thr_key[f];
     const unsigned int ti = a.thr_idx[f];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int base = blockIdx.x * (256u * SCAN_PER_THREAD) + threadIdx.x;
     unsigned long long k[SCAN_PER_THREAD];
-    unsigned char s8[SCAN_PER_THREAD];
+    unsigned int sw[SCAN_PER_THREAD];
 #pragma unroll
-    for (int j = 0; j < SCAN_PER_THREAD; j++) {            // all loads first (coalesced, 8 in flight per thread)
+    for (int j = 0; j < SCAN_PER_THREAD; j++) {            // all loads first (coalesced, 16 in flight per thread)
         const unsigned int p = base + j * 256u;
-        k[j] = p < npx ? (unsigned long long)__double_as_longlong(resp[p]) : 0ull;
-        s8[j] = p < npx ? st[p] : (unsigned char)1;
+        k[j] = p < npx ? (unsigned long long)__double_as_longlong(__ldg(resp + p)) : 0ull;
+        sw[j] = p < npx ? __ldg(sup + (p >> 5)) : 0xFFFFFFFFu;
     }
-    unsigned int keep_mask = 0, cnt = 0;
+    unsigned int keep_mask = 0, cnt = 0, hmin = 0xFFFFFFFFu, hmax = 0u;
 #pragma unroll
     for (int j = 0; j < SCAN_PER_THREAD; j++) {
         const unsigned int p = base + j * 256u;
-        if (k[j] != 0ull && s8[j] == 0 && prio_ge(k[j], p, tk, ti)) { keep_mask |= 1u << j; cnt++; }
+        if (k[j] != 0ull && !((sw[j] >> (p & 31u)) & 1u) && prio_ge(k[j], p, tk, ti)) {
+            keep_mask |= 1u << j; cnt++;
+            hmin = min(hmin, (unsigned int)(k[j] >> 32)); hmax = max(hmax, (unsigned int)(k[j] >> 32));
+        }
     }
     // block-wide exclusive offsets: warp scan, then one global atomic per CTA
     unsigned int incl = cnt;
@@ -675,238 +688,218 @@ harris_nms_scan(NmsArgs a) {
         const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= o) incl += v;
     }
+    hmin = __reduce_min_sync(0xFFFFFFFFu, hmin);
+    hmax = __reduce_max_sync(0xFFFFFFFFu, hmax);
     if (lane == 31) s_warp[warp] = incl;
+    if (lane == 0) { s_min[warp] = hmin; s_max[warp] = hmax; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int t = 0;
-        for (int w = 0; w < 8; w++) { const unsigned int c = s_warp[w]; s_warp[w] = t; t += c; }
-        s_total = t;
-        s_base = t ? atomicAdd(&a.counters[f * 4 + 0], t) : 0u;
-    }
-    __syncthreads();
-    // compact the kept pixels of this CTA (position + score bits) so that the 8-neighbour test below runs with
-    // dense lanes instead of once per sparse (thread, j) slot
-    const unsigned int total = s_total;
-    {
-        unsigned int o = s_warp[warp] + incl - cnt;
-#pragma unroll
-        for (int j = 0; j < SCAN_PER_THREAD; j++)
-            if (keep_mask & (1u << j)) { s_p[o] = base + j * 256u; s_k[o] = k[j]; o++; }
-    }
-    __syncthreads();
-    for (unsigned int t = threadIdx.x; t < total; t += 256u) {
-        const unsigned int p = s_p[t];
-        const unsigned long long kp = s_k[t];
-        const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
-        unsigned long long kq[8];
-        unsigned char sq[8];
-        unsigned int qi[8];
-#pragma unroll
-        for (int n = 0; n < 8; n++) {                      // the 8-neighbourhood, loads first
-            const int dy = (n < 3) ? -1 : (n < 6) ? 1 : 0;
-            const int dx = (n < 6) ? (n % 3) - 1 : (n == 6 ? -1 : 1);
-            const int y = py + dy, x = px + dx;
-            kq[n] = 0ull; sq[n] = 1; qi[n] = 0;
-            if (a.r >= 1 && y >= 0 && y < H && x >= 0 && x < W) {
-                qi[n] = (unsigned int)(y * W + x);
-                sq[n] = st[qi[n]];
-                kq[n] = (unsigned long long)__double_as_longlong(resp[qi[n]]);
-            }
+        unsigned int t = 0, mn = 0xFFFFFFFFu, mx = 0u;
+        for (int w = 0; w < 8; w++) {
+            const unsigned int c = s_warp[w]; s_warp[w] = t; t += c;
+            mn = min(mn, s_min[w]); mx = max(mx, s_max[w]);
         }
-        unsigned int blocker = NMS_NONE;
-#pragma unroll
-        for (int n = 0; n < 8; n++)
-            if (sq[n] == 0 && prio_gt(kq[n], qi[n], kp, p)) blocker = qi[n];
-        alive[s_base + t] = make_uint4(p, blocker, (unsigned int)kp, (unsigned int)(kp >> 32));
+        s_base = t ? atomicAdd(&a.counters[f * 4 + 0], t) : 0u;
+        if (t) { atomicMin(&a.counters[f * 4 + 2], mn); atomicMax(&a.counters[f * 4 + 3], mx); }
     }
+    __syncthreads();
+    unsigned int o = s_base + s_warp[warp] + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < SCAN_PER_THREAD; j++)
+        if (keep_mask & (1u << j)) ent[o++] = make_uint4(base + j * 256u, (unsigned int)k[j], (unsigned int)(k[j] >> 32), 0u);
 }
 
-// ---- NMS step 4 (one CTA per frame): rounds + final selection.
-// A round: entries whose blocker is still alive are kept without further work; the others are re-tested,
-// rings 1-2 by one lane per candidate (all loads issued up front), rings 3..r by a whole warp for the
-// few that are 5x5 maxima among the alive.  Unbeaten candidates become picks and suppress their window.
-// Candidates that fall below the (tightening) threshold are dropped and flagged dead, so nothing stays
-// blocked behind them.
-constexpr int NMS_SMEM_PICKS = 4096;   // picks mirrored in shared memory for the per-round threshold selects
+// ---- NMS step 4 (one CTA per frame): the entries are ordered into priority bins (high word of the score, 2048
+// ---- bins over the frame's range) and the bins are processed from the top in bands of about a thousand
+// ---- entries.  When a band starts, everything of higher priority is decided, so an entry competes only with
+// ---- the undecided entries of its own band: it becomes a pick as soon as none of them with higher priority
+// ---- lies in its window.  "Suppressed" and "undecided member of this band" are two bitmaps in shared memory,
+// ---- so a window test is 2r+1 funnel shifts and a score load only for the rare neighbour found.  The loop
+// ---- stops when the picks decided so far (local maxima + band picks down to the current bin) number K.
+constexpr int NMS_BINS = 2048;
+constexpr int NMS_BAND = 1024;       // entries per band (one per thread)
+constexpr int NMS_NEW_CAP = 1024;    // new picks per round (the surplus waits for the next round)
 
 __global__ void __launch_bounds__(N_THREADS)
-harris_nms_frame(NmsArgs a) {
+harris_nms_bands(NmsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ unsigned int hist[256];
     __shared__ unsigned int s_misc[4];
-    __shared__ unsigned int s_cnt[4];          // 0: survivors, 1: picks, 2: new picks, 3: next alive
-    __shared__ signed char s_wdy[NMS_MAX_WIN], s_wdx[NMS_MAX_WIN];   // window offsets, nearest ring first
+    __shared__ unsigned int s_cnt[8];          // 0/1: new picks, 2/3: blocked (double buffered by round), 4: picks, 5: gather
+    __shared__ unsigned int s_ws[32], s_wl[32];
     const int f = blockIdx.x;
     const int H = a.H, W = a.W, r = a.r, K = a.K;
     const unsigned int npx = (unsigned int)H * W;
     const double* resp = a.resp + (size_t)f * npx;
-    unsigned char* st = a.state + (size_t)f * npx;
-    uint4* alive = a.alive_a + (size_t)f * npx;
-    uint4* alive_next = a.alive_b + (size_t)f * npx;
+    const uint4* ent_a = a.ent_a + (size_t)f * npx;
+    uint4* ent_b = a.ent_b + (size_t)f * npx;
     unsigned long long* pk = a.pick_key + (size_t)f * a.lm_cap;
     unsigned int* pi = a.pick_idx + (size_t)f * a.lm_cap;
-    unsigned int* newp = a.new_idx + (size_t)f * a.lm_cap;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int N_WARPS = N_THREADS / 32;
-    const int win = 2 * r + 1, nwin = win * win, nnb = nwin - 1;
-    // shared-memory mirror of the picks (keys then indices); the final sort reuses the same storage
-    unsigned int P2 = 1;
-    while (P2 < (unsigned)max(K, 1)) P2 <<= 1;
-    const unsigned int cap_s = max(P2, (unsigned)NMS_SMEM_PICKS);
-    unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);
-    unsigned int* si = reinterpret_cast<unsigned int*>(sk + cap_s);
+    const int win = 2 * r + 1;
 
-    for (int j = tid; j < nwin; j += N_THREADS) {
-        const int dy = j / win - r, dx = j % win - r;
-        const int rho = max(abs(dy), abs(dx));
-        if (rho == 0) continue;
-        int local;
-        if (dy == -rho) local = dx + rho;
-        else if (dy == rho) local = 2 * rho + 1 + dx + rho;
-        else if (dx == -rho) local = 4 * rho + 2 + (dy + rho - 1);
-        else local = 4 * rho + 2 + (2 * rho - 1) + (dy + rho - 1);
-        const int slot = (2 * rho - 1) * (2 * rho - 1) - 1 + local;
-        s_wdy[slot] = (signed char)dy;
-        s_wdx[slot] = (signed char)dx;
+    unsigned int* endR = reinterpret_cast<unsigned int*>(smem_raw);   // [BINS] entries with rank <= R (rank 0 = top bin)
+    unsigned int* cur = endR + NMS_BINS;                              // [BINS] scatter cursors
+    unsigned int* lmR = cur + NMS_BINS;                               // [BINS] local-maximum picks with rank <= R
+    unsigned int* newp = lmR + NMS_BINS;                              // [NEW_CAP]
+    unsigned int* S = a.sup + (size_t)f * a.bm_words;
+    unsigned int* M = a.mem ? a.mem + (size_t)f * a.bm_words : nullptr;
+    if (a.bitmaps_in_smem) {
+        unsigned int* gs = S;
+        S = newp + NMS_NEW_CAP;
+        M = S + a.bm_words;
+        for (unsigned int w = tid; w < a.bm_words; w += N_THREADS) { S[w] = gs[w]; M[w] = 0u; }
     }
-    unsigned long long tk = a.thr_key[f];
-    unsigned int ti = a.thr_idx[f];
-    unsigned int n_alive = a.counters[f * 4 + 0];
-    const unsigned int n_picks0 = a.counters[f * 4 + 1];
-    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = n_picks0; s_cnt[2] = 0; s_cnt[3] = 0; }
-    for (unsigned int j = tid; j < min(n_picks0, cap_s); j += N_THREADS) { sk[j] = pk[j]; si[j] = pi[j]; }
+    const unsigned int n = a.counters[f * 4 + 0];
+    const unsigned int n_p0 = a.counters[f * 4 + 1];
+    const unsigned int gmin = a.counters[f * 4 + 2], gmax = a.counters[f * 4 + 3];
     const unsigned int n_lm = min(a.lm_count[f], a.lm_cap);
-    const unsigned int n_alive0 = n_alive;
-    unsigned int rounds = 0;
+    for (int j = tid; j < NMS_BINS; j += N_THREADS) { endR[j] = 0u; lmR[j] = 0u; }
+    if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0; s_cnt[4] = n_p0; s_cnt[5] = 0; }
     __syncthreads();
-    const int n_lane = min(24, nnb);           // rings 1-2: tested by one lane per candidate
-    while (n_alive > 0) {
-        // every pick found so far is a pick of the reference; with >= K of them, nothing below the K-th
-        // best can be among the first K any more: tighten the threshold and let the alive list shrink.
-        const unsigned int n_picks_now = s_cnt[1];
-        if (n_picks_now > (unsigned)K) {
-            if (n_picks_now <= cap_s) block_select_kth(sk, si, n_picks_now, (unsigned)K, hist, s_misc, &tk, &ti);
-            else block_select_kth(pk, pi, n_picks_now, (unsigned)K, hist, s_misc, &tk, &ti);
+    unsigned int rounds = 0;
+    if (n > 0) {
+        int shift = 0;
+        while (((gmax - gmin) >> shift) >= (unsigned)NMS_BINS) shift++;
+        // ---- counting sort of the entries by bin rank ----
+        for (unsigned int j = tid; j < n; j += N_THREADS) atomicAdd(&endR[(gmax - ent_a[j].z) >> shift], 1u);
+        for (unsigned int j = tid; j < n_p0; j += N_THREADS) {
+            const unsigned int h = (unsigned int)(pk[j] >> 32);
+            const unsigned int rk = h >= gmax ? 0u : (gmax - h) >> shift;
+            if (rk < (unsigned)NMS_BINS) atomicAdd(&lmR[rk], 1u);       // below every entry: never needed
         }
-        // pass A: one entry per lane
-        const unsigned int n_round = (n_alive + 31u) & ~31u;
-        for (unsigned int j = tid; j < n_round; j += N_THREADS) {
-            const bool valid = j < n_alive;
-            const uint4 e = valid ? alive[j] : make_uint4(0u, NMS_NONE, 0u, 0u);
-            const unsigned int p = e.x;
-            const unsigned long long k = ((unsigned long long)e.w << 32) | e.z;
-            const unsigned char sp = valid ? st[p] : (unsigned char)1;
-            const unsigned char sb = (valid && e.y != NMS_NONE) ? st[e.y] : (unsigned char)1;
-            bool live = valid && sp == 0;
-            if (live && !prio_ge(k, p, tk, ti)) { st[p] = 1; live = false; }   // below the threshold: irrelevant from now on
-            const bool blocked = live && sb == 0;          // its blocker is still alive: nothing to do
-            const bool test = live && !blocked;
-            const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
-            unsigned int blocker = blocked ? e.y : NMS_NONE;
-            for (int c0 = 0; c0 < n_lane && test && blocker == NMS_NONE; c0 += 8) {
-                unsigned long long kq[8];
-                unsigned char sq[8];
-                unsigned int qi[8];
+        __syncthreads();
+        {   // inclusive scans over the 2048 ranks, two per thread
+            const unsigned int a0 = endR[2 * tid], a1 = endR[2 * tid + 1];
+            const unsigned int l0 = lmR[2 * tid], l1 = lmR[2 * tid + 1];
+            unsigned int sa = a0 + a1, sl = l0 + l1;
 #pragma unroll
-                for (int n = 0; n < 8; n++) {
-                    kq[n] = 0ull; sq[n] = 1; qi[n] = 0;
-                    if (c0 + n < n_lane) {
-                        const int y = py + s_wdy[c0 + n], x = px + s_wdx[c0 + n];
-                        if (y >= 0 && y < H && x >= 0 && x < W) {
-                            qi[n] = (unsigned int)(y * W + x);
-                            sq[n] = st[qi[n]];
-                            kq[n] = (unsigned long long)__double_as_longlong(resp[qi[n]]);
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int va = __shfl_up_sync(0xFFFFFFFFu, sa, o), vl = __shfl_up_sync(0xFFFFFFFFu, sl, o);
+                if (lane >= o) { sa += va; sl += vl; }
+            }
+            if (lane == 31) { s_ws[warp] = sa; s_wl[warp] = sl; }
+            __syncthreads();
+            unsigned int oa = 0, ol = 0;
+            for (int w = 0; w < warp; w++) { oa += s_ws[w]; ol += s_wl[w]; }
+            const unsigned int ea = oa + sa - (a0 + a1), el = ol + sl - (l0 + l1);   // exclusive
+            cur[2 * tid] = ea; cur[2 * tid + 1] = ea + a0;
+            endR[2 * tid] = ea + a0; endR[2 * tid + 1] = ea + a0 + a1;
+            lmR[2 * tid] = el + l0; lmR[2 * tid + 1] = el + l0 + l1;
+        }
+        __syncthreads();
+        for (unsigned int j = tid; j < n; j += N_THREADS) {
+            const uint4 e = ent_a[j];
+            ent_b[atomicAdd(&cur[(gmax - e.z) >> shift], 1u)] = e;
+        }
+        __syncthreads();
+        // ---- bands ----
+        unsigned int b0 = 0;
+        int r_prev = -1, par = 0;
+        while (b0 < n) {
+            // first non-empty rank after r_prev, then as many whole ranks as fit the band
+            int lo = r_prev + 1, hi = NMS_BINS - 1;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (endR[mid] > b0) hi = mid; else lo = mid + 1; }
+            int r_new = lo;
+            hi = NMS_BINS - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (endR[mid] <= b0 + NMS_BAND) lo = mid; else hi = mid - 1; }
+            if (endR[lo] <= b0 + NMS_BAND) r_new = max(r_new, lo);
+            const unsigned int b1 = endR[r_new];
+            const bool single = b1 - b0 <= (unsigned)N_THREADS;
+            uint4 ec = make_uint4(0u, 0u, 0u, 0u);
+            for (unsigned int j = b0 + tid; j < b1; j += N_THREADS) {
+                const uint4 e = ent_b[j];
+                if (single) ec = e;
+                if (!bm_test(S, e.x)) atomicOr(&M[e.x >> 5], 1u << (e.x & 31u));
+            }
+            __syncthreads();
+            while (true) {
+                // phase A: undecided entries look for an undecided neighbour of higher priority
+                unsigned int blk = 0;
+                for (unsigned int j = b0 + tid; j < b1; j += N_THREADS) {
+                    const uint4 e = single ? ec : ent_b[j];
+                    const unsigned int p = e.x;
+                    if (!bm_test(M, p)) continue;
+                    if (bm_test(S, p)) { atomicAnd(&M[p >> 5], ~(1u << (p & 31u))); continue; }   // suppressed meanwhile
+                    const unsigned long long k = ((unsigned long long)e.z << 32) | e.y;
+                    const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
+                    const int x0 = max(px - r, 0), len = min(px + r, W - 1) - x0 + 1;
+                    bool blocked = false;
+                    for (int dy = -r; dy <= r && !blocked; dy++) {
+                        const int y = py + dy;
+                        if (y < 0 || y >= H) continue;
+                        const unsigned int q0 = (unsigned int)(y * W + x0);
+                        unsigned int fld = bm_get_range(M, q0, len);
+                        if (dy == 0) fld &= ~(1u << (px - x0));
+                        while (fld && !blocked) {
+                            const unsigned int q = q0 + (unsigned int)(__ffs(fld) - 1);
+                            fld &= fld - 1u;
+                            if (bm_test(S, q)) continue;                     // dead, its bit just lingers
+                            const unsigned long long kq = (unsigned long long)__double_as_longlong(resp[q]);
+                            blocked = prio_gt(kq, q, k, p);
                         }
                     }
-                }
-#pragma unroll
-                for (int n = 0; n < 8; n++)
-                    if (sq[n] == 0 && prio_gt(kq[n], qi[n], k, p)) blocker = qi[n];
-            }
-            const bool keep = blocked || (test && blocker != NMS_NONE);
-            const bool surv = test && blocker == NMS_NONE;
-            const unsigned int mb = __ballot_sync(0xFFFFFFFFu, keep);
-            const unsigned int ms = __ballot_sync(0xFFFFFFFFu, surv);
-            unsigned int ob = 0, os = 0;
-            if (lane == 0) {
-                if (mb) ob = atomicAdd(&s_cnt[3], (unsigned int)__popc(mb));
-                if (ms) os = atomicAdd(&s_cnt[0], (unsigned int)__popc(ms));
-            }
-            ob = __shfl_sync(0xFFFFFFFFu, ob, 0);
-            os = __shfl_sync(0xFFFFFFFFu, os, 0);
-            const unsigned int below = (1u << lane) - 1u;
-            if (keep) alive_next[ob + __popc(mb & below)] = make_uint4(p, blocker, e.z, e.w);
-            if (surv) alive_next[npx - 1u - (os + __popc(ms & below))] = make_uint4(p, NMS_NONE, e.z, e.w);   // survivors grow from the end
-        }
-        __syncthreads();
-        // pass B: one warp per survivor, rings 3..r
-        const unsigned int n_surv = s_cnt[0];
-        for (unsigned int j = warp; j < n_surv; j += N_WARPS) {
-            const uint4 e = alive_next[npx - 1u - j];
-            const unsigned int p = e.x;
-            const unsigned long long k = ((unsigned long long)e.w << 32) | e.z;
-            const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
-            unsigned int hitmask = 0, myq = 0;
-            for (int base = n_lane; base < nnb && !hitmask; base += 32) {
-                const int j2 = base + lane;
-                bool hit = false;
-                if (j2 < nnb) {
-                    const int y = py + s_wdy[j2], x = px + s_wdx[j2];
-                    if (y >= 0 && y < H && x >= 0 && x < W) {
-                        myq = (unsigned int)(y * W + x);
-                        const unsigned char sq = st[myq];
-                        const unsigned long long kq = (unsigned long long)__double_as_longlong(resp[myq]);
-                        hit = (sq == 0) && prio_gt(kq, myq, k, p);
+                    if (blocked) blk++;
+                    else {
+                        const unsigned int s = atomicAdd(&s_cnt[par], 1u);
+                        if (s < (unsigned)NMS_NEW_CAP) newp[s] = p; else blk++;   // waits for the next round
                     }
                 }
-                hitmask = __ballot_sync(0xFFFFFFFFu, hit);
+                blk = __reduce_add_sync(0xFFFFFFFFu, blk);
+                if (lane == 0 && blk) atomicAdd(&s_cnt[2 + par], blk);
+                __syncthreads();
+                const unsigned int n_new = min(s_cnt[par], (unsigned)NMS_NEW_CAP);
+                const unsigned int n_blk = s_cnt[2 + par];
+                if (tid == 0) { s_cnt[par ^ 1] = 0; s_cnt[2 + (par ^ 1)] = 0; }
+                // phase B: the new picks suppress their boxes, one box row per thread
+                for (unsigned int it = tid; it < n_new * (unsigned)win; it += N_THREADS) {
+                    const unsigned int j = it / (unsigned)win;
+                    const int dy = (int)(it - j * (unsigned)win) - r;
+                    const unsigned int p = newp[j];
+                    const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
+                    const int y = py + dy;
+                    if (dy == 0) {
+                        atomicAnd(&M[p >> 5], ~(1u << (p & 31u)));
+                        const unsigned int s = atomicAdd(&s_cnt[4], 1u);
+                        pk[s] = (unsigned long long)__double_as_longlong(resp[p]); pi[s] = p;
+                    }
+                    if (y < 0 || y >= H) continue;
+                    const int x0 = max(px - r, 0), x1 = min(px + r, W - 1);
+                    bm_set_range(S, (unsigned int)(y * W + x0), x1 - x0 + 1);
+                }
+                __syncthreads();
+                par ^= 1;
+                rounds++;
+                if (n_blk == 0) break;
             }
-            const unsigned int blocker = hitmask ? __shfl_sync(0xFFFFFFFFu, myq, __ffs(hitmask) - 1) : NMS_NONE;
-            if (lane == 0) {
-                if (hitmask) alive_next[atomicAdd(&s_cnt[3], 1u)] = make_uint4(p, blocker, e.z, e.w);
-                else newp[atomicAdd(&s_cnt[2], 1u)] = p;
-            }
+            b0 = b1;
+            r_prev = r_new;
+            if (lmR[r_new] + (s_cnt[4] - n_p0) >= (unsigned)K) break;      // the K best picks are all known
         }
-        __syncthreads();
-        const unsigned int n_new = s_cnt[2];
-        for (unsigned int j = warp; j < n_new; j += N_WARPS) {
-            const unsigned int p = newp[j];
-            if (lane == 0) {
-                const unsigned int s = atomicAdd(&s_cnt[1], 1u);
-                const unsigned long long k = (unsigned long long)__double_as_longlong(resp[p]);
-                pk[s] = k; pi[s] = p;
-                if (s < cap_s) { sk[s] = k; si[s] = p; }
-            }
-            mark_window_warp(st, H, W, r, p, lane);
-        }
-        __syncthreads();
-        n_alive = s_cnt[3];
-        __syncthreads();
-        if (tid == 0) { s_cnt[0] = 0; s_cnt[2] = 0; s_cnt[3] = 0; }
-        uint4* t = alive; alive = alive_next; alive_next = t;
-        rounds++;
-        __syncthreads();
     }
     // ---- final: K best picks in priority order ----
-    const unsigned int n_picks = s_cnt[1];
+    __syncthreads();
+    const unsigned int n_picks = s_cnt[4];
     if (tid == 0) {
-        a.stats[f * 4 + 0] = n_lm; a.stats[f * 4 + 1] = n_alive0;
+        a.stats[f * 4 + 0] = n_lm; a.stats[f * 4 + 1] = n;
         a.stats[f * 4 + 2] = rounds; a.stats[f * 4 + 3] = n_picks;
     }
+    unsigned int P2 = 1;
+    while (P2 < (unsigned)max(K, 1)) P2 <<= 1;
+    unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);   // the band state is not needed any more
+    unsigned int* si = reinterpret_cast<unsigned int*>(sk + P2);
     unsigned long long fk = 0ull;
     unsigned int fi = 0xFFFFFFFFu;
     const unsigned int n_out = min(n_picks, (unsigned)K);
     if (n_picks > (unsigned)K) block_select_kth(pk, pi, n_picks, (unsigned)K, hist, s_misc, &fk, &fi);
-    // gather into shared memory, padded to a power of two (the mirror is not needed any more)
     __syncthreads();
     for (unsigned int j = tid; j < P2; j += N_THREADS) { sk[j] = 0ull; si[j] = 0xFFFFFFFFu; }
-    if (tid == 0) s_cnt[0] = 0;
     __syncthreads();
     for (unsigned int j = tid; j < n_picks; j += N_THREADS) {
         const unsigned long long k = pk[j];
         const unsigned int i = pi[j];
         if (prio_ge(k, i, fk, fi)) {
-            const unsigned int s = atomicAdd(&s_cnt[0], 1u);
+            const unsigned int s = atomicAdd(&s_cnt[5], 1u);
             if (s < P2) { sk[s] = k; si[s] = i; }
         }
     }
@@ -1072,23 +1065,34 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     const size_t npx = (size_t)H * W;
     const size_t lm_cap = vo_harris_lm_cap(H, W, radius);
     const size_t F = n_frames;
+    const size_t bm_words = npx / 32 + 2;
+    unsigned int P2 = 1;
+    while (P2 < (unsigned)num_keypoints) P2 <<= 1;
+    // shared memory of the band kernel: bin tables + new-pick list (+ the two bitmaps when they fit); the final
+    // sort reuses the same storage
+    const size_t smem_tables = (size_t)(3 * NMS_BINS + NMS_NEW_CAP) * 4;
+    const bool bm_smem = smem_tables + 2 * bm_words * 4 <= 220 * 1024;
+    size_t smem_bands = smem_tables + (bm_smem ? 2 * bm_words * 4 : 0);
+    if ((size_t)P2 * 12 > smem_bands) smem_bands = (size_t)P2 * 12;
     // carve scratch
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_lmk = carve(F * lm_cap * 8), o_lmi = carve(F * lm_cap * 4), o_cnt = carve(F * 4);
-    const size_t o_state = carve(F * npx), o_aa = carve(F * npx * 16), o_ab = carve(F * npx * 16);
-    const size_t o_pk = carve(F * lm_cap * 8), o_pi = carve(F * lm_cap * 4), o_new = carve(F * lm_cap * 4);
+    const size_t o_sup = carve(F * bm_words * 4), o_mem = carve(bm_smem ? 0 : F * bm_words * 4);
+    const size_t o_ea = carve(F * npx * 16), o_eb = carve(F * npx * 16);
+    const size_t o_pk = carve(F * lm_cap * 8), o_pi = carve(F * lm_cap * 4);
     const size_t o_stats = carve(F * 16);
     const size_t o_tk = carve(F * 8), o_ti = carve(F * 4), o_ctr = carve(F * 16);
     int rc = vo_buf_reserve(&ctx->scratch[0], off);
     if (rc) return rc;
     unsigned char* base = (unsigned char*)ctx->scratch[0].p;
     VO_CUDA(cudaMemsetAsync(base + o_cnt, 0, F * 4, stream));
-    VO_CUDA(cudaMemsetAsync(base + o_state, 0, F * npx, stream));
+    VO_CUDA(cudaMemsetAsync(base + o_sup, 0, F * bm_words * 4, stream));
+    if (!bm_smem) VO_CUDA(cudaMemsetAsync(base + o_mem, 0, F * bm_words * 4, stream));
 
     static bool attr_set = false;
     if (!attr_set) {
-        VO_CUDA(cudaFuncSetAttribute(harris_nms_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VO_CUDA(cudaFuncSetAttribute(harris_nms_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_set = true;
     }
     {
@@ -1109,16 +1113,15 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     a.resp = d_resp; a.H = H; a.W = W; a.r = radius; a.K = num_keypoints; a.lm_cap = (unsigned)lm_cap;
     a.lm_key = (unsigned long long*)(base + o_lmk); a.lm_idx = (unsigned int*)(base + o_lmi);
     a.lm_count = (unsigned int*)(base + o_cnt);
-    a.state = base + o_state; a.alive_a = (uint4*)(base + o_aa); a.alive_b = (uint4*)(base + o_ab);
+    a.sup = (unsigned int*)(base + o_sup); a.mem = bm_smem ? nullptr : (unsigned int*)(base + o_mem);
+    a.bm_words = (unsigned)bm_words;
+    a.ent_a = (uint4*)(base + o_ea); a.ent_b = (uint4*)(base + o_eb);
     a.pick_key = (unsigned long long*)(base + o_pk); a.pick_idx = (unsigned int*)(base + o_pi);
-    a.new_idx = (unsigned int*)(base + o_new);
     a.kp_xy = d_kp_xy;
     a.stats = d_stats_or_null ? d_stats_or_null : (unsigned int*)(base + o_stats);
     a.thr_key = (unsigned long long*)(base + o_tk); a.thr_idx = (unsigned int*)(base + o_ti);
     a.counters = (unsigned int*)(base + o_ctr);
-    unsigned int P2 = 1;
-    while (P2 < (unsigned)num_keypoints) P2 <<= 1;
-    const size_t smem_nms = (size_t)(P2 > (unsigned)NMS_SMEM_PICKS ? P2 : (unsigned)NMS_SMEM_PICKS) * 12;
+    a.bitmaps_in_smem = bm_smem ? 1 : 0;
     harris_nms_select<<<n_frames, N_THREADS, NMS_SELECT_SMEM * 12, stream>>>(a);
     ctx->launches++;
     VO_CHECK_LAUNCH();
@@ -1126,7 +1129,7 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     harris_nms_scan<<<g3, 256, 0, stream>>>(a);
     ctx->launches++;
     VO_CHECK_LAUNCH();
-    harris_nms_frame<<<n_frames, N_THREADS, smem_nms, stream>>>(a);
+    harris_nms_bands<<<n_frames, N_THREADS, smem_bands, stream>>>(a);
     ctx->launches++;
     VO_CHECK_LAUNCH();
     return VO_OK;
