@@ -43,6 +43,21 @@ if what == "harris_time":
         e1.record(st)
         torch.cuda.synchronize()
     print("harris_response ms/launch: %.4f" % (e0.elapsed_time(e1) / 20))
+elif what == "nms_time":
+    resps = []
+    for t in range(P):
+        rr = torch.empty((S, H, W), dtype=torch.float64, device=dev)
+        nat.check(L.vo_harris_response_dev(ctx.handle, pool[t].data_ptr(), S, H, W, pitch, H * pitch, 9, C.c_double(0.09),
+                                           rr.data_ptr(), stream), "resp")
+        resps.append(rr)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for rep in range(2):
+        e0.record(st)
+        for i in range(12):
+            nat.check(L.vo_harris_nms_dev(ctx.handle, resps[i % P].data_ptr(), S, H, W, 5, 1000, kp.data_ptr(), None, stream), "nms")
+        e1.record(st)
+        torch.cuda.synchronize()
+    print("harris_nms ms/call: %.4f" % (e0.elapsed_time(e1) / 12))
 elif what in ("harris", "nms"):
     for i in range(5):
         fr = pool[i % P]

@@ -557,7 +557,7 @@ struct NmsArgs {
     unsigned int* sup;                 // [F][bm_words] bitmap: pixel lies in the box of a pick
     unsigned int* mem;                 // [F][bm_words] bitmap: undecided entry of the current band (global fallback only)
     unsigned int bm_words;             // words per frame bitmap (H*W/32 + 2: the range helpers read one word ahead)
-    uint4* ent_a;                      // [F][H*W] entries {pixel, key lo, key hi, -} in scan order
+    uint4* ent_a;                      // [F][H*W] entries {pixel, key lo, key hi, y << 16 | x} in scan order
     uint4* ent_b;                      // [F][H*W] the same entries ordered by priority bin
     unsigned long long* pick_key;      // [F][lm_cap]
     unsigned int* pick_idx;            // [F][lm_cap]
@@ -567,6 +567,8 @@ struct NmsArgs {
     unsigned int* thr_idx;             // [F] threshold (tie-break index)
     unsigned int* counters;            // [F][4]: entries, picks, min / max high word of the entries' keys
     int bitmaps_in_smem;
+    unsigned int smem_bytes;           // dynamic shared memory of the band kernel
+    unsigned int band;                 // entries per band (<= N_THREADS)
 };
 
 // ---- bitmaps: bit p = pixel p (row-major, no row padding) ----
@@ -706,7 +708,10 @@ harris_nms_scan(NmsArgs a) {
     unsigned int o = s_base + s_warp[warp] + incl - cnt;
 #pragma unroll
     for (int j = 0; j < SCAN_PER_THREAD; j++)
-        if (keep_mask & (1u << j)) ent[o++] = make_uint4(base + j * 256u, (unsigned int)k[j], (unsigned int)(k[j] >> 32), 0u);
+        if (keep_mask & (1u << j)) {
+            const unsigned int p = base + j * 256u, py = p / (unsigned)a.W;
+            ent[o++] = make_uint4(p, (unsigned int)k[j], (unsigned int)(k[j] >> 32), (py << 16) | (p - py * (unsigned)a.W));
+        }
 }
 
 // ---- NMS step 4 (one CTA per frame): the entries are ordered into priority bins (high word of the score, 2048
@@ -719,7 +724,102 @@ harris_nms_scan(NmsArgs a) {
 constexpr int NMS_BINS = 2048;
 constexpr int NMS_BAND = 1024;       // entries per band (one per thread)
 constexpr int NMS_NEW_CAP = 1024;    // new picks per round (the surplus waits for the next round)
+constexpr int NMS_HASH = 2048;       // open-addressing table for the (at most NMS_BAND) undecided entries of a band
+constexpr unsigned int NMS_EMPTY = 0xFFFFFFFFu;
+constexpr size_t NMS_TABLES_BYTES = (size_t)(3 * NMS_BINS + NMS_NEW_CAP) * 4 + (size_t)NMS_HASH * 16 + (size_t)NMS_NEW_CAP * 8;
 
+__device__ __forceinline__ unsigned int nms_hash(unsigned int p) { return (p * 2654435761u) >> 21; }   // 11 bits
+
+#ifdef VO_NMS_TIMING
+#define VO_NMS_T0() t_x = clock64()
+#define VO_NMS_T1(acc) acc += clock64() - t_x
+#else
+#define VO_NMS_T0()
+#define VO_NMS_T1(acc)
+#endif
+
+// score of an undecided entry of the current band (all of them are in the table {pixel, key lo, key hi, -})
+__device__ __forceinline__ unsigned long long nms_lookup(const uint4* tab, unsigned int q) {
+    unsigned int h = nms_hash(q);
+    uint4 t = tab[h];
+    for (int n = 0; t.x != q && t.x != NMS_EMPTY && n < NMS_HASH; n++) {
+        h = (h + 1u) & (NMS_HASH - 1);
+        t = tab[h];
+    }
+    return t.x == q ? (((unsigned long long)t.z << 32) | t.y) : 0ull;
+}
+
+// an undecided, unsuppressed entry of the band with higher priority inside the window of (py, px), or NMS_EMPTY
+template <int R>
+__device__ __forceinline__ unsigned int nms_find_blocker(const unsigned int* M, const unsigned int* S, const uint4* tab,
+                                                         int H, int W, int r_rt, int py, int px,
+                                                         unsigned int p, unsigned long long k) {
+    const int r = R > 0 ? R : r_rt;
+    const int x0 = max(px - r, 0), len = min(px + r, W - 1) - x0 + 1;
+    if (R > 0) {
+        unsigned int fld[2 * R + 1], any = 0u;
+#pragma unroll
+        for (int i = 0; i <= 2 * R; i++) {               // all window rows first: 2 loads each, independent
+            const int y = py + i - R;
+            fld[i] = (y >= 0 && y < H) ? bm_get_range(M, (unsigned int)(y * W + x0), len) : 0u;
+        }
+        fld[R] &= ~(1u << (px - x0));
+#pragma unroll
+        for (int i = 0; i <= 2 * R; i++) any |= fld[i];
+        if (!any) return NMS_EMPTY;
+#pragma unroll
+        for (int i = 0; i <= 2 * R; i++) {
+            unsigned int f = fld[i];
+            const unsigned int q0 = (unsigned int)((py + i - R) * W + x0);
+            while (f) {
+                const unsigned int q = q0 + (unsigned int)(__ffs(f) - 1);
+                f &= f - 1u;
+                const bool dead = bm_test(S, q);             // its bit just lingers; both loads issue together
+                const unsigned long long kq = nms_lookup(tab, q);
+                if (!dead && prio_gt(kq, q, k, p)) return q;
+            }
+        }
+        return NMS_EMPTY;
+    }
+    for (int dy = -r; dy <= r; dy++) {
+        const int y = py + dy;
+        if (y < 0 || y >= H) continue;
+        const unsigned int q0 = (unsigned int)(y * W + x0);
+        unsigned int f = bm_get_range(M, q0, len);
+        if (dy == 0) f &= ~(1u << (px - x0));
+        while (f) {
+            const unsigned int q = q0 + (unsigned int)(__ffs(f) - 1);
+            f &= f - 1u;
+            const bool dead = bm_test(S, q);
+            const unsigned long long kq = nms_lookup(tab, q);
+            if (!dead && prio_gt(kq, q, k, p)) return q;
+        }
+    }
+    return NMS_EMPTY;
+}
+
+// the new picks of a round suppress their boxes (one box row per thread) and are appended to the pick list
+__device__ __forceinline__ void nms_apply_picks(unsigned int* S, unsigned int* M, const unsigned int* newp, const unsigned long long* newk,
+                                                unsigned int n_new, int H, int W, int r, unsigned long long* pk, unsigned int* pi,
+                                                unsigned int picks_base) {
+    const unsigned int win = 2u * r + 1u;
+    for (unsigned int it = threadIdx.x; it < n_new * win; it += N_THREADS) {
+        const unsigned int j = it / win;
+        const int dy = (int)(it - j * win) - r;
+        const unsigned int p = newp[j];
+        const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
+        const int y = py + dy;
+        if (dy == 0) {
+            atomicAnd(&M[p >> 5], ~(1u << (p & 31u)));
+            pk[picks_base + j] = newk[j]; pi[picks_base + j] = p;
+        }
+        if (y < 0 || y >= H) continue;
+        const int x0 = max(px - r, 0), x1 = min(px + r, W - 1);
+        bm_set_range(S, (unsigned int)(y * W + x0), x1 - x0 + 1);
+    }
+}
+
+template <int R>
 __global__ void __launch_bounds__(N_THREADS)
 harris_nms_bands(NmsArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -742,11 +842,13 @@ harris_nms_bands(NmsArgs a) {
     unsigned int* cur = endR + NMS_BINS;                              // [BINS] scatter cursors
     unsigned int* lmR = cur + NMS_BINS;                               // [BINS] local-maximum picks with rank <= R
     unsigned int* newp = lmR + NMS_BINS;                              // [NEW_CAP]
+    uint4* tab = reinterpret_cast<uint4*>(newp + NMS_NEW_CAP);        // [HASH] pixel -> score of the band's undecided entries
+    unsigned long long* newk = reinterpret_cast<unsigned long long*>(tab + NMS_HASH);   // [NEW_CAP] scores of the new picks
     unsigned int* S = a.sup + (size_t)f * a.bm_words;
     unsigned int* M = a.mem ? a.mem + (size_t)f * a.bm_words : nullptr;
     if (a.bitmaps_in_smem) {
         unsigned int* gs = S;
-        S = newp + NMS_NEW_CAP;
+        S = reinterpret_cast<unsigned int*>(newk + NMS_NEW_CAP);
         M = S + a.bm_words;
         for (unsigned int w = tid; w < a.bm_words; w += N_THREADS) { S[w] = gs[w]; M[w] = 0u; }
     }
@@ -755,14 +857,26 @@ harris_nms_bands(NmsArgs a) {
     const unsigned int gmin = a.counters[f * 4 + 2], gmax = a.counters[f * 4 + 3];
     const unsigned int n_lm = min(a.lm_count[f], a.lm_cap);
     for (int j = tid; j < NMS_BINS; j += N_THREADS) { endR[j] = 0u; lmR[j] = 0u; }
+    for (int j = tid; j < NMS_HASH; j += N_THREADS) tab[j].x = NMS_EMPTY;
     if (tid == 0) { s_cnt[0] = 0; s_cnt[1] = 0; s_cnt[2] = 0; s_cnt[3] = 0; s_cnt[4] = n_p0; s_cnt[5] = 0; }
     __syncthreads();
     unsigned int rounds = 0;
+    unsigned int n_picks_run = n_p0;           // picks so far (uniform across the CTA)
+#ifdef VO_NMS_TIMING
+    long long t_0 = clock64(), t_1 = t_0, t_2 = t_0, t_x = 0, acc_i = 0, acc_a = 0, acc_b = 0;
+    unsigned int n_bands = 0;
+#endif
     if (n > 0) {
         int shift = 0;
         while (((gmax - gmin) >> shift) >= (unsigned)NMS_BINS) shift++;
         // ---- counting sort of the entries by bin rank ----
-        for (unsigned int j = tid; j < n; j += N_THREADS) atomicAdd(&endR[(gmax - ent_a[j].z) >> shift], 1u);
+        for (unsigned int j0 = 0; j0 < n; j0 += 8 * N_THREADS) {          // loads batched: this loop is latency bound
+            unsigned int z[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const unsigned int j = j0 + u * N_THREADS + tid; z[u] = j < n ? ent_a[j].z : 0u; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) if (j0 + u * N_THREADS + tid < n) atomicAdd(&endR[(gmax - z[u]) >> shift], 1u);
+        }
         for (unsigned int j = tid; j < n_p0; j += N_THREADS) {
             const unsigned int h = (unsigned int)(pk[j] >> 32);
             const unsigned int rk = h >= gmax ? 0u : (gmax - h) >> shift;
@@ -788,116 +902,203 @@ harris_nms_bands(NmsArgs a) {
             lmR[2 * tid] = el + l0; lmR[2 * tid + 1] = el + l0 + l1;
         }
         __syncthreads();
-        for (unsigned int j = tid; j < n; j += N_THREADS) {
-            const uint4 e = ent_a[j];
-            ent_b[atomicAdd(&cur[(gmax - e.z) >> shift], 1u)] = e;
+        for (unsigned int j0 = 0; j0 < n; j0 += 8 * N_THREADS) {
+            uint4 e[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { const unsigned int j = j0 + u * N_THREADS + tid; if (j < n) e[u] = ent_a[j]; }
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (j0 + u * N_THREADS + tid < n) ent_b[atomicAdd(&cur[(gmax - e[u].z) >> shift], 1u)] = e[u];
         }
         __syncthreads();
+#ifdef VO_NMS_TIMING
+        t_1 = clock64();
+#endif
         // ---- bands ----
-        unsigned int b0 = 0;
-        int r_prev = -1, par = 0;
-        while (b0 < n) {
-            // first non-empty rank after r_prev, then as many whole ranks as fit the band
-            int lo = r_prev + 1, hi = NMS_BINS - 1;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (endR[mid] > b0) hi = mid; else lo = mid + 1; }
-            int r_new = lo;
+        // band = as many whole ranks as fit NMS_BAND entries (at least one rank); its range depends only on the
+        // bin table, so the entries of the next band are fetched while the current one is processed
+        auto band_end = [&](unsigned int from, int r_from, int* r_out) -> unsigned int {
+            int lo = r_from + 1, hi = NMS_BINS - 1;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (endR[mid] > from) hi = mid; else lo = mid + 1; }
+            int r_new = lo;                              // first non-empty rank
             hi = NMS_BINS - 1;
-            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (endR[mid] <= b0 + NMS_BAND) lo = mid; else hi = mid - 1; }
-            if (endR[lo] <= b0 + NMS_BAND) r_new = max(r_new, lo);
-            const unsigned int b1 = endR[r_new];
-            const bool single = b1 - b0 <= (unsigned)N_THREADS;
-            uint4 ec = make_uint4(0u, 0u, 0u, 0u);
-            for (unsigned int j = b0 + tid; j < b1; j += N_THREADS) {
-                const uint4 e = ent_b[j];
-                if (single) ec = e;
-                if (!bm_test(S, e.x)) atomicOr(&M[e.x >> 5], 1u << (e.x & 31u));
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (endR[mid] <= from + a.band) lo = mid; else hi = mid - 1; }
+            if (endR[lo] <= from + a.band) r_new = max(r_new, lo);
+            *r_out = r_new;
+            return endR[r_new];
+        };
+        int par = 0, r_cur = -1, r_next = -1;
+        unsigned int b0 = 0, b1 = band_end(0u, -1, &r_cur), b2 = b1;
+        uint4 e_next = make_uint4(0u, 0u, 0u, 0u);
+        if (b0 + tid < b1) e_next = ent_b[b0 + tid];
+        while (true) {
+            VO_NMS_T0();
+            const uint4 ec = e_next;
+            if (b1 < n) {
+                b2 = band_end(b1, r_cur, &r_next);
+                if (b1 + tid < b2) e_next = ent_b[b1 + tid];
             }
-            __syncthreads();
-            while (true) {
-                // phase A: undecided entries look for an undecided neighbour of higher priority
-                unsigned int blk = 0;
-                for (unsigned int j = b0 + tid; j < b1; j += N_THREADS) {
-                    const uint4 e = single ? ec : ent_b[j];
-                    const unsigned int p = e.x;
-                    if (!bm_test(M, p)) continue;
-                    if (bm_test(S, p)) { atomicAnd(&M[p >> 5], ~(1u << (p & 31u))); continue; }   // suppressed meanwhile
-                    const unsigned long long k = ((unsigned long long)e.z << 32) | e.y;
-                    const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
-                    const int x0 = max(px - r, 0), len = min(px + r, W - 1) - x0 + 1;
-                    bool blocked = false;
-                    for (int dy = -r; dy <= r && !blocked; dy++) {
-                        const int y = py + dy;
-                        if (y < 0 || y >= H) continue;
-                        const unsigned int q0 = (unsigned int)(y * W + x0);
-                        unsigned int fld = bm_get_range(M, q0, len);
-                        if (dy == 0) fld &= ~(1u << (px - x0));
-                        while (fld && !blocked) {
-                            const unsigned int q = q0 + (unsigned int)(__ffs(fld) - 1);
-                            fld &= fld - 1u;
-                            if (bm_test(S, q)) continue;                     // dead, its bit just lingers
-                            const unsigned long long kq = (unsigned long long)__double_as_longlong(resp[q]);
-                            blocked = prio_gt(kq, q, k, p);
+            const bool single = b1 - b0 <= (unsigned)N_THREADS;    // the normal case: one entry per thread, scores hashed
+            if (single) {
+                // ---------------- one entry per thread, kept in registers ----------------
+                const unsigned int p = ec.x;
+                const unsigned long long k = ((unsigned long long)ec.z << 32) | ec.y;
+                const int py = (int)(ec.w >> 16), px = (int)(ec.w & 0xFFFFu);
+                bool und = (b0 + tid < b1) && !bm_test(S, p);
+                unsigned int my_h = 0, blocker = NMS_EMPTY;
+                if (und) {
+                    atomicOr(&M[p >> 5], 1u << (p & 31u));
+                    my_h = nms_hash(p);
+                    while (atomicCAS(&tab[my_h].x, NMS_EMPTY, p) != NMS_EMPTY) my_h = (my_h + 1u) & (NMS_HASH - 1);
+                    tab[my_h].y = ec.y; tab[my_h].z = ec.z;
+                }
+                const bool inserted = und;
+                __syncthreads();
+                VO_NMS_T1(acc_i);
+                while (true) {
+                    VO_NMS_T0();
+                    // phase A: an undecided entry is blocked while an undecided neighbour of higher priority exists
+                    unsigned int blk = 0;
+                    bool is_new = false;
+                    if (und) {
+                        if (bm_test(S, p)) {                                   // suppressed by a pick of the last round
+                            und = false;
+                            atomicAnd(&M[p >> 5], ~(1u << (p & 31u)));
+                        } else {
+                            if (blocker == NMS_EMPTY || !bm_test(M, blocker) || bm_test(S, blocker))
+                                blocker = nms_find_blocker<R>(M, S, tab, H, W, r, py, px, p, k);
+                            blk = blocker != NMS_EMPTY ? 1u : 0u;
+                            is_new = blocker == NMS_EMPTY;
                         }
                     }
-                    if (blocked) blk++;
-                    else {
-                        const unsigned int s = atomicAdd(&s_cnt[par], 1u);
-                        if (s < (unsigned)NMS_NEW_CAP) newp[s] = p; else blk++;   // waits for the next round
+                    {   // one atomic per warp for the slots of the new picks
+                        const unsigned int mnew = __ballot_sync(0xFFFFFFFFu, is_new);
+                        unsigned int base_s = 0;
+                        if (lane == 0 && mnew) base_s = atomicAdd(&s_cnt[par], (unsigned int)__popc(mnew));
+                        base_s = __shfl_sync(0xFFFFFFFFu, base_s, 0);
+                        if (is_new) {
+                            const unsigned int s = base_s + __popc(mnew & ((1u << lane) - 1u));
+                            if (s < (unsigned)NMS_NEW_CAP) { newp[s] = p; newk[s] = k; und = false; }
+                            else blk = 1u;                                     // list full: next round
+                        }
                     }
+                    blk = __reduce_add_sync(0xFFFFFFFFu, blk);
+                    if (lane == 0 && blk) atomicAdd(&s_cnt[2 + par], blk);
+                    __syncthreads();
+                    VO_NMS_T1(acc_a);
+                    VO_NMS_T0();
+                    const unsigned int n_new = min(s_cnt[par], (unsigned)NMS_NEW_CAP);
+                    const unsigned int n_blk = s_cnt[2 + par];
+                    if (tid == 0) { s_cnt[par ^ 1] = 0; s_cnt[2 + (par ^ 1)] = 0; }
+                    nms_apply_picks(S, M, newp, newk, n_new, H, W, r, pk, pi, n_picks_run);
+                    n_picks_run += n_new;
+                    if (n_blk == 0 && inserted) tab[my_h].x = NMS_EMPTY;       // last round: leave the table empty
+                    __syncthreads();
+                    VO_NMS_T1(acc_b);
+                    par ^= 1;
+                    rounds++;
+                    if (n_blk == 0) break;
                 }
-                blk = __reduce_add_sync(0xFFFFFFFFu, blk);
-                if (lane == 0 && blk) atomicAdd(&s_cnt[2 + par], blk);
+            } else {
+                // ---------------- a single oversize bin (massive ties): strips of entries, scores from global memory ----------------
+                for (unsigned int j = b0 + tid; j < b1; j += N_THREADS) {
+                    const unsigned int p = ent_b[j].x;
+                    if (!bm_test(S, p)) atomicOr(&M[p >> 5], 1u << (p & 31u));
+                }
                 __syncthreads();
-                const unsigned int n_new = min(s_cnt[par], (unsigned)NMS_NEW_CAP);
-                const unsigned int n_blk = s_cnt[2 + par];
-                if (tid == 0) { s_cnt[par ^ 1] = 0; s_cnt[2 + (par ^ 1)] = 0; }
-                // phase B: the new picks suppress their boxes, one box row per thread
-                for (unsigned int it = tid; it < n_new * (unsigned)win; it += N_THREADS) {
-                    const unsigned int j = it / (unsigned)win;
-                    const int dy = (int)(it - j * (unsigned)win) - r;
-                    const unsigned int p = newp[j];
-                    const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
-                    const int y = py + dy;
-                    if (dy == 0) {
-                        atomicAnd(&M[p >> 5], ~(1u << (p & 31u)));
-                        const unsigned int s = atomicAdd(&s_cnt[4], 1u);
-                        pk[s] = (unsigned long long)__double_as_longlong(resp[p]); pi[s] = p;
+                while (true) {
+                    unsigned int blk = 0;
+                    for (unsigned int j = b0 + tid; j < b1; j += N_THREADS) {
+                        const uint4 e = ent_b[j];
+                        const unsigned int p = e.x;
+                        if (!bm_test(M, p)) continue;
+                        if (bm_test(S, p)) { atomicAnd(&M[p >> 5], ~(1u << (p & 31u))); continue; }
+                        const unsigned long long k = ((unsigned long long)e.z << 32) | e.y;
+                        const int py = (int)(e.w >> 16), px = (int)(e.w & 0xFFFFu);
+                        const int x0 = max(px - r, 0), len = min(px + r, W - 1) - x0 + 1;
+                        bool blocked = false;
+                        for (int dy = -r; dy <= r && !blocked; dy++) {
+                            const int y = py + dy;
+                            if (y < 0 || y >= H) continue;
+                            const unsigned int q0 = (unsigned int)(y * W + x0);
+                            unsigned int fld = bm_get_range(M, q0, len);
+                            if (dy == 0) fld &= ~(1u << (px - x0));
+                            while (fld && !blocked) {
+                                const unsigned int q = q0 + (unsigned int)(__ffs(fld) - 1);
+                                fld &= fld - 1u;
+                                if (bm_test(S, q)) continue;                   // dead, its bit just lingers
+                                blocked = prio_gt((unsigned long long)__double_as_longlong(resp[q]), q, k, p);
+                            }
+                        }
+                        if (!blocked) {
+                            const unsigned int s = atomicAdd(&s_cnt[par], 1u);
+                            if (s < (unsigned)NMS_NEW_CAP) { newp[s] = p; newk[s] = k; } else blocked = true;
+                        }
+                        if (blocked) blk++;
                     }
-                    if (y < 0 || y >= H) continue;
-                    const int x0 = max(px - r, 0), x1 = min(px + r, W - 1);
-                    bm_set_range(S, (unsigned int)(y * W + x0), x1 - x0 + 1);
+                    blk = __reduce_add_sync(0xFFFFFFFFu, blk);
+                    if (lane == 0 && blk) atomicAdd(&s_cnt[2 + par], blk);
+                    __syncthreads();
+                    const unsigned int n_new = min(s_cnt[par], (unsigned)NMS_NEW_CAP);
+                    const unsigned int n_blk = s_cnt[2 + par];
+                    if (tid == 0) { s_cnt[par ^ 1] = 0; s_cnt[2 + (par ^ 1)] = 0; }
+                    nms_apply_picks(S, M, newp, newk, n_new, H, W, r, pk, pi, n_picks_run);
+                    n_picks_run += n_new;
+                    __syncthreads();
+                    par ^= 1;
+                    rounds++;
+                    if (n_blk == 0) break;
                 }
-                __syncthreads();
-                par ^= 1;
-                rounds++;
-                if (n_blk == 0) break;
             }
-            b0 = b1;
-            r_prev = r_new;
-            if (lmR[r_new] + (s_cnt[4] - n_p0) >= (unsigned)K) break;      // the K best picks are all known
+#ifdef VO_NMS_TIMING
+            n_bands++;
+#endif
+            if (lmR[r_cur] + (n_picks_run - n_p0) >= (unsigned)K) break;   // the K best picks are all known
+            if (b1 >= n) break;
+            b0 = b1; b1 = b2; r_cur = r_next;
         }
     }
     // ---- final: K best picks in priority order ----
     __syncthreads();
-    const unsigned int n_picks = s_cnt[4];
+    const unsigned int n_picks = n_picks_run;
     if (tid == 0) {
         a.stats[f * 4 + 0] = n_lm; a.stats[f * 4 + 1] = n;
         a.stats[f * 4 + 2] = rounds; a.stats[f * 4 + 3] = n_picks;
     }
+#ifdef VO_NMS_TIMING
+    t_2 = clock64();
+#endif
     unsigned int P2 = 1;
     while (P2 < (unsigned)max(K, 1)) P2 <<= 1;
-    unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);   // the band state is not needed any more
-    unsigned int* si = reinterpret_cast<unsigned int*>(sk + P2);
+    const unsigned int n_out = min(n_picks, (unsigned)K);
     unsigned long long fk = 0ull;
     unsigned int fi = 0xFFFFFFFFu;
-    const unsigned int n_out = min(n_picks, (unsigned)K);
-    if (n_picks > (unsigned)K) block_select_kth(pk, pi, n_picks, (unsigned)K, hist, s_misc, &fk, &fi);
+    // a few more picks than K (the usual case): sort them all and keep the first K.  Otherwise select the K-th
+    // best first (picks staged behind the sort area when they fit, so the 12 passes run at shared-memory latency).
+    unsigned int PA = P2;
+    while (PA < n_picks) PA <<= 1;
+    const bool sort_all = PA <= 4096u && (size_t)PA * 12 <= a.smem_bytes;
+    if (sort_all) P2 = PA;
+    unsigned long long* sk = reinterpret_cast<unsigned long long*>(smem_raw);   // the band state is not needed any more
+    unsigned int* si = reinterpret_cast<unsigned int*>(sk + P2);
+    const unsigned long long* qk = pk;
+    const unsigned int* qi = pi;
+    if (!sort_all && n_picks > (unsigned)K) {
+        if (((size_t)P2 + n_picks) * 12 + 16 <= a.smem_bytes) {
+            unsigned long long* tk2 = reinterpret_cast<unsigned long long*>(smem_raw + (((size_t)P2 * 12 + 15) & ~(size_t)15));
+            unsigned int* ti2 = reinterpret_cast<unsigned int*>(tk2 + n_picks);
+            for (unsigned int j = tid; j < n_picks; j += N_THREADS) { tk2[j] = pk[j]; ti2[j] = pi[j]; }
+            qk = tk2; qi = ti2;
+            __syncthreads();
+        }
+        block_select_kth(qk, qi, n_picks, (unsigned)K, hist, s_misc, &fk, &fi);
+    }
     __syncthreads();
     for (unsigned int j = tid; j < P2; j += N_THREADS) { sk[j] = 0ull; si[j] = 0xFFFFFFFFu; }
     __syncthreads();
     for (unsigned int j = tid; j < n_picks; j += N_THREADS) {
-        const unsigned long long k = pk[j];
-        const unsigned int i = pi[j];
+        const unsigned long long k = qk[j];
+        const unsigned int i = qi[j];
         if (prio_ge(k, i, fk, fi)) {
             const unsigned int s = atomicAdd(&s_cnt[5], 1u);
             if (s < P2) { sk[s] = k; si[s] = i; }
@@ -944,6 +1145,14 @@ harris_nms_bands(NmsArgs a) {
         }
         out[2 * j] = x; out[2 * j + 1] = y;
     }
+#ifdef VO_NMS_TIMING
+    __syncthreads();
+    if (tid == 0) {   // probe build only: cycles of {sort, bands, final}, bands processed
+        a.stats[f * 4 + 0] = (unsigned int)(t_1 - t_0); a.stats[f * 4 + 1] = (unsigned int)(acc_i + acc_a);
+        a.stats[f * 4 + 2] = (unsigned int)acc_b; a.stats[f * 4 + 3] = (unsigned int)(clock64() - t_2);
+        (void)n_bands;
+    }
+#endif
 }
 
 // harris.py:160-194: raw (2r+1)^2 patches around each keypoint from a zero-padded image.
@@ -1062,6 +1271,7 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     VO_REQUIRE(radius >= 0 && radius <= 15, "harris nms: radius must be in [0, 15] (got %d)", radius);
     VO_REQUIRE(num_keypoints >= 1 && num_keypoints <= 16384, "harris nms: num_keypoints must be in [1, 16384]");
     VO_REQUIRE(H >= 2 * radius + 1 && W >= 2 * radius + 1, "harris nms: image smaller than the suppression box");
+    VO_REQUIRE(H < 65536 && W < 65536, "harris nms: frame sides must be below 65536");
     const size_t npx = (size_t)H * W;
     const size_t lm_cap = vo_harris_lm_cap(H, W, radius);
     const size_t F = n_frames;
@@ -1070,7 +1280,7 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     while (P2 < (unsigned)num_keypoints) P2 <<= 1;
     // shared memory of the band kernel: bin tables + new-pick list (+ the two bitmaps when they fit); the final
     // sort reuses the same storage
-    const size_t smem_tables = (size_t)(3 * NMS_BINS + NMS_NEW_CAP) * 4;
+    const size_t smem_tables = NMS_TABLES_BYTES;
     const bool bm_smem = smem_tables + 2 * bm_words * 4 <= 220 * 1024;
     size_t smem_bands = smem_tables + (bm_smem ? 2 * bm_words * 4 : 0);
     if ((size_t)P2 * 12 > smem_bands) smem_bands = (size_t)P2 * 12;
@@ -1092,7 +1302,8 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
 
     static bool attr_set = false;
     if (!attr_set) {
-        VO_CUDA(cudaFuncSetAttribute(harris_nms_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        VO_CUDA(cudaFuncSetAttribute(harris_nms_bands<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+        VO_CUDA(cudaFuncSetAttribute(harris_nms_bands<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_set = true;
     }
     {
@@ -1122,6 +1333,12 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     a.thr_key = (unsigned long long*)(base + o_tk); a.thr_idx = (unsigned int*)(base + o_ti);
     a.counters = (unsigned int*)(base + o_ctr);
     a.bitmaps_in_smem = bm_smem ? 1 : 0;
+    a.smem_bytes = (unsigned)smem_bands;
+    {
+        static int band = 0;
+        if (!band) { const char* e = getenv("VO_NMS_BAND"); band = e ? atoi(e) : NMS_BAND; if (band < 32 || band > N_THREADS) band = NMS_BAND; }
+        a.band = (unsigned)band;
+    }
     harris_nms_select<<<n_frames, N_THREADS, NMS_SELECT_SMEM * 12, stream>>>(a);
     ctx->launches++;
     VO_CHECK_LAUNCH();
@@ -1129,7 +1346,8 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     harris_nms_scan<<<g3, 256, 0, stream>>>(a);
     ctx->launches++;
     VO_CHECK_LAUNCH();
-    harris_nms_bands<<<n_frames, N_THREADS, smem_bands, stream>>>(a);
+    if (radius == 5) harris_nms_bands<5><<<n_frames, N_THREADS, smem_bands, stream>>>(a);
+    else harris_nms_bands<0><<<n_frames, N_THREADS, smem_bands, stream>>>(a);
     ctx->launches++;
     VO_CHECK_LAUNCH();
     return VO_OK;
