@@ -72,3 +72,17 @@ def test_batch_and_empty(ctx):
         assert np.array_equal(n1, nxt[f]) and np.array_equal(s1, st[f]) and np.array_equal(e1, err[f])
     n0, s0, e0 = _track(ctx, a[0], b[0], np.zeros((0, 2), np.float32))
     assert n0.shape == (0, 2) and s0.shape == (0,)
+
+
+def test_near_integer_positions(ctx):
+    """window corners a hair off the pixel grid: the fourth bilinear weight 2^14 - (w00 + w01 + w10) rounds to -1
+    or 0, which the packed dp2a path must treat as a signed 16-bit value (integer shifts keep the tracked
+    positions near the grid during the iterations too)"""
+    a, b = _shifted_pair(200, 260, 11, 2, -1)
+    rng = np.random.default_rng(4)
+    base = np.stack([rng.integers(20, 240, 600), rng.integers(20, 180, 600)], axis=1).astype(np.float32)
+    eps = rng.choice(np.array([0.0, 1e-5, 2e-5, 3e-5, 6e-5, 1e-4, -1e-5, -3e-5, 0.5, 0.99997], np.float32), size=(600, 2))
+    pts = (base + eps).astype(np.float32)
+    nxt, st, err = _track(ctx, a, b, pts)
+    nxt_o, st_o, err_o = oracle.klt_track(a, b, pts)
+    assert np.array_equal(st, st_o) and np.array_equal(nxt, nxt_o) and np.array_equal(err, err_o)

@@ -7,6 +7,8 @@
 // Host code only: it sequences the launchers of harris.cu / klt.cu / p3p.cu / triangulation.cu on
 // one stream, so the whole step is capturable in a CUDA graph.
 #include "../../include/vo_b200.h"
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launchers.cuh"
 
@@ -36,6 +38,11 @@ struct vo_frontend {
     int prefetched;           // number of uploaded-but-not-yet-consumed steps (0..2), oldest first
     cudaStream_t copy_stream;  // uploads / downloads of the host entry point overlap compute on the main stream
     cudaEvent_t ev_up[8], ev_done[8];
+    // the stages of a step form a fork-join graph: {pyramid -> KLT}, {Harris response -> NMS}, {P3P -> triangulation};
+    // the latency-bound per-frame kernels (NMS bands, RANSAC replay) then run under the issue-bound ones
+    cudaStream_t side[2];
+    cudaEvent_t ev_fork, ev_level0, ev_harris, ev_pose;
+    int overlap;               // 0: everything on one stream (VO_FRONTEND_SERIAL=1)
 };
 
 extern "C" {
@@ -97,6 +104,20 @@ int vo_frontend_create(vo_ctx* ctx, const vo_frontend_params* prm, vo_frontend**
         VO_CUDA(cudaEventCreateWithFlags(&fe->ev_up[i], cudaEventDisableTiming));
         VO_CUDA(cudaEventCreateWithFlags(&fe->ev_done[i], cudaEventDisableTiming));
     }
+    {   // the side streams get the highest priority: their per-frame, latency-bound kernels are then scheduled
+        // into the SM slots the tracker's short-lived CTAs free, instead of queueing behind its whole grid
+        int prio_lo = 0, prio_hi = 0;
+        VO_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        for (int i = 0; i < 2; i++) VO_CUDA(cudaStreamCreateWithPriority(&fe->side[i], cudaStreamNonBlocking, prio_hi));
+    }
+    VO_CUDA(cudaEventCreateWithFlags(&fe->ev_fork, cudaEventDisableTiming));
+    VO_CUDA(cudaEventCreateWithFlags(&fe->ev_level0, cudaEventDisableTiming));
+    VO_CUDA(cudaEventCreateWithFlags(&fe->ev_harris, cudaEventDisableTiming));
+    VO_CUDA(cudaEventCreateWithFlags(&fe->ev_pose, cudaEventDisableTiming));
+    {
+        const char* e = getenv("VO_FRONTEND_SERIAL");
+        fe->overlap = !(e && e[0] == '1');
+    }
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = fe;
     return VO_OK;
@@ -108,6 +129,8 @@ void vo_frontend_destroy(vo_frontend* fe) {
     cudaStreamSynchronize(fe->ctx->stream);
     cudaStreamSynchronize(fe->copy_stream);
     for (int i = 0; i < 8; i++) { cudaEventDestroy(fe->ev_up[i]); cudaEventDestroy(fe->ev_done[i]); }
+    for (int i = 0; i < 2; i++) { cudaStreamSynchronize(fe->side[i]); cudaStreamDestroy(fe->side[i]); }
+    cudaEventDestroy(fe->ev_fork); cudaEventDestroy(fe->ev_level0); cudaEventDestroy(fe->ev_harris); cudaEventDestroy(fe->ev_pose);
     cudaStreamDestroy(fe->copy_stream);
     cudaFree(fe->stage[0]); cudaFree(fe->stage[1]);
     cudaFree(fe->base);
@@ -144,9 +167,17 @@ static int frontend_run_range(vo_frontend* fe, int s0, int n, const uint8_t* d_f
     uint8_t* pyr_new = fe->pyr[nxt] + (size_t)s0 * fe->frame_bytes;
     const uint8_t* pyr_old = fe->pyr[fe->cur] + (size_t)s0 * fe->frame_bytes;
     int rc;
+    // streams: s carries pyramid -> KLT; sh the Harris detector; sp pose + triangulation.  Both side streams
+    // fork from s and join it again, so the step is still one unit of work on s (and capturable into a graph).
+    cudaStream_t sh = fe->overlap ? fe->side[0] : s, sp = fe->overlap ? fe->side[1] : s;
+    if (fe->overlap) {
+        VO_CUDA(cudaEventRecord(fe->ev_fork, s));
+        VO_CUDA(cudaStreamWaitEvent(sp, fe->ev_fork, 0));
+    }
     // 1. pyramid of the new frames (level 0 copied unless already uploaded into the slot)
     if ((rc = vo_launch_klt_pyramid(ctx, d_frames + (size_t)s0 * frame_stride, n, p.H, p.W, pitch, frame_stride,
-                                    p.klt_max_level, p.klt_win, pyr_new, s))) return rc;
+                                    p.klt_max_level, p.klt_win, pyr_new, s, fe->overlap ? fe->ev_level0 : nullptr))) return rc;
+    if (fe->overlap) VO_CUDA(cudaStreamWaitEvent(sh, fe->ev_level0, 0));
     // 2. KLT: last frame's keypoints into the new frame (klt.py:233-239)
     if (fe->steps > 0) {
         if ((rc = vo_launch_klt_track(ctx, pyr_old, pyr_new, n, p.H, p.W, p.klt_max_level, p.klt_win, p.klt_max_iters,
@@ -156,27 +187,34 @@ static int frontend_run_range(vo_frontend* fe, int s0, int n, const uint8_t* d_f
     }
     // 3. Harris on the new frame (harris.py:86-158); its keypoints seed the next step's tracking
     if ((rc = vo_launch_harris_response(ctx, pyr_new, n, p.H, p.W, fe->pitch0, fe->frame_bytes, p.patch_size, p.kappa,
-                                        fe->resp + (size_t)s0 * npx, s))) return rc;
+                                        fe->resp + (size_t)s0 * npx, sh))) return rc;
     if ((rc = vo_launch_harris_nms(ctx, fe->resp + (size_t)s0 * npx, n, p.H, p.W, p.nms_radius, p.num_keypoints,
-                                   fe->kp + (size_t)s0 * K * 2, nullptr, s))) return rc;
-    if ((rc = vo_launch_kp_to_points(ctx, fe->kp + (size_t)s0 * K * 2, (size_t)n * K, fe->pts_prev + (size_t)s0 * K * 2, s))) return rc;
+                                   fe->kp + (size_t)s0 * K * 2, nullptr, sh))) return rc;
     // 4. P3P + RANSAC (p3p.py:123-186 with use_opencv=False)
     if ((rc = vo_launch_p3p_score(ctx, d_landmarks + (size_t)s0 * N * 3, d_kp2d + (size_t)s0 * N * 2, n, p.n_corr, K9,
                                   d_sample_idx + (size_t)s0 * Hn * 4, p.n_hyp, p.p3p_threshold,
                                   fe->models + (size_t)s0 * Hn * 12, fe->valid + (size_t)s0 * Hn,
-                                  fe->counts + (size_t)s0 * Hn, s))) return rc;
+                                  fe->counts + (size_t)s0 * Hn, sp))) return rc;
     if ((rc = vo_launch_p3p_select(ctx, d_landmarks + (size_t)s0 * N * 3, d_kp2d + (size_t)s0 * N * 2, n, p.n_corr, K9,
                                    fe->models + (size_t)s0 * Hn * 12, fe->valid + (size_t)s0 * Hn,
                                    fe->counts + (size_t)s0 * Hn, p.n_hyp, p.p3p_threshold, d_iters_table, initial_iters, 0, -1,
                                    fe->best4 + (size_t)s0 * 4, fe->consumed + s0, fe->iters_out + s0,
-                                   fe->inliers + (size_t)s0 * N, fe->pose + (size_t)s0 * 12, s))) return rc;
+                                   fe->inliers + (size_t)s0 * N, fe->pose + (size_t)s0 * 12, sp))) return rc;
     // 5. triangulation of new landmarks (triangulation.py:38-86)
     if (p.n_tri > 0) {
         VO_REQUIRE(d_tri_p1 && d_tri_p2 && d_tri_proj1 && d_tri_proj2, "vo_frontend_step: null triangulation input");
         if ((rc = vo_launch_triangulate(ctx, d_tri_p1 + (size_t)s0 * T * 2, d_tri_p2 + (size_t)s0 * T * 2, n * p.n_tri,
                                         d_tri_proj1 + (size_t)s0 * T * 12, 1, d_tri_proj2 + (size_t)s0 * 12, p.n_tri,
-                                        p.tri_mode, fe->tri_out + (size_t)s0 * T * 3, s))) return rc;
+                                        p.tri_mode, fe->tri_out + (size_t)s0 * T * 3, sp))) return rc;
     }
+    // join: the new keypoints replace the tracked set only after the tracker has read it
+    if (fe->overlap) {
+        VO_CUDA(cudaEventRecord(fe->ev_harris, sh));
+        VO_CUDA(cudaEventRecord(fe->ev_pose, sp));
+        VO_CUDA(cudaStreamWaitEvent(s, fe->ev_harris, 0));
+        VO_CUDA(cudaStreamWaitEvent(s, fe->ev_pose, 0));
+    }
+    if ((rc = vo_launch_kp_to_points(ctx, fe->kp + (size_t)s0 * K * 2, (size_t)n * K, fe->pts_prev + (size_t)s0 * K * 2, s))) return rc;
     return VO_OK;
 }
 

@@ -17,7 +17,7 @@ int vo_launch_harris_descriptors(vo_ctx* ctx, const uint8_t* d_img, int n_frames
 int vo_klt_layout_host(int H, int W, int max_level, int win, int* n_levels, int* level_h, int* level_w,
                        size_t* level_pitch, size_t* level_offset, size_t* frame_bytes);
 int vo_launch_klt_pyramid(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
-                          size_t frame_stride, int max_level, int win, uint8_t* d_pyr, cudaStream_t stream);
+                          size_t frame_stride, int max_level, int win, uint8_t* d_pyr, cudaStream_t stream, cudaEvent_t level0_done = nullptr);
 int vo_launch_klt_track(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d_pyr_next, int n_frames, int H, int W,
                         int max_level, int win, int max_iters, double epsilon, double min_eig,
                         const float* d_prev_pts, int n_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
