@@ -81,7 +81,7 @@ def test_near_integer_positions(ctx):
     a, b = _shifted_pair(200, 260, 11, 2, -1)
     rng = np.random.default_rng(4)
     base = np.stack([rng.integers(20, 240, 600), rng.integers(20, 180, 600)], axis=1).astype(np.float32)
-    eps = rng.choice(np.array([0.0, 1e-5, 2e-5, 3e-5, 6e-5, 1e-4, -1e-5, -3e-5, 0.5, 0.99997], np.float32), size=(600, 2))
+    eps = rng.choice(np.array([0.0, 1e-5, 2e-5, 3e-5, 6e-5, 1e-4, -1e-5, -3e-5, 0.5, 0.99997, 3.8e-5, 4.6e-5], np.float32), size=(600, 2))
     pts = (base + eps).astype(np.float32)
     nxt, st, err = _track(ctx, a, b, pts)
     nxt_o, st_o, err_o = oracle.klt_track(a, b, pts)
