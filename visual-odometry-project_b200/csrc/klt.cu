@@ -756,7 +756,9 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
     constexpr int T = (W2 + 31) / 32;                      // window pixels per lane
     constexpr int PATCH_BYTES = (PN * PN + 15) & ~15;
     constexpr int IV_BYTES = (T * 32 * 2 + 15) & ~15;      // padded to whole warps: the unrolled loops read every slot
-    constexpr int PER_WARP = (PATCH_BYTES + DN * DN * 4 + IV_BYTES + T * 32 * 4 + 15) & ~15;
+    constexpr int AN = WIN + 2;                            // side of the interpolated patch of the fast setup
+    constexpr int DP_BYTES = ((AN * AN > DN * DN ? AN * AN : DN * DN) * 4 + 15) & ~15;
+    constexpr int PER_WARP = (PATCH_BYTES + DP_BYTES + IV_BYTES + T * 32 * 4 + 15) & ~15;
     __shared__ __align__(16) unsigned char smem[KLT_SWARPS * PER_WARP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pt = blockIdx.x * KLT_SWARPS + warp;
@@ -764,8 +766,9 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
     if (pt >= n_pts) return;
     uint8_t* patch = smem + warp * PER_WARP;                                  // I (PN^2), later J (DN^2)
     short* dpatch = reinterpret_cast<short*>(patch + PATCH_BYTES);             // [DN*DN][2]
-    short* Iw = reinterpret_cast<short*>(patch + PATCH_BYTES + DN * DN * 4);   // [W2]
-    int* Gw = reinterpret_cast<int*>(patch + PATCH_BYTES + DN * DN * 4 + IV_BYTES);   // [W2]  (Ix | Iy << 16)
+    int* At = reinterpret_cast<int*>(patch + PATCH_BYTES);                     // [AN*AN] (fast setup, same storage)
+    short* Iw = reinterpret_cast<short*>(patch + PATCH_BYTES + DP_BYTES);      // [W2]
+    int* Gw = reinterpret_cast<int*>(patch + PATCH_BYTES + DP_BYTES + IV_BYTES);   // [W2]  (Ix | Iy << 16)
 
     const uint8_t* Ip = pyr_prev + (size_t)f * lay.frame_bytes;
     const uint8_t* Jp = pyr_next + (size_t)f * lay.frame_bytes;
@@ -809,6 +812,40 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
         __syncwarp();
         stage_patch_fast<PN>(I, rows, cols, pitch, ipx - 1, ipy - 1, patch, lane);
         __syncwarp();
+        int sA11 = 0, sA12 = 0, sA22 = 0;
+        if (ipx >= 0 && ipy >= 0 && ipx + DN <= cols && ipy + DN <= rows) {   // warp-uniform
+            // Fast setup.  Every derivative sample of the window lies inside the image, so no sample is zeroed and
+            // the integer identity  sum_k w_k Scharr(I)(p + k) = Scharr(sum_k w_k I(. + k))(p)  holds exactly: first
+            // the un-descaled bilinear patch A (AN x AN, 32-bit), then per window pixel one 3x3 neighbourhood of A
+            // gives I (centre), Ix and Iy.  Same integers as the reference order, a third of the instructions.
+            {
+                int qy = lane / AN, qx = lane - qy * AN;
+#pragma unroll 2
+                for (int i = lane; i < AN * AN; i += 32) {
+                    const uint8_t* s0 = patch + qy * PN + qx;
+                    At[i] = (int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[PN] * iw10 + (int)s0[PN + 1] * iw11;
+                    qx += 32 % AN; qy += 32 / AN;
+                    if (qx >= AN) { qx -= AN; qy++; }
+                }
+            }
+            __syncwarp();
+            int y = ly0, x = lx0;
+#pragma unroll 2
+            for (int i = lane; i < W2; i += 32) {
+                const int* r0 = At + y * AN + x;
+                const int* r1 = r0 + AN;
+                const int* r2 = r1 + AN;
+                const int a00 = r0[0], a01 = r0[1], a02 = r0[2], a10 = r1[0], a11 = r1[1], a12 = r1[2], a20 = r2[0], a21 = r2[1], a22 = r2[2];
+                const int iv = descale(a11, W_BITS - 5);
+                const int ix = descale(((a02 - a00) + (a22 - a20)) * 3 + (a12 - a10) * 10, W_BITS);
+                const int iy = descale(((a20 - a00) + (a22 - a02)) * 3 + (a21 - a01) * 10, W_BITS);
+                Iw[i] = (short)iv;
+                Gw[i] = (ix & 0xFFFF) | (iy << 16);
+                sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
+                x += 32 % WIN; y += 32 / WIN;
+                if (x >= WIN) { x -= WIN; y++; }
+            }
+        } else {
         {
             int qy = lane / DN, qx = lane - qy * DN;
 #pragma unroll 2
@@ -832,7 +869,6 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
             }
         }
         __syncwarp();
-        int sA11 = 0, sA12 = 0, sA22 = 0;
         {
             int y = ly0, x = lx0;
 #pragma unroll 2
@@ -849,6 +885,7 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
                 x += 32 % WIN; y += 32 / WIN;
                 if (x >= WIN) { x -= WIN; y++; }
             }
+        }
         }
         const long long iA11 = warp_sum_exact(sA11), iA12 = warp_sum_exact(sA12), iA22 = warp_sum_exact(sA22);
         const float A11 = (float)iA11 * FLT_SCALE, A12 = (float)iA12 * FLT_SCALE, A22 = (float)iA22 * FLT_SCALE;
