@@ -86,3 +86,35 @@ def test_near_integer_positions(ctx):
     nxt, st, err = _track(ctx, a, b, pts)
     nxt_o, st_o, err_o = oracle.klt_track(a, b, pts)
     assert np.array_equal(st, st_o) and np.array_equal(nxt, nxt_o) and np.array_equal(err, err_o)
+
+
+@pytest.mark.parametrize("shape", [(97, 131), (376, 1241), (61, 63), (64, 256), (130, 243), (33, 1000)])
+def test_pyramid_levels_vs_oracle(ctx, shape):
+    """vo_klt_build_pyramid_dev level by level against the oracle's cv2.pyrDown restatement (bit-exact), sizes whose
+    last input word straddles the border in every way (W % 4 = 0..3), two frames per call"""
+    import ctypes as C
+    import torch
+    from vo import _native as nat
+    H, W = shape
+    imgs = np.stack([synthetic_image(H, W, seed=H + W), synthetic_image(H, W, seed=H * W)])
+    L = nat.lib()
+    nl = C.c_int()
+    lh, lw = (C.c_int * 8)(), (C.c_int * 8)()
+    lp, lo = (C.c_size_t * 8)(), (C.c_size_t * 8)()
+    fb = C.c_size_t()
+    nat.check(L.vo_klt_pyramid_layout(H, W, 3, 5, C.byref(nl), lh, lw, lp, lo, C.byref(fb)), "layout")
+    d_img = torch.from_numpy(imgs).cuda()
+    d_pyr = torch.zeros((2, fb.value), dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    nat.check(L.vo_klt_build_pyramid_dev(ctx.handle, d_img.data_ptr(), 2, H, W, W, H * W, 3, 5, d_pyr.data_ptr(), None), "pyramid")
+    ctx.synchronize()
+    pyr = d_pyr.cpu().numpy()
+    assert nl.value >= 2
+    for f in range(2):
+        ref = imgs[f]
+        for l in range(nl.value):
+            if l > 0:
+                ref = oracle.pyr_down(ref)
+            got = pyr[f, lo[l]:lo[l] + lh[l] * lp[l]].reshape(lh[l], lp[l])[:, :lw[l]]
+            assert ref.shape == (lh[l], lw[l])
+            assert np.array_equal(got, ref), (shape, f, l)

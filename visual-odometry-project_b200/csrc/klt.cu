@@ -28,38 +28,57 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-// cv2.pyrDown (uint8, 1 channel, BORDER_REFLECT_101): separable [1 4 6 4 1] in shared memory.
-// CTA = 64 x 16 outputs: the (2*64+3) x (2*16+3) input region is staged once (reflected at the image
-// border), the horizontal pass writes 35 x 64 row sums (<= 4080, int16), the vertical pass rounds
-// (sum + 128) >> 8 exactly like OpenCV's integer path.
-constexpr int PD_W = 64, PD_H = 16, PD_IW = 2 * PD_W + 3, PD_IH = 2 * PD_H + 3, PD_IP = 132;
-__global__ void __launch_bounds__(256)
+// cv2.pyrDown (uint8, 1 channel, BORDER_REFLECT_101): separable [1 4 6 4 1], streamed by warps, nothing in
+// shared memory.  A lane owns one aligned 32-bit word of an input row (4 pixels = 2 outputs); the two horizontal
+// sums are dp4a([1 4 6 4]) on the word (or on bytes funnelled in from the left neighbour by shuffle) plus the
+// fifth tap; the warp walks down the rows keeping the five row sums of each output in registers, and rounds
+// (sum + 128) >> 8 exactly like OpenCV's integer path.  The first and last lane only feed their neighbours
+// (strips overlap by one word on each side), words that straddle the image border are assembled from
+// reflected byte loads.
+constexpr int PD_WARPS = 8, PD_ROWS = 24, PD_OUT_W = 60;   // 30 words -> 60 outputs per warp, 24 output rows
+__global__ void __launch_bounds__(PD_WARPS * 32)
 pyr_down_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch, size_t sframe,
                 uint8_t* __restrict__ dst, int dh, int dw, size_t dpitch, size_t dframe) {
-    __shared__ uint8_t tile[PD_IH * PD_IP];
-    __shared__ short hs[PD_IH * PD_W];
-    const int ox = blockIdx.x * PD_W, oy = blockIdx.y * PD_H;
+    constexpr unsigned int FULL = 0xFFFFFFFFu, TAPS = 0x04060401u;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * PD_WARPS + warp;
+    if (strip * PD_OUT_W >= dw) return;                   // warp-uniform
+    const int wi = 30 * strip - 1 + lane;                 // this lane's word of the input row
+    const int bx = 4 * wi;
+    const bool fast = bx >= 0 && bx + 3 < W;
     const uint8_t* s = src + (size_t)blockIdx.z * sframe;
-    const int ix0 = 2 * ox - 2, iy0 = 2 * oy - 2;
-    for (int i = threadIdx.x; i < PD_IH * PD_IW; i += 256) {
-        const int ty = i / PD_IW, tx = i - ty * PD_IW;
-        tile[ty * PD_IP + tx] = s[(size_t)reflect101(iy0 + ty, H) * spitch + reflect101(ix0 + tx, W)];
+    uint8_t* d = dst + (size_t)blockIdx.z * dframe;
+    const int oy0 = blockIdx.y * PD_ROWS, oy1 = min(dh, oy0 + PD_ROWS);
+    int rx[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) rx[k] = reflect101(bx + k, W);
+    auto load_word = [&](int iy) -> unsigned int {
+        const uint8_t* r = s + (size_t)reflect101(iy, H) * spitch;
+        if (fast) return *reinterpret_cast<const unsigned int*>(r + bx);
+        return (unsigned int)r[rx[0]] | ((unsigned int)r[rx[1]] << 8) | ((unsigned int)r[rx[2]] << 16) | ((unsigned int)r[rx[3]] << 24);
+    };
+    auto hsum = [&](unsigned int w, int& ha, int& hb) {    // row sums of outputs 2 wi and 2 wi + 1
+        const unsigned int prev = __shfl_up_sync(FULL, w, 1), next = __shfl_down_sync(FULL, w, 1);
+        ha = (int)__dp4a(__byte_perm(prev, w, 0x5432), TAPS, (w >> 16) & 0xFFu);
+        hb = (int)__dp4a(w, TAPS, next & 0xFFu);
+    };
+    int a0, a1, a2, a3, a4, b0, b1, b2, b3, b4;
+    {
+        const unsigned int w0 = load_word(2 * oy0 - 2), w1 = load_word(2 * oy0 - 1), w2 = load_word(2 * oy0);
+        hsum(w0, a0, b0); hsum(w1, a1, b1); hsum(w2, a2, b2);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < PD_IH * PD_W; i += 256) {
-        const int ty = i / PD_W, x = i - ty * PD_W;
-        const uint8_t* r = tile + ty * PD_IP + 2 * x;
-        hs[i] = (short)((int)r[0] + (int)r[4] + 4 * ((int)r[1] + (int)r[3]) + 6 * (int)r[2]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < PD_H * PD_W; i += 256) {
-        const int y = i / PD_W, x = i - y * PD_W;
-        const int dx = ox + x, dy = oy + y;
-        if (dx < dw && dy < dh) {
-            const short* c = hs + (2 * y) * PD_W + x;
-            const int acc = (int)c[0] + (int)c[4 * PD_W] + 4 * ((int)c[PD_W] + (int)c[3 * PD_W]) + 6 * (int)c[2 * PD_W];
-            dst[(size_t)blockIdx.z * dframe + (size_t)dy * dpitch + dx] = (uint8_t)((acc + 128) >> 8);
+    const bool writes = lane >= 1 && lane <= 30 && 2 * wi < dw;
+    for (int y = oy0; y < oy1; y++) {
+        const unsigned int w3 = load_word(2 * y + 1), w4 = load_word(2 * y + 2);
+        hsum(w3, a3, b3); hsum(w4, a4, b4);
+        const unsigned int oa = (unsigned int)(a0 + a4 + 4 * (a1 + a3) + 6 * a2 + 128) >> 8;
+        const unsigned int ob = (unsigned int)(b0 + b4 + 4 * (b1 + b3) + 6 * b2 + 128) >> 8;
+        if (writes) {
+            uint8_t* o = d + (size_t)y * dpitch + 2 * wi;
+            if (2 * wi + 1 < dw) *reinterpret_cast<unsigned short*>(o) = (unsigned short)(oa | (ob << 8));
+            else *o = (uint8_t)oa;
         }
+        a0 = a2; a1 = a3; a2 = a4; b0 = b2; b1 = b3; b2 = b4;
     }
 }
 
@@ -1045,8 +1064,8 @@ int vo_launch_klt_pyramid(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H
     }
     if (level0_done) VO_CUDA(cudaEventRecord(level0_done, stream));   // level 0 is all the Harris detector reads
     for (int l = 1; l < L.n_levels; l++) {
-        dim3 g(vo_div_up(L.w[l], PD_W), vo_div_up(L.h[l], PD_H), n_frames);
-        pyr_down_kernel<<<g, 256, 0, stream>>>(d_pyr + L.offset[l - 1], L.h[l - 1], L.w[l - 1], L.pitch[l - 1],
+        dim3 g(vo_div_up(vo_div_up(L.w[l], PD_OUT_W), PD_WARPS), vo_div_up(L.h[l], PD_ROWS), n_frames);
+        pyr_down_kernel<<<g, PD_WARPS * 32, 0, stream>>>(d_pyr + L.offset[l - 1], L.h[l - 1], L.w[l - 1], L.pitch[l - 1],
                                                L.frame_bytes, d_pyr + L.offset[l], L.h[l], L.w[l], L.pitch[l],
                                                L.frame_bytes);
         ctx->launches++;
