@@ -96,7 +96,7 @@ def test_pyramid_levels_vs_oracle(ctx, shape):
     import torch
     from vo import _native as nat
     H, W = shape
-    imgs = np.stack([synthetic_image(H, W, seed=H + W), synthetic_image(H, W, seed=H * W)])
+    imgs = np.ascontiguousarray(np.stack([synthetic_image(H, W, seed=H + W), synthetic_image(H, W, seed=H * W)]))   # C order
     L = nat.lib()
     nl = C.c_int()
     lh, lw = (C.c_int * 8)(), (C.c_int * 8)()
