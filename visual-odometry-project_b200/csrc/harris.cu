@@ -667,20 +667,25 @@ harris_nms_scan(NmsArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int base = blockIdx.x * (256u * SCAN_PER_THREAD) + threadIdx.x;
     unsigned long long k[SCAN_PER_THREAD];
-    unsigned int sw[SCAN_PER_THREAD];
 #pragma unroll
-    for (int j = 0; j < SCAN_PER_THREAD; j++) {            // all loads first (coalesced, 16 in flight per thread)
+    for (int j = 0; j < SCAN_PER_THREAD; j++) {            // all loads first (coalesced, 8 in flight per thread)
         const unsigned int p = base + j * 256u;
         k[j] = p < npx ? (unsigned long long)__double_as_longlong(__ldg(resp + p)) : 0ull;
-        sw[j] = p < npx ? __ldg(sup + (p >> 5)) : 0xFFFFFFFFu;
     }
+    // cheap test first: only pixels whose high word reaches the threshold's (a fifth of the frame, in blobs) get the
+    // exact comparison and the bitmap lookup, and whole warps skip that when none of their 32 pixels qualifies
+    const unsigned int thi = (unsigned int)(tk >> 32);
     unsigned int keep_mask = 0, cnt = 0, hmin = 0xFFFFFFFFu, hmax = 0u;
 #pragma unroll
     for (int j = 0; j < SCAN_PER_THREAD; j++) {
-        const unsigned int p = base + j * 256u;
-        if (k[j] != 0ull && !((sw[j] >> (p & 31u)) & 1u) && prio_ge(k[j], p, tk, ti)) {
-            keep_mask |= 1u << j; cnt++;
-            hmin = min(hmin, (unsigned int)(k[j] >> 32)); hmax = max(hmax, (unsigned int)(k[j] >> 32));
+        const unsigned int hi = (unsigned int)(k[j] >> 32);
+        const bool maybe = hi >= thi && k[j] != 0ull;
+        if (__any_sync(0xFFFFFFFFu, maybe)) {
+            const unsigned int p = base + j * 256u;
+            if (maybe && prio_ge(k[j], p, tk, ti) && !((__ldg(sup + (p >> 5)) >> (p & 31u)) & 1u)) {
+                keep_mask |= 1u << j; cnt++;
+                hmin = min(hmin, hi); hmax = max(hmax, hi);
+            }
         }
     }
     // block-wide exclusive offsets: warp scan, then one global atomic per CTA
@@ -827,6 +832,10 @@ harris_nms_bands(NmsArgs a) {
     __shared__ unsigned int s_misc[4];
     __shared__ unsigned int s_cnt[8];          // 0/1: new picks, 2/3: blocked (double buffered by round), 4: picks, 5: gather
     __shared__ unsigned int s_ws[32], s_wl[32];
+#ifdef VO_NMS_TIMING
+    __shared__ unsigned int s_dbg[8];
+    if (threadIdx.x < 8) s_dbg[threadIdx.x] = 0;
+#endif
     const int f = blockIdx.x;
     const int H = a.H, W = a.W, r = a.r, K = a.K;
     const unsigned int npx = (unsigned int)H * W;
@@ -984,8 +993,20 @@ harris_nms_bands(NmsArgs a) {
                     }
                     blk = __reduce_add_sync(0xFFFFFFFFu, blk);
                     if (lane == 0 && blk) atomicAdd(&s_cnt[2 + par], blk);
+#ifdef VO_NMS_TIMING
+                    {
+                        const unsigned int nu = __popc(__ballot_sync(0xFFFFFFFFu, und || is_new));
+                        if (lane == 0) {
+                            const unsigned int dtw = (unsigned int)(clock64() - t_x);
+                            atomicMax(&s_dbg[4 + (rounds & 1)], dtw); atomicAdd(&s_dbg[1], dtw); atomicAdd(&s_dbg[3], nu);
+                        }
+                    }
+#endif
                     __syncthreads();
                     VO_NMS_T1(acc_a);
+#ifdef VO_NMS_TIMING
+                    if (tid == 0) { s_dbg[0] += s_dbg[4 + (rounds & 1)]; s_dbg[4 + ((rounds + 1) & 1)] = 0; }
+#endif
                     VO_NMS_T0();
                     const unsigned int n_new = min(s_cnt[par], (unsigned)NMS_NEW_CAP);
                     const unsigned int n_blk = s_cnt[2 + par];
@@ -1148,9 +1169,9 @@ harris_nms_bands(NmsArgs a) {
 #ifdef VO_NMS_TIMING
     __syncthreads();
     if (tid == 0) {   // probe build only: cycles of {sort, bands, final}, bands processed
-        a.stats[f * 4 + 0] = (unsigned int)(t_1 - t_0); a.stats[f * 4 + 1] = (unsigned int)(acc_i + acc_a);
-        a.stats[f * 4 + 2] = (unsigned int)acc_b; a.stats[f * 4 + 3] = (unsigned int)(clock64() - t_2);
-        (void)n_bands;
+        a.stats[f * 4 + 0] = s_dbg[0]; a.stats[f * 4 + 1] = s_dbg[1] / 32u;
+        a.stats[f * 4 + 2] = (unsigned int)acc_a; a.stats[f * 4 + 3] = s_dbg[3];
+        (void)n_bands; (void)t_1; (void)t_2; (void)acc_i; (void)acc_b;
     }
 #endif
 }
