@@ -396,7 +396,8 @@ def main():
             "status": np.empty((S, KP), np.uint8), "err": np.empty((S, KP), np.float32),
             "best4": np.empty((S, 4), np.int32), "inliers": np.empty((S, N), np.uint8),
             "pose": np.empty((S, 12), np.float64), "tri_out": np.empty((S * T, 3), np.float64)}
-    outs = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in outs.items()}
+    # two result sets: the download of step t lands in one while step t+1 is being submitted with the other
+    outs2 = [{k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in outs.items()} for _ in range(2)]
     hb = {k: v.numpy() for k, v in hostbuf.items()}
     pool_np = pool_pinned.numpy()
 
@@ -404,20 +405,27 @@ def main():
         fe2.prefetch_host(pool_np[i % P], hb["landmarks"], hb["kp2d"], hb["samples"], hb["table"], hb["tri_p1"],
                           hb["tri_p2"], hb["tri_proj1"], hb["tri_proj2"])
 
-    def step_host(i):
-        # documented call order: the upload of step i+1 is queued on the copy stream, then step i (whose inputs
-        # were uploaded during step i-1) runs and its results are read back; every step moves h2d + d2h bytes.
+    def submit(i):
+        # documented call order (include/vo_b200.h): the upload of step i+1 is queued, then step i (whose inputs were
+        # uploaded during step i-1) is submitted together with the download of its results.  Every step moves
+        # h2d + d2h bytes; with two steps in flight the GPU always has the next step queued.
         prefetch(i + 1)
-        fe2.step_host(None, None, None, K9, None, None, init, None, None, None, None, outs)
+        fe2.submit_host(None, None, None, K9, None, None, init, None, None, None, None, outs2[i & 1])
+
+    def run_pipelined(first, n):
+        for i in range(n):
+            submit(first + i)
+            if i > 0:
+                fe2.wait_host()           # results of step first + i - 1 are on the host
+        if n > 0:
+            fe2.wait_host()               # drain: results of the last step are on the host
 
     e2e_steps = args.e2e_steps or args.steps
     prefetch(0)
-    for i in range(warmup):
-        step_host(i)
+    run_pipelined(0, warmup)
     barrier()
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        step_host(warmup + i)
+    run_pipelined(warmup, e2e_steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * S * e2e_steps / e2e_s
@@ -448,7 +456,7 @@ def main():
                                     f"({P * S * H * pitch / 1e6:.0f} MB) + {S * H * W * 8 / 1e6:.0f} MB score maps per step",
                        "parallelism": f"{world} x independent sequence shards, no collective"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "vo_frontend_prefetch_host + vo_frontend_step_host (pinned host buffers in, results out, every step; the upload of step t+1 overlaps the compute of step t)"},
+                    "steps": e2e_steps, "api": "vo_frontend_prefetch_host + vo_frontend_submit_host + vo_frontend_wait_host (pinned host buffers in, results out on the host, every step; two steps in flight: the upload of step t+1 and the download of step t-1 overlap the compute of step t)"},
             "gpu_launches": int(launches) * world,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "single_sequence": single,
         }))

@@ -187,6 +187,20 @@ int vo_frontend_step_host(vo_frontend* fe, const uint8_t* h_frames, const double
                           const double* h_tri_proj1, const double* h_tri_proj2, int32_t* h_kp_xy, float* h_tracked,
                           uint8_t* h_status, float* h_err, int32_t* h_best4, uint8_t* h_inliers, double* h_pose,
                           double* h_tri_out);
+/* Pipelined form of vo_frontend_step_host (main.py:248-287 for a stream of frames): submit enqueues the step and
+ * the download of its results into the given host buffers and returns at once; wait blocks until the oldest
+ * submitted step's results are on the host.  Up to two steps may be in flight, so the GPU never idles between
+ * steps and the download of step t runs under the compute of step t+1 (outputs alternate between two device
+ * sets).  Call order: prefetch(0); per step t: prefetch(t+1); submit(t); wait() for step t-1.  The host buffers
+ * of a submitted step must stay untouched until its wait returns.                                       */
+int vo_frontend_submit_host(vo_frontend* fe, const uint8_t* h_frames, const double* h_landmarks, const double* h_kp2d,
+                            const double* K9, const int32_t* h_sample_idx, const int32_t* h_iters_table,
+                            int initial_iters, const double* h_tri_p1, const double* h_tri_p2,
+                            const double* h_tri_proj1, const double* h_tri_proj2, int32_t* h_kp_xy, float* h_tracked,
+                            uint8_t* h_status, float* h_err, int32_t* h_best4, uint8_t* h_inliers, double* h_pose,
+                            double* h_tri_out);
+int vo_frontend_wait_host(vo_frontend* fe);
+
 
 #ifdef __cplusplus
 }

@@ -67,3 +67,48 @@ def test_frontend_matches_individual_ops(ctx, use_prefetch):
             assert np.array_equal(outs["tri_out"][s * T:(s + 1) * T], X)
             assert np.allclose(X, g["X"][s], atol=1e-6)
     fe.close()
+
+
+def test_frontend_pipelined_matches_sequential(ctx):
+    """prefetch + submit + wait with two steps in flight gives, step for step, what step_host gives"""
+    from vo.frontend import Frontend
+    S, H, W, KP, N, Hn, T, n_steps = 2, 120, 200, 150, 300, 128, 64, 6
+    big = [synthetic_image(H + 30, W + 30, seed=70 + s) for s in range(S)]
+    frames = [np.stack([np.ascontiguousarray(b[10 + t:10 + t + H, 10 + 2 * t:10 + 2 * t + W]) for b in big]) for t in range(n_steps)]
+    g = _inputs(S, H, W, N, Hn, T, seed=9)
+    table = np.full(N + 1, 10 ** 6, np.int32)
+    K9 = np.ascontiguousarray(g["K"].reshape(9))
+    args = (g["landmarks"], g["kp2d"], g["samples"], table, g["tri_p1"], g["tri_p2"], g["tri_proj1"], g["tri_proj2"])
+
+    def new_outs():
+        return dict(kp_xy=np.zeros((S, KP, 2), np.int32), tracked=np.zeros((S, KP, 2), np.float32), status=np.zeros((S, KP), np.uint8),
+                    err=np.zeros((S, KP), np.float32), best4=np.zeros((S, 4), np.int32), inliers=np.zeros((S, N), np.uint8),
+                    pose=np.zeros((S, 12)), tri_out=np.zeros((S * T, 3)))
+
+    ref = []
+    fe = Frontend(S, H, W, num_keypoints=KP, n_corr=N, n_hyp=Hn, p3p_threshold=1.5, n_tri=T, tri_mode=1, ctx=ctx)
+    for t in range(n_steps):
+        o = new_outs()
+        fe.step_host(frames[t], g["landmarks"], g["kp2d"], K9, g["samples"], table, 10 ** 6, g["tri_p1"], g["tri_p2"],
+                     g["tri_proj1"], g["tri_proj2"], o)
+        ref.append(o)
+    fe.close()
+
+    fe = Frontend(S, H, W, num_keypoints=KP, n_corr=N, n_hyp=Hn, p3p_threshold=1.5, n_tri=T, tri_mode=1, ctx=ctx)
+    got = [new_outs() for _ in range(n_steps)]
+    fe.prefetch_host(frames[0], *args)
+    for t in range(n_steps):
+        if t + 1 < n_steps:
+            fe.prefetch_host(frames[t + 1], *args)
+        fe.submit_host(None, None, None, K9, None, None, 10 ** 6, None, None, None, None, got[t])
+        if t > 0:
+            fe.wait_host()
+    fe.wait_host()
+    with pytest.raises(Exception):
+        fe.wait_host()                               # nothing in flight any more
+    fe.close()
+    for t in range(n_steps):
+        for k in ref[t]:
+            if t == 0 and k in ("tracked", "status", "err"):
+                continue                             # no previous keypoints at the first step
+            assert np.array_equal(got[t][k], ref[t][k]), (t, k)

@@ -43,6 +43,12 @@ struct vo_frontend {
     cudaStream_t side[2];
     cudaEvent_t ev_fork, ev_level0, ev_harris, ev_pose;
     int overlap;               // 0: everything on one stream (VO_FRONTEND_SERIAL=1)
+    // pipelined host entry point: the step's outputs alternate between two sets so that the download of step t
+    // (on its own stream) runs under the compute of step t+1
+    struct OutSet { int32_t* kp; float* pts_next; float* err; uint8_t* status; int32_t* best4; uint8_t* inliers; double* pose; double* tri_out; } outs[2];
+    cudaStream_t down_stream;
+    cudaEvent_t ev_res[2];
+    int in_flight, sub_next;
 };
 
 extern "C" {
@@ -68,6 +74,8 @@ int vo_frontend_create(vo_ctx* ctx, const vo_frontend_params* prm, vo_frontend**
     const size_t o_st = carve(S * K), o_m = carve(S * Hn * 96), o_v = carve(S * Hn), o_c = carve(S * Hn * 4);
     const size_t o_b4 = carve(S * 16), o_con = carve(S * 4), o_it = carve(S * 4), o_in = carve(S * N), o_pose = carve(S * 96);
     const size_t o_to = carve(S * T * 24 + 256);
+    const size_t o2_kp = carve(S * K * 8), o2_pn = carve(S * K * 8), o2_err = carve(S * K * 4), o2_st = carve(S * K);
+    const size_t o2_b4 = carve(S * 16), o2_in = carve(S * N), o2_pose = carve(S * 96), o2_to = carve(S * T * 24 + 256);
     const size_t o_sl = carve(S * N * 24), o_sk = carve(S * N * 16), o_ss = carve(S * Hn * 16), o_stb = carve((N + 1) * 4);
     const size_t o_fr = carve(S * npx + 256);
     const size_t o_t1 = carve(S * T * 16 + 256), o_t2 = carve(S * T * 16 + 256), o_tp1 = carve(S * T * 96 + 256), o_tp2 = carve(S * 96);
@@ -89,6 +97,10 @@ int vo_frontend_create(vo_ctx* ctx, const vo_frontend_params* prm, vo_frontend**
     fe->s_table = (int32_t*)(b + o_stb); fe->s_tri_p1 = (double*)(b + o_t1); fe->s_tri_p2 = (double*)(b + o_t2);
     fe->s_tri_proj1 = (double*)(b + o_tp1); fe->s_tri_proj2 = (double*)(b + o_tp2);
     fe->s_frames = b + o_fr;
+    fe->outs[0] = {fe->kp, fe->pts_next, fe->err, fe->status, fe->best4, fe->inliers, fe->pose, fe->tri_out};
+    fe->outs[1] = {(int32_t*)(b + o2_kp), (float*)(b + o2_pn), (float*)(b + o2_err), b + o2_st, (int32_t*)(b + o2_b4), b + o2_in,
+                   (double*)(b + o2_pose), (double*)(b + o2_to)};
+    fe->in_flight = 0; fe->sub_next = 0;
     {
         size_t o = 0;
         auto cv = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
@@ -110,6 +122,8 @@ int vo_frontend_create(vo_ctx* ctx, const vo_frontend_params* prm, vo_frontend**
         VO_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
         for (int i = 0; i < 2; i++) VO_CUDA(cudaStreamCreateWithPriority(&fe->side[i], cudaStreamNonBlocking, prio_hi));
     }
+    VO_CUDA(cudaStreamCreateWithFlags(&fe->down_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) VO_CUDA(cudaEventCreateWithFlags(&fe->ev_res[i], cudaEventDisableTiming));
     VO_CUDA(cudaEventCreateWithFlags(&fe->ev_fork, cudaEventDisableTiming));
     VO_CUDA(cudaEventCreateWithFlags(&fe->ev_level0, cudaEventDisableTiming));
     VO_CUDA(cudaEventCreateWithFlags(&fe->ev_harris, cudaEventDisableTiming));
@@ -131,6 +145,8 @@ void vo_frontend_destroy(vo_frontend* fe) {
     for (int i = 0; i < 8; i++) { cudaEventDestroy(fe->ev_up[i]); cudaEventDestroy(fe->ev_done[i]); }
     for (int i = 0; i < 2; i++) { cudaStreamSynchronize(fe->side[i]); cudaStreamDestroy(fe->side[i]); }
     cudaEventDestroy(fe->ev_fork); cudaEventDestroy(fe->ev_level0); cudaEventDestroy(fe->ev_harris); cudaEventDestroy(fe->ev_pose);
+    cudaStreamSynchronize(fe->down_stream); cudaStreamDestroy(fe->down_stream);
+    for (int i = 0; i < 2; i++) cudaEventDestroy(fe->ev_res[i]);
     cudaStreamDestroy(fe->copy_stream);
     cudaFree(fe->stage[0]); cudaFree(fe->stage[1]);
     cudaFree(fe->base);
@@ -244,6 +260,7 @@ static int frontend_upload(vo_frontend* fe, int set, const uint8_t* h_frames, co
     const size_t S = p.n_seq, N = p.n_corr, Hn = p.n_hyp, T = p.n_tri, npx = (size_t)p.H * p.W;
     unsigned char* b = fe->stage[set];
     cudaStream_t cs = fe->copy_stream;
+    VO_CUDA(cudaStreamWaitEvent(cs, fe->ev_done[set], 0));   // the step that read this set before has finished
     // one contiguous copy per array (a pitched 2-D copy of 1241-byte rows is several times slower over PCIe);
     // the pyramid builder re-pitches the frames into the level-0 slots on the device.
     VO_CUDA(cudaMemcpyAsync(b + fe->so_fr, h_frames, S * npx, cudaMemcpyHostToDevice, cs));
@@ -276,26 +293,27 @@ int vo_frontend_prefetch_host(vo_frontend* fe, const uint8_t* h_frames, const do
     return VO_OK;
 }
 
-int vo_frontend_step_host(vo_frontend* fe, const uint8_t* h_frames, const double* h_landmarks, const double* h_kp2d,
-                          const double* K9, const int32_t* h_sample_idx, const int32_t* h_iters_table,
-                          int initial_iters, const double* h_tri_p1, const double* h_tri_p2,
-                          const double* h_tri_proj1, const double* h_tri_proj2, int32_t* h_kp_xy, float* h_tracked,
-                          uint8_t* h_status, float* h_err, int32_t* h_best4, uint8_t* h_inliers, double* h_pose,
-                          double* h_tri_out) {
-    VO_REQUIRE(fe && K9 && h_kp_xy && h_pose, "vo_frontend_step_host: null argument");
+int vo_frontend_submit_host(vo_frontend* fe, const uint8_t* h_frames, const double* h_landmarks, const double* h_kp2d,
+                            const double* K9, const int32_t* h_sample_idx, const int32_t* h_iters_table,
+                            int initial_iters, const double* h_tri_p1, const double* h_tri_p2,
+                            const double* h_tri_proj1, const double* h_tri_proj2, int32_t* h_kp_xy, float* h_tracked,
+                            uint8_t* h_status, float* h_err, int32_t* h_best4, uint8_t* h_inliers, double* h_pose,
+                            double* h_tri_out) {
+    VO_REQUIRE(fe && K9 && h_kp_xy && h_pose, "vo_frontend_submit_host: null argument");
+    VO_REQUIRE(fe->in_flight < 2, "vo_frontend_submit_host: two submitted steps are already in flight (call vo_frontend_wait_host)");
     vo_ctx* ctx = fe->ctx;
     VO_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t s = ctx->stream, cs = fe->copy_stream;
+    cudaStream_t s = ctx->stream, ds = fe->down_stream;
     const vo_frontend_params& p = fe->p;
     const size_t S = p.n_seq, K = p.num_keypoints, N = p.n_corr, T = p.n_tri, npx = (size_t)p.H * p.W;
-    if (T > 0) VO_REQUIRE(h_tri_out, "vo_frontend_step_host: null triangulation output");
+    if (T > 0) VO_REQUIRE(h_tri_out, "vo_frontend_submit_host: null triangulation output");
     int set;
     if (fe->prefetched) {                 // inputs were uploaded by vo_frontend_prefetch_host (host pointers may be NULL)
         set = (fe->stage_next + 2 - fe->prefetched) & 1;     // oldest pending set
         fe->prefetched--;
     } else {
-        VO_REQUIRE(h_frames && h_landmarks && h_kp2d && h_sample_idx && h_iters_table, "vo_frontend_step_host: null input");
-        if (T > 0) VO_REQUIRE(h_tri_p1 && h_tri_p2 && h_tri_proj1 && h_tri_proj2, "vo_frontend_step_host: null triangulation buffer");
+        VO_REQUIRE(h_frames && h_landmarks && h_kp2d && h_sample_idx && h_iters_table, "vo_frontend_submit_host: null input");
+        if (T > 0) VO_REQUIRE(h_tri_p1 && h_tri_p2 && h_tri_proj1 && h_tri_proj2, "vo_frontend_submit_host: null triangulation buffer");
         set = fe->stage_next;
         int rc = frontend_upload(fe, set, h_frames, h_landmarks, h_kp2d, h_sample_idx, h_iters_table, h_tri_p1, h_tri_p2,
                                  h_tri_proj1, h_tri_proj2);
@@ -304,6 +322,12 @@ int vo_frontend_step_host(vo_frontend* fe, const uint8_t* h_frames, const double
     }
     const bool had_prev = fe->steps > 0;
     unsigned char* b = fe->stage[set];
+    // this step writes output set `slot`; its previous contents (two submits ago) must have left the device
+    const int slot = fe->sub_next;
+    const vo_frontend::OutSet& o = fe->outs[slot];
+    VO_CUDA(cudaStreamWaitEvent(s, fe->ev_res[slot], 0));
+    fe->kp = o.kp; fe->pts_next = o.pts_next; fe->err = o.err; fe->status = o.status;
+    fe->best4 = o.best4; fe->inliers = o.inliers; fe->pose = o.pose; fe->tri_out = o.tri_out;
     VO_CUDA(cudaStreamWaitEvent(s, fe->ev_up[set], 0));
     int rc = frontend_run_range(fe, 0, (int)S, b + fe->so_fr, (size_t)p.W, npx, (const double*)(b + fe->so_l),
                                 (const double*)(b + fe->so_k), K9, (const int32_t*)(b + fe->so_s),
@@ -313,17 +337,45 @@ int vo_frontend_step_host(vo_frontend* fe, const uint8_t* h_frames, const double
     if (rc) return rc;
     fe->cur = 1 - fe->cur;
     fe->steps++;
-    // results come back on the compute stream (a prefetch for the following step may be using the copy stream)
-    VO_CUDA(cudaMemcpyAsync(h_kp_xy, fe->kp, S * K * 8, cudaMemcpyDeviceToHost, s));
-    if (had_prev && h_tracked) VO_CUDA(cudaMemcpyAsync(h_tracked, fe->pts_next, S * K * 8, cudaMemcpyDeviceToHost, s));
-    if (had_prev && h_status) VO_CUDA(cudaMemcpyAsync(h_status, fe->status, S * K, cudaMemcpyDeviceToHost, s));
-    if (had_prev && h_err) VO_CUDA(cudaMemcpyAsync(h_err, fe->err, S * K * 4, cudaMemcpyDeviceToHost, s));
-    if (h_best4) VO_CUDA(cudaMemcpyAsync(h_best4, fe->best4, S * 16, cudaMemcpyDeviceToHost, s));
-    if (h_inliers) VO_CUDA(cudaMemcpyAsync(h_inliers, fe->inliers, S * N, cudaMemcpyDeviceToHost, s));
-    VO_CUDA(cudaMemcpyAsync(h_pose, fe->pose, S * 96, cudaMemcpyDeviceToHost, s));
-    if (T > 0) VO_CUDA(cudaMemcpyAsync(h_tri_out, fe->tri_out, S * T * 24, cudaMemcpyDeviceToHost, s));
-    VO_CUDA(cudaStreamSynchronize(s));
+    VO_CUDA(cudaEventRecord(fe->ev_done[set], s));      // staging set free again, outputs complete
+    // results come back on their own stream, under the next step's compute
+    VO_CUDA(cudaStreamWaitEvent(ds, fe->ev_done[set], 0));
+    VO_CUDA(cudaMemcpyAsync(h_kp_xy, o.kp, S * K * 8, cudaMemcpyDeviceToHost, ds));
+    if (had_prev && h_tracked) VO_CUDA(cudaMemcpyAsync(h_tracked, o.pts_next, S * K * 8, cudaMemcpyDeviceToHost, ds));
+    if (had_prev && h_status) VO_CUDA(cudaMemcpyAsync(h_status, o.status, S * K, cudaMemcpyDeviceToHost, ds));
+    if (had_prev && h_err) VO_CUDA(cudaMemcpyAsync(h_err, o.err, S * K * 4, cudaMemcpyDeviceToHost, ds));
+    if (h_best4) VO_CUDA(cudaMemcpyAsync(h_best4, o.best4, S * 16, cudaMemcpyDeviceToHost, ds));
+    if (h_inliers) VO_CUDA(cudaMemcpyAsync(h_inliers, o.inliers, S * N, cudaMemcpyDeviceToHost, ds));
+    VO_CUDA(cudaMemcpyAsync(h_pose, o.pose, S * 96, cudaMemcpyDeviceToHost, ds));
+    if (T > 0) VO_CUDA(cudaMemcpyAsync(h_tri_out, o.tri_out, S * T * 24, cudaMemcpyDeviceToHost, ds));
+    VO_CUDA(cudaEventRecord(fe->ev_res[slot], ds));
+    fe->in_flight++;
+    fe->sub_next = 1 - slot;
     return VO_OK;
+}
+
+int vo_frontend_wait_host(vo_frontend* fe) {
+    VO_REQUIRE(fe, "vo_frontend_wait_host: null argument");
+    VO_REQUIRE(fe->in_flight > 0, "vo_frontend_wait_host: nothing was submitted");
+    VO_CUDA(cudaSetDevice(fe->ctx->device));
+    const int slot = (fe->sub_next + 2 - fe->in_flight) & 1;   // oldest submitted step
+    VO_CUDA(cudaEventSynchronize(fe->ev_res[slot]));
+    fe->in_flight--;
+    return VO_OK;
+}
+
+int vo_frontend_step_host(vo_frontend* fe, const uint8_t* h_frames, const double* h_landmarks, const double* h_kp2d,
+                          const double* K9, const int32_t* h_sample_idx, const int32_t* h_iters_table,
+                          int initial_iters, const double* h_tri_p1, const double* h_tri_p2,
+                          const double* h_tri_proj1, const double* h_tri_proj2, int32_t* h_kp_xy, float* h_tracked,
+                          uint8_t* h_status, float* h_err, int32_t* h_best4, uint8_t* h_inliers, double* h_pose,
+                          double* h_tri_out) {
+    VO_REQUIRE(fe && fe->in_flight == 0, "vo_frontend_step_host: submitted steps are still in flight (call vo_frontend_wait_host)");
+    int rc = vo_frontend_submit_host(fe, h_frames, h_landmarks, h_kp2d, K9, h_sample_idx, h_iters_table, initial_iters, h_tri_p1,
+                                     h_tri_p2, h_tri_proj1, h_tri_proj2, h_kp_xy, h_tracked, h_status, h_err, h_best4, h_inliers,
+                                     h_pose, h_tri_out);
+    if (rc) return rc;
+    return vo_frontend_wait_host(fe);
 }
 
 }  // extern "C"

@@ -76,6 +76,9 @@ def lib():
             "vo_frontend_prefetch_host": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
             "vo_frontend_step_host": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp,
                                             vp, vp, vp, vp, vp, vp, vp, vp]),
+            "vo_frontend_submit_host": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp,
+                                              vp, vp, vp, vp, vp, vp, vp, vp]),
+            "vo_frontend_wait_host": (i32, [vp]),
         })
         for name, (rt, at) in _optional.items():
             if hasattr(L, name):  # all are present in a complete build; tests/test_abi.py checks that

@@ -51,6 +51,23 @@ class Frontend:
             hp(out.get("tri_out")))
         nat.check(rc, "vo_frontend_step_host")
 
+    def submit_host(self, frames, landmarks, kp2d, K9, samples, table, initial_iters, tri_p1, tri_p2, tri_proj1,
+                    tri_proj2, out):
+        """Pipelined step_host: enqueue the step and the download of its results into `out`, return at once.
+        `wait_host()` blocks until the oldest submitted step's results are in its `out` arrays; at most two steps
+        may be in flight, and their `out` arrays must not be touched until the matching wait returns."""
+        def hp(a):
+            return a.ctypes.data_as(C.c_void_p) if a is not None else None
+        rc = nat.lib().vo_frontend_submit_host(
+            self._h, hp(frames), hp(landmarks), hp(kp2d), hp(K9), hp(samples), hp(table), int(initial_iters),
+            hp(tri_p1), hp(tri_p2), hp(tri_proj1), hp(tri_proj2), hp(out["kp_xy"]), hp(out.get("tracked")),
+            hp(out.get("status")), hp(out.get("err")), hp(out.get("best4")), hp(out.get("inliers")), hp(out["pose"]),
+            hp(out.get("tri_out")))
+        nat.check(rc, "vo_frontend_submit_host")
+
+    def wait_host(self):
+        nat.check(nat.lib().vo_frontend_wait_host(self._h), "vo_frontend_wait_host")
+
     def prefetch_host(self, frames, landmarks, kp2d, samples, table, tri_p1, tri_p2, tri_proj1, tri_proj2):
         """Start uploading the NEXT step's inputs while the current step computes (see vo_frontend_prefetch_host)."""
         def hp(a):
