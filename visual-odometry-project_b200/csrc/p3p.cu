@@ -258,34 +258,47 @@ p3p_solve_kernel(const double* __restrict__ landmarks, const double* __restrict_
     valid[(size_t)f * n_hyp + h] = found ? 1 : 0;
 }
 
-// one warp per (frame, hypothesis): inlier count over all N correspondences
-constexpr int COUNT_WARPS = 8;
+// one warp per (frame, hypothesis): inlier count over all N correspondences.  The 16 hypotheses of a CTA belong to
+// the same frame, so its correspondences are staged once per CTA in shared memory as five planes (X, Y, Z, u, v):
+// the inner loop then reads conflict-free 8-byte words instead of waiting on 24-byte-strided global loads, and the
+// FP64 pipe is what is left.
+constexpr int COUNT_WARPS = 16;
+constexpr int COUNT_CHUNK = 1024;       // correspondences staged at a time (40 KB)
 __global__ void __launch_bounds__(COUNT_WARPS * 32)
 p3p_count_kernel(const double* __restrict__ landmarks, const double* __restrict__ keypoints, int N, Intr K,
                  const double* __restrict__ models, const unsigned char* __restrict__ valid, int n_hyp,
                  double threshold, int* __restrict__ counts) {
+    __shared__ double sX[COUNT_CHUNK], sY[COUNT_CHUNK], sZ[COUNT_CHUNK], sU[COUNT_CHUNK], sV[COUNT_CHUNK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x * COUNT_WARPS + warp;
     const int f = blockIdx.y;
-    if (h >= n_hyp) return;
-    const size_t hi = (size_t)f * n_hyp + h;
-    if (!valid[hi]) {
-        if (lane == 0) counts[hi] = 0;
-        return;
-    }
+    const size_t hi = (size_t)f * n_hyp + (h < n_hyp ? h : 0);
+    const bool active = h < n_hyp && valid[hi] != 0;        // warp-uniform; inactive warps still help staging
     double m[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) m[i] = models[hi * 12 + i];
+    for (int i = 0; i < 12; i++) m[i] = active ? models[hi * 12 + i] : 0.0;
     const double* L = landmarks + (size_t)f * N * 3;
     const double* P = keypoints + (size_t)f * N * 2;
     int c = 0;
-    for (int base = 0; base < N; base += 32) {
-        const int i = base + lane;
-        bool in = false;
-        if (i < N) in = reproj_err2(m, L[3 * i], L[3 * i + 1], L[3 * i + 2], P[2 * i], P[2 * i + 1], K) < threshold;
-        c += __popc(__ballot_sync(0xFFFFFFFFu, in));
+    for (int c0 = 0; c0 < N; c0 += COUNT_CHUNK) {
+        const int n = min(COUNT_CHUNK, N - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += COUNT_WARPS * 32) {
+            const double* l = L + 3 * (size_t)(c0 + i);
+            const double* q = P + 2 * (size_t)(c0 + i);
+            sX[i] = l[0]; sY[i] = l[1]; sZ[i] = l[2]; sU[i] = q[0]; sV[i] = q[1];
+        }
+        __syncthreads();
+        if (active) {
+            for (int base = 0; base < n; base += 32) {
+                const int i = base + lane;
+                bool in = false;
+                if (i < n) in = reproj_err2(m, sX[i], sY[i], sZ[i], sU[i], sV[i], K) < threshold;
+                c += __popc(__ballot_sync(0xFFFFFFFFu, in));
+            }
+        }
     }
-    if (lane == 0) counts[hi] = c;
+    if (lane == 0 && h < n_hyp) counts[(size_t)f * n_hyp + h] = c;
 }
 
 // one CTA per frame: ransac.py:90-121 over the pre-scored hypotheses, then the winner's mask
