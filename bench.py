@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--pool", type=int, default=6, help="distinct frame sets cycled through (inputs > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
+    ap.add_argument("--no-single-sequence", action="store_true", help="skip the S = 1 leg (keeps an ncu launch list to one batch size)")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -370,7 +371,7 @@ def main():
 
     # ---- one sequence alone (latency-bound): device-resident steps of a single 1241x376 stream -----
     single = None
-    if rank == 0:
+    if rank == 0 and not args.no_single_sequence:
         fe1 = Frontend(1, H, W, num_keypoints=KP, n_corr=N, n_hyp=Hn, p3p_threshold=P3P_THR, n_tri=T, tri_mode=1, ctx=ctx)
         def step_one(i):
             fr = pool_d[i % P][0:1]
