@@ -796,7 +796,14 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
     const float half = (float)(WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
     const int top = lay.n_levels - 1;
-    const int ly0 = lane / WIN, lx0 = lane - ly0 * WIN;      // window coordinates of this lane's first pixel
+    // Window pixel of (slot t, lane): slots 0..8 hold rows 2t and 2t+1, columns 0..15 (lane = 16 * row parity + column),
+    // slot 9 holds column 16 of row `lane`.  With t a compile-time constant every address is a per-lane base plus an
+    // immediate, so the unrolled loops carry no index arithmetic.  (The generic setup below keeps running counters.)
+    static_assert(WIN == 17, "the slot mapping of klt_track_packed is laid out for a 17 x 17 window");
+    const int ly0 = lane / WIN, lx0 = lane - ly0 * WIN;      // generic setup: i = lane + 32 t walks the window row-major
+    const int hi = lane >> 4, lx = lane & 15;
+    auto slot_y = [&](int t) { return t < T - 1 ? 2 * t + hi : lane; };
+    auto slot_x = [&](int t) { return t < T - 1 ? lx : 16; };
     unsigned int jw[T];
 #pragma unroll
     for (int t = 0; t < T; t++) jw[t] = 0u;
@@ -848,21 +855,20 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
                 }
             }
             __syncwarp();
-            int y = ly0, x = lx0;
-#pragma unroll 2
-            for (int i = lane; i < W2; i += 32) {
-                const int* r0 = At + y * AN + x;
+            const int* a_lane = At + hi * AN + lx;
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const int* r0 = t < T - 1 ? a_lane + t * 2 * AN : At + lane * AN + 16;
+                const bool valid = slot_y(t) < WIN;
                 const int* r1 = r0 + AN;
                 const int* r2 = r1 + AN;
                 const int a00 = r0[0], a01 = r0[1], a02 = r0[2], a10 = r1[0], a11 = r1[1], a12 = r1[2], a20 = r2[0], a21 = r2[1], a22 = r2[2];
-                const int iv = descale(a11, W_BITS - 5);
-                const int ix = descale(((a02 - a00) + (a22 - a20)) * 3 + (a12 - a10) * 10, W_BITS);
-                const int iy = descale(((a20 - a00) + (a22 - a02)) * 3 + (a21 - a01) * 10, W_BITS);
-                Iw[i] = (short)iv;
-                Gw[i] = (ix & 0xFFFF) | (iy << 16);
+                const int iv = valid ? descale(a11, W_BITS - 5) : 0;
+                const int ix = valid ? descale(((a02 - a00) + (a22 - a20)) * 3 + (a12 - a10) * 10, W_BITS) : 0;
+                const int iy = valid ? descale(((a20 - a00) + (a22 - a02)) * 3 + (a21 - a01) * 10, W_BITS) : 0;
+                Iw[t * 32 + lane] = (short)iv;
+                Gw[t * 32 + lane] = (ix & 0xFFFF) | (iy << 16);
                 sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
-                x += 32 % WIN; y += 32 / WIN;
-                if (x >= WIN) { x -= WIN; y++; }
             }
         } else {
         {
@@ -889,9 +895,10 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
         }
         __syncwarp();
         {
-            int y = ly0, x = lx0;
-#pragma unroll 2
-            for (int i = lane; i < W2; i += 32) {
+#pragma unroll 1
+            for (int t = 0; t < T; t++) {
+                const int y = slot_y(t), x = slot_x(t), i = t * 32 + lane;
+                if (y >= WIN) { Iw[i] = 0; Gw[i] = 0; continue; }
                 const uint8_t* s0 = patch + (y + 1) * PN + (x + 1);
                 const int iv = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[PN] * iw10 + (int)s0[PN + 1] * iw11, W_BITS - 5);
                 const short* d0 = dpatch + 2 * (y * DN + x);
@@ -901,8 +908,6 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
                 Iw[i] = (short)iv;
                 Gw[i] = (ix & 0xFFFF) | (iy << 16);
                 sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
-                x += 32 % WIN; y += 32 / WIN;
-                if (x >= WIN) { x -= WIN; y++; }
             }
         }
         }
@@ -941,25 +946,23 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
                 const bool inside = inx >= 0 && iny >= 0 && inx + DN <= cols && iny + DN <= rows;   // warp-uniform
                 if (inside) {
                     const uint8_t* base = J + (size_t)iny * pitch + inx;
-                    int y = ly0, x = lx0;
+                    const int ip = (int)pitch;
+                    int off = hi * ip + lx;
 #pragma unroll
                     for (int t = 0; t < T; t++) {
-                        const uint8_t* s0 = base + y * (int)pitch + x;
-                        jw[t] = (t * 32 + lane < W2) ? ((unsigned)s0[0] | ((unsigned)s0[1] << 8) | ((unsigned)s0[pitch] << 16) | ((unsigned)s0[pitch + 1] << 24)) : 0u;
-                        x += 32 % WIN; y += 32 / WIN;
-                        if (x >= WIN) { x -= WIN; y++; }
+                        const uint8_t* s0 = t < T - 1 ? base + off : base + lane * ip + 16;
+                        jw[t] = slot_y(t) < WIN ? ((unsigned)s0[0] | ((unsigned)s0[1] << 8) | ((unsigned)s0[ip] << 16) | ((unsigned)s0[ip + 1] << 24)) : 0u;
+                        off += 2 * ip;
                     }
                 } else {
                     __syncwarp();
                     stage_patch_fast<DN>(J, rows, cols, pitch, inx, iny, patch, lane);
                     __syncwarp();
-                    int y = ly0, x = lx0;
+                    const uint8_t* p_lane = patch + hi * DN + lx;
 #pragma unroll
                     for (int t = 0; t < T; t++) {
-                        const uint8_t* s0 = patch + y * DN + x;
-                        jw[t] = (t * 32 + lane < W2) ? ((unsigned)s0[0] | ((unsigned)s0[1] << 8) | ((unsigned)s0[DN] << 16) | ((unsigned)s0[DN + 1] << 24)) : 0u;
-                        x += 32 % WIN; y += 32 / WIN;
-                        if (x >= WIN) { x -= WIN; y++; }
+                        const uint8_t* s0 = t < T - 1 ? p_lane + t * 2 * DN : patch + lane * DN + 16;
+                        jw[t] = slot_y(t) < WIN ? ((unsigned)s0[0] | ((unsigned)s0[1] << 8) | ((unsigned)s0[DN] << 16) | ((unsigned)s0[DN + 1] << 24)) : 0u;
                     }
                 }
                 sx = inx; sy = iny;
