@@ -754,6 +754,32 @@ klt_track_small(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict_
 // at a compile-time offset, so the unrolled loop has no index arithmetic.
 // ---------------------------------------------------------------------------------------------
 
+// (win+3)^2 = 20 x 20 patch of klt_track_packed<17>: rows in pairs x 16 columns (10 loads per lane at a running
+// offset) + the last four columns (3 loads per lane); when the patch crosses the border the generic path reflects.
+__device__ __forceinline__ void stage_patch20(const uint8_t* __restrict__ img, int rows, int cols, size_t pitch,
+                                              int x0, int y0, uint8_t* sm, int lane) {
+    constexpr int N = 20;
+    if (!(x0 >= 0 && y0 >= 0 && x0 + N <= cols && y0 + N <= rows)) {       // warp-uniform
+        stage_patch_fast<N>(img, rows, cols, pitch, x0, y0, sm, lane);
+        return;
+    }
+    const uint8_t* base = img + (size_t)y0 * pitch + x0;
+    const int ip = (int)pitch, hi = lane >> 4, lx = lane & 15, qy = lane >> 2, qx = 16 + (lane & 3);
+    uint8_t v[13];
+    int off = hi * ip + lx;
+#pragma unroll
+    for (int t = 0; t < 10; t++) { v[t] = base[off]; off += 2 * ip; }
+    off = qy * ip + qx;
+#pragma unroll
+    for (int u = 0; u < 3; u++) { v[10 + u] = (8 * u + qy < N) ? base[off] : (uint8_t)0; off += 8 * ip; }
+    uint8_t* s0 = sm + hi * N + lx;
+#pragma unroll
+    for (int t = 0; t < 10; t++) s0[t * 2 * N] = v[t];
+    uint8_t* s1 = sm + qy * N + qx;
+#pragma unroll
+    for (int u = 0; u < 3; u++) if (8 * u + qy < N) s1[u * 8 * N] = v[10 + u];
+}
+
 // dp2a with signed 16-bit halves of a and unsigned bytes of b: c + a.lo * b.byte0 + a.hi * b.byte1 (lo) / bytes 2, 3 (hi)
 __device__ __forceinline__ int dp2a_lo_su(unsigned int a, unsigned int b, int c) {
     int d;
@@ -836,7 +862,7 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
         int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
 
         __syncwarp();
-        stage_patch_fast<PN>(I, rows, cols, pitch, ipx - 1, ipy - 1, patch, lane);
+        stage_patch20(I, rows, cols, pitch, ipx - 1, ipy - 1, patch, lane);
         __syncwarp();
         int sA11 = 0, sA12 = 0, sA22 = 0;
         if (ipx >= 0 && ipy >= 0 && ipx + DN <= cols && ipy + DN <= rows) {   // warp-uniform
@@ -844,14 +870,23 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
             // the integer identity  sum_k w_k Scharr(I)(p + k) = Scharr(sum_k w_k I(. + k))(p)  holds exactly: first
             // the un-descaled bilinear patch A (AN x AN, 32-bit), then per window pixel one 3x3 neighbourhood of A
             // gives I (centre), Ix and Iy.  Same integers as the reference order, a third of the instructions.
-            {
-                int qy = lane / AN, qx = lane - qy * AN;
-#pragma unroll 2
-                for (int i = lane; i < AN * AN; i += 32) {
-                    const uint8_t* s0 = patch + qy * PN + qx;
-                    At[i] = (int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[PN] * iw10 + (int)s0[PN + 1] * iw11;
-                    qx += 32 % AN; qy += 32 / AN;
-                    if (qx >= AN) { qx -= AN; qy++; }
+            {   // AN x AN = 19 x 19 positions: row pairs x 16 columns (10 slots), then columns 16..18 (2 slots)
+                const uint8_t* p_lane = patch + hi * PN + lx;
+                int* o_lane = At + hi * AN + lx;
+#pragma unroll
+                for (int t = 0; t < 10; t++) {
+                    const uint8_t* s0 = p_lane + t * 2 * PN;
+                    const int a = (int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[PN] * iw10 + (int)s0[PN + 1] * iw11;
+                    if (2 * t + hi < AN) o_lane[t * 2 * AN] = a;
+                }
+                // remaining 3 x 19 = 57 positions, column-major: position q = lane + 32 u -> (row q % 19, column 16 + q / 19)
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const int q = lane + 32 * u, qc = q / AN, qr = q - qc * AN;
+                    if (q < 3 * AN) {
+                        const uint8_t* s0 = patch + qr * PN + 16 + qc;
+                        At[qr * AN + 16 + qc] = (int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[PN] * iw10 + (int)s0[PN + 1] * iw11;
+                    }
                 }
             }
             __syncwarp();
