@@ -558,7 +558,8 @@ struct NmsArgs {
     unsigned int* mem;                 // [F][bm_words] bitmap: undecided entry of the current band (global fallback only)
     unsigned int bm_words;             // words per frame bitmap (H*W/32 + 2: the range helpers read one word ahead)
     uint4* ent_a;                      // [F][H*W] entries {pixel, key lo, key hi, y << 16 | x} in scan order
-    uint4* ent_b;                      // [F][H*W] the same entries ordered by priority bin
+    unsigned int* ent_h;               // [F][H*W] high words of the entries' scores (all the binning pass needs)
+    uint4* ent_b;                      // [F][H*W] the same entries ordered by priority bin (filled lazily from the top)
     unsigned long long* pick_key;      // [F][lm_cap]
     unsigned int* pick_idx;            // [F][lm_cap]
     int* kp_xy;                        // [F][K][2]
@@ -653,7 +654,7 @@ harris_nms_select(NmsArgs a) {
 // ---- every box.  Only these can still become picks.
 constexpr int SCAN_PER_THREAD = 8;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 harris_nms_scan(NmsArgs a) {
     __shared__ unsigned int s_base;
     __shared__ unsigned int s_warp[8], s_min[8], s_max[8];
@@ -662,6 +663,7 @@ harris_nms_scan(NmsArgs a) {
     const double* resp = a.resp + (size_t)f * npx;
     const unsigned int* sup = a.sup + (size_t)f * a.bm_words;
     uint4* ent = a.ent_a + (size_t)f * npx;
+    unsigned int* enth = a.ent_h + (size_t)f * npx;
     const unsigned long long tk = a.thr_key[f];
     const unsigned int ti = a.thr_idx[f];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -715,6 +717,7 @@ harris_nms_scan(NmsArgs a) {
     for (int j = 0; j < SCAN_PER_THREAD; j++)
         if (keep_mask & (1u << j)) {
             const unsigned int p = base + j * 256u, py = p / (unsigned)a.W;
+            enth[o] = (unsigned int)(k[j] >> 32);
             ent[o++] = make_uint4(p, (unsigned int)k[j], (unsigned int)(k[j] >> 32), (py << 16) | (p - py * (unsigned)a.W));
         }
 }
@@ -729,6 +732,7 @@ harris_nms_scan(NmsArgs a) {
 constexpr int NMS_BINS = 2048;
 constexpr int NMS_BAND = 1024;       // entries per band (one per thread)
 constexpr int NMS_NEW_CAP = 1024;    // new picks per round (the surplus waits for the next round)
+constexpr int NMS_LAZY = 8192;       // entries put in order per scatter pass
 constexpr int NMS_HASH = 2048;       // open-addressing table for the (at most NMS_BAND) undecided entries of a band
 constexpr unsigned int NMS_EMPTY = 0xFFFFFFFFu;
 constexpr size_t NMS_TABLES_BYTES = (size_t)(3 * NMS_BINS + NMS_NEW_CAP) * 4 + (size_t)NMS_HASH * 16 + (size_t)NMS_NEW_CAP * 8;
@@ -841,6 +845,7 @@ harris_nms_bands(NmsArgs a) {
     const unsigned int npx = (unsigned int)H * W;
     const double* resp = a.resp + (size_t)f * npx;
     const uint4* ent_a = a.ent_a + (size_t)f * npx;
+    const unsigned int* ent_h = a.ent_h + (size_t)f * npx;
     uint4* ent_b = a.ent_b + (size_t)f * npx;
     unsigned long long* pk = a.pick_key + (size_t)f * a.lm_cap;
     unsigned int* pi = a.pick_idx + (size_t)f * a.lm_cap;
@@ -882,7 +887,7 @@ harris_nms_bands(NmsArgs a) {
         for (unsigned int j0 = 0; j0 < n; j0 += 8 * N_THREADS) {          // loads batched: this loop is latency bound
             unsigned int z[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) { const unsigned int j = j0 + u * N_THREADS + tid; z[u] = j < n ? ent_a[j].z : 0u; }
+            for (int u = 0; u < 8; u++) { const unsigned int j = j0 + u * N_THREADS + tid; z[u] = j < n ? ent_h[j] : 0u; }
 #pragma unroll
             for (int u = 0; u < 8; u++) if (j0 + u * N_THREADS + tid < n) atomicAdd(&endR[(gmax - z[u]) >> shift], 1u);
         }
@@ -911,15 +916,34 @@ harris_nms_bands(NmsArgs a) {
             lmR[2 * tid] = el + l0; lmR[2 * tid + 1] = el + l0 + l1;
         }
         __syncthreads();
-        for (unsigned int j0 = 0; j0 < n; j0 += 8 * N_THREADS) {
-            uint4 e[8];
+        // The ordered list is filled lazily from the top: the loop below usually stops after a few thousand entries,
+        // so only the ranks that hold the first NMS_LAZY entries are scattered now (one pass over the high words, full
+        // entries fetched for those ranks only); extend() adds the next ranks if the bands get that far.
+        unsigned int sorted_upto = 0;                        // entries [0, sorted_upto) of ent_b are in place
+        int r_sorted = -1;                                   // ... they are the ranks <= r_sorted
+        auto extend = [&](unsigned int needed) {
+            while (sorted_upto < needed && sorted_upto < n) {
+                int lo = r_sorted + 1, hi = NMS_BINS - 1;    // smallest rank whose cumulative count reaches the target
+                const unsigned int target = min(n, max(needed, sorted_upto + (unsigned)NMS_LAZY));
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (endR[mid] >= target) hi = mid; else lo = mid + 1; }
+                const unsigned int r_lo = (unsigned int)(r_sorted + 1), r_hi = (unsigned int)lo;
+                for (unsigned int j0 = 0; j0 < n; j0 += 8 * N_THREADS) {
+                    unsigned int z[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) { const unsigned int j = j0 + u * N_THREADS + tid; if (j < n) e[u] = ent_a[j]; }
+                    for (int u = 0; u < 8; u++) { const unsigned int j = j0 + u * N_THREADS + tid; z[u] = j < n ? ent_h[j] : 0u; }
 #pragma unroll
-            for (int u = 0; u < 8; u++)
-                if (j0 + u * N_THREADS + tid < n) ent_b[atomicAdd(&cur[(gmax - e[u].z) >> shift], 1u)] = e[u];
-        }
-        __syncthreads();
+                    for (int u = 0; u < 8; u++) {
+                        const unsigned int j = j0 + u * N_THREADS + tid;
+                        const unsigned int rk = (gmax - z[u]) >> shift;
+                        if (j < n && rk >= r_lo && rk <= r_hi) ent_b[atomicAdd(&cur[rk], 1u)] = ent_a[j];
+                    }
+                }
+                r_sorted = lo;
+                sorted_upto = endR[lo];
+                __syncthreads();
+            }
+        };
+        extend(1u);
 #ifdef VO_NMS_TIMING
         t_1 = clock64();
 #endif
@@ -939,12 +963,14 @@ harris_nms_bands(NmsArgs a) {
         int par = 0, r_cur = -1, r_next = -1;
         unsigned int b0 = 0, b1 = band_end(0u, -1, &r_cur), b2 = b1;
         uint4 e_next = make_uint4(0u, 0u, 0u, 0u);
+        extend(b1);
         if (b0 + tid < b1) e_next = ent_b[b0 + tid];
         while (true) {
             VO_NMS_T0();
             const uint4 ec = e_next;
             if (b1 < n) {
                 b2 = band_end(b1, r_cur, &r_next);
+                extend(b2);
                 if (b1 + tid < b2) e_next = ent_b[b1 + tid];
             }
             const bool single = b1 - b0 <= (unsigned)N_THREADS;    // the normal case: one entry per thread, scores hashed
@@ -1310,7 +1336,7 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_lmk = carve(F * lm_cap * 8), o_lmi = carve(F * lm_cap * 4), o_cnt = carve(F * 4);
     const size_t o_sup = carve(F * bm_words * 4), o_mem = carve(bm_smem ? 0 : F * bm_words * 4);
-    const size_t o_ea = carve(F * npx * 16), o_eb = carve(F * npx * 16);
+    const size_t o_ea = carve(F * npx * 16), o_eb = carve(F * npx * 16), o_eh = carve(F * npx * 4);
     const size_t o_pk = carve(F * lm_cap * 8), o_pi = carve(F * lm_cap * 4);
     const size_t o_stats = carve(F * 16);
     const size_t o_tk = carve(F * 8), o_ti = carve(F * 4), o_ctr = carve(F * 16);
@@ -1347,7 +1373,7 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     a.lm_count = (unsigned int*)(base + o_cnt);
     a.sup = (unsigned int*)(base + o_sup); a.mem = bm_smem ? nullptr : (unsigned int*)(base + o_mem);
     a.bm_words = (unsigned)bm_words;
-    a.ent_a = (uint4*)(base + o_ea); a.ent_b = (uint4*)(base + o_eb);
+    a.ent_a = (uint4*)(base + o_ea); a.ent_b = (uint4*)(base + o_eb); a.ent_h = (unsigned int*)(base + o_eh);
     a.pick_key = (unsigned long long*)(base + o_pk); a.pick_idx = (unsigned int*)(base + o_pi);
     a.kp_xy = d_kp_xy;
     a.stats = d_stats_or_null ? d_stats_or_null : (unsigned int*)(base + o_stats);
