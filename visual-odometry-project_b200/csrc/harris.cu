@@ -654,7 +654,7 @@ harris_nms_select(NmsArgs a) {
 // ---- every box.  Only these can still become picks.
 constexpr int SCAN_PER_THREAD = 8;
 
-__global__ void __launch_bounds__(256, 6)
+__global__ void __launch_bounds__(256, 8)
 harris_nms_scan(NmsArgs a) {
     __shared__ unsigned int s_base;
     __shared__ unsigned int s_warp[8], s_min[8], s_max[8];
@@ -1143,33 +1143,103 @@ harris_nms_bands(NmsArgs a) {
     __syncthreads();
     for (unsigned int j = tid; j < P2; j += N_THREADS) { sk[j] = 0ull; si[j] = 0xFFFFFFFFu; }
     __syncthreads();
-    for (unsigned int j = tid; j < n_picks; j += N_THREADS) {
-        const unsigned long long k = qk[j];
-        const unsigned int i = qi[j];
-        if (prio_ge(k, i, fk, fi)) {
-            const unsigned int s = atomicAdd(&s_cnt[5], 1u);
-            if (s < P2) { sk[s] = k; si[s] = i; }
+    if (sort_all || n_picks <= (unsigned)K) {                 // every pick is kept: plain copy
+        for (unsigned int j = tid; j < n_picks; j += N_THREADS) { sk[j] = qk[j]; si[j] = qi[j]; }
+    } else {
+        for (unsigned int j0 = 0; j0 < n_picks; j0 += N_THREADS) {   // one atomic per warp for the slots
+            const unsigned int j = j0 + tid;
+            unsigned long long k = 0ull;
+            unsigned int i = 0u;
+            bool keep = false;
+            if (j < n_picks) { k = qk[j]; i = qi[j]; keep = prio_ge(k, i, fk, fi); }
+            const unsigned int mk = __ballot_sync(0xFFFFFFFFu, keep);
+            unsigned int base_s = 0;
+            if (lane == 0 && mk) base_s = atomicAdd(&s_cnt[5], (unsigned int)__popc(mk));
+            base_s = __shfl_sync(0xFFFFFFFFu, base_s, 0);
+            const unsigned int sl = base_s + __popc(mk & ((1u << lane) - 1u));
+            if (keep && sl < P2) { sk[sl] = k; si[sl] = i; }
         }
     }
     __syncthreads();
-    // bitonic sort, highest priority first
-    for (unsigned int size = 2; size <= P2; size <<= 1) {
-        for (unsigned int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (unsigned int j = tid; j < P2; j += N_THREADS) {
-                const unsigned int l = j ^ stride;
-                if (l > j) {
-                    const bool desc = ((j & size) == 0);
-                    const unsigned long long kj = sk[j], kl = sk[l];
-                    const unsigned int ij = si[j], il = si[l];
-                    const bool j_first = prio_gt(kj, ij, kl, il);  // j has higher priority
-                    if (desc ? !j_first : j_first) {
-                        if (!(kj == kl && ij == il)) { sk[j] = kl; sk[l] = kj; si[j] = il; si[l] = ij; }
+#ifdef VO_NMS_TIMING
+    const long long t_f1 = clock64();
+#endif
+    // bitonic sort, highest priority first.  Element e = tid + 1024 u lives in registers; compare-exchanges with a
+    // partner less than 32 elements away (45 of the 66 stages for 2048 elements) are warp shuffles, the others go
+    // through shared memory.  P2 <= 4096 here: at most four elements per thread.
+    if (P2 <= 4u * N_THREADS) {
+        unsigned long long kr[4];
+        unsigned int ir[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned int e = tid + u * N_THREADS;
+            kr[u] = e < P2 ? sk[e] : 0ull; ir[u] = e < P2 ? si[e] : 0xFFFFFFFFu;
+        }
+        const int n_u = (int)((P2 + N_THREADS - 1) / N_THREADS);     // elements per thread in use
+        auto stage_shfl = [&](unsigned int size, unsigned int stride) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (u >= n_u) break;
+                const unsigned int e = tid + u * N_THREADS;
+                const unsigned long long ko = __shfl_xor_sync(0xFFFFFFFFu, kr[u], stride);
+                const unsigned int io = __shfl_xor_sync(0xFFFFFFFFu, ir[u], stride);
+                const bool lower = (e & stride) == 0, desc = (e & size) == 0;
+                // (j, l) = (lower, upper) element of the pair; exchange when their order contradicts the direction
+                const bool j_first = lower ? prio_gt(kr[u], ir[u], ko, io) : prio_gt(ko, io, kr[u], ir[u]);
+                if (desc ? !j_first : j_first) { kr[u] = ko; ir[u] = io; }
+            }
+        };
+        for (unsigned int size = 2; size <= P2; size <<= 1) {
+            unsigned int stride = size >> 1;
+            if (stride >= 32u) {
+                __syncthreads();
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const unsigned int e = tid + u * N_THREADS; if (e < P2) { sk[e] = kr[u]; si[e] = ir[u]; } }
+                __syncthreads();
+                for (; stride >= 32u; stride >>= 1) {
+                    for (unsigned int j = tid; j < P2; j += N_THREADS) {
+                        const unsigned int l = j ^ stride;
+                        if (l > j) {
+                            const bool desc = ((j & size) == 0);
+                            const unsigned long long kj = sk[j], kl = sk[l];
+                            const unsigned int ij = si[j], il = si[l];
+                            const bool j_first = prio_gt(kj, ij, kl, il);  // j has higher priority
+                            if (desc ? !j_first : j_first) { sk[j] = kl; sk[l] = kj; si[j] = il; si[l] = ij; }
+                        }
+                    }
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) { const unsigned int e = tid + u * N_THREADS; if (e < P2) { kr[u] = sk[e]; ir[u] = si[e]; } }
+            }
+            for (; stride > 0; stride >>= 1) stage_shfl(size, stride);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const unsigned int e = tid + u * N_THREADS; if (e < P2) { sk[e] = kr[u]; si[e] = ir[u]; } }
+        __syncthreads();
+    } else {
+        for (unsigned int size = 2; size <= P2; size <<= 1) {
+            for (unsigned int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (unsigned int j = tid; j < P2; j += N_THREADS) {
+                    const unsigned int l = j ^ stride;
+                    if (l > j) {
+                        const bool desc = ((j & size) == 0);
+                        const unsigned long long kj = sk[j], kl = sk[l];
+                        const unsigned int ij = si[j], il = si[l];
+                        const bool j_first = prio_gt(kj, ij, kl, il);  // j has higher priority
+                        if (desc ? !j_first : j_first) {
+                            if (!(kj == kl && ij == il)) { sk[j] = kl; sk[l] = kj; si[j] = il; si[l] = ij; }
+                        }
                     }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
+#ifdef VO_NMS_TIMING
+    const long long t_f2 = clock64();
+#endif
     // harris.py:150 with a negative slice start zeroes nothing: the same pixel is returned for
     // every remaining iteration.  Find the first such pick (if any).
     if (tid == 0) s_misc[0] = 0xFFFFFFFFu;
@@ -1195,8 +1265,8 @@ harris_nms_bands(NmsArgs a) {
 #ifdef VO_NMS_TIMING
     __syncthreads();
     if (tid == 0) {   // probe build only: cycles of {sort, bands, final}, bands processed
-        a.stats[f * 4 + 0] = s_dbg[0]; a.stats[f * 4 + 1] = s_dbg[1] / 32u;
-        a.stats[f * 4 + 2] = (unsigned int)acc_a; a.stats[f * 4 + 3] = s_dbg[3];
+        a.stats[f * 4 + 0] = (unsigned int)(t_1 - t_0); a.stats[f * 4 + 1] = (unsigned int)(t_f1 - t_2);
+        a.stats[f * 4 + 2] = (unsigned int)(t_f2 - t_f1); a.stats[f * 4 + 3] = (unsigned int)(clock64() - t_f2);
         (void)n_bands; (void)t_1; (void)t_2; (void)acc_i; (void)acc_b;
     }
 #endif
