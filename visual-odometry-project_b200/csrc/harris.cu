@@ -162,8 +162,19 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
     // next tile is requested as soon as phase H has consumed the current one, so its HBM latency hides
     // behind phase V.  Tiles start 11 columns left of a multiple of 128 so that the TMA box (which begins
     // 5 columns further left) starts on a 16-byte boundary, as cp.async.bulk.tensor needs for 1-byte data.
-    auto issue_load = [&](int t) {
-        const int bx = t % tiles_x, by = (t / tiles_x) % tiles_y, fr = t / (tiles_x * tiles_y);
+    // tile t -> (column bx, row by, frame fr), advanced by the grid stride without divisions (the decomposition of
+    // the stride is computed once; a division per tile and thread was 8 % of the kernel's instructions)
+    const int st_x = (int)gridDim.x % tiles_x, st_q = (int)gridDim.x / tiles_x, st_y = st_q % tiles_y, st_f = st_q / tiles_y;
+    auto advance = [&](int& bx, int& by, int& fr) {
+        bx += st_x;
+        const int cx = bx >= tiles_x ? 1 : 0;
+        bx -= cx ? tiles_x : 0;
+        by += st_y + cx;
+        const int cy = by >= tiles_y ? 1 : 0;
+        by -= cy ? tiles_y : 0;
+        fr += st_f + cy;
+    };
+    auto issue_load = [&](int bx, int by, int fr) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(FT_IMG_BYTES) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -172,12 +183,14 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if ((int)blockIdx.x < n_tiles) issue_load(blockIdx.x);
     }
+    int tbx = (int)blockIdx.x % tiles_x, tby = ((int)blockIdx.x / tiles_x) % tiles_y, tfr = (int)blockIdx.x / (tiles_x * tiles_y);
+    if (tid == 0 && (int)blockIdx.x < n_tiles) issue_load(tbx, tby, tfr);
     __syncthreads();
     uint32_t parity = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, parity ^= 1) {
-    const int x0 = (tile % tiles_x) * FT_W - FT_XSHIFT, y0 = ((tile / tiles_x) % tiles_y) * FT_H, f = tile / (tiles_x * tiles_y);
+    const int x0 = tbx * FT_W - FT_XSHIFT, y0 = tby * FT_H, f = tfr;
+    advance(tbx, tby, tfr);                                  // now the coordinates of this CTA's next tile
     {   // all threads wait for the tile
         uint32_t done = 0;
         while (!done) {
@@ -237,7 +250,7 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
     __syncthreads();
     if (tid == 0 && tile + (int)gridDim.x < n_tiles) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of img precede the async overwrite
-        issue_load(tile + gridDim.x);
+        issue_load(tbx, tby, tfr);
     }
     // ---------------- phase V ----------------
     {
