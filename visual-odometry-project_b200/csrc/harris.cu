@@ -360,14 +360,33 @@ __device__ __forceinline__ bool localmax_exact_lane(const double* __restrict__ s
         if (y < 0 || y >= H) continue;
         const double* row = src + (size_t)y * W + xc;
         if (R > 0) {
-            unsigned long long qk[2 * R + 1];
+            // high words first (4-byte loads, one compare each): a larger one ends the test, an equal one (rare) asks
+            // for the low word.  Candidates away from the left / right border skip the column range checks.
+            const unsigned int chi = (unsigned int)(ck >> 32), clo = (unsigned int)ck;
+            const unsigned int* rowh = reinterpret_cast<const unsigned int*>(row) + 1;
+            unsigned int qh[2 * R + 1];
+            if (xc >= R && xc + R < W) {
 #pragma unroll
-            for (int dx = -R; dx <= R; dx++)
-                qk[dx + R] = (xc + dx >= 0 && xc + dx < W) ? (unsigned long long)__double_as_longlong(__ldg(row + dx)) : 0ull;
+                for (int dx = -R; dx <= R; dx++) qh[dx + R] = __ldg(rowh + 2 * dx);
+            } else {
+#pragma unroll
+                for (int dx = -R; dx <= R; dx++) qh[dx + R] = (xc + dx >= 0 && xc + dx < W) ? __ldg(rowh + 2 * dx) : 0u;
+            }
+            bool gt = false;
+            unsigned int tie = 0u;
 #pragma unroll
             for (int dx = -R; dx <= R; dx++) {
-                const bool before = (dy < 0) || (dy == 0 && dx < 0);   // raster order: ties go to the earlier pixel
-                if (!(dy == 0 && dx == 0) && (before ? (qk[dx + R] >= ck) : (qk[dx + R] > ck))) ok = false;
+                if (dy == 0 && dx == 0) continue;
+                gt = gt || qh[dx + R] > chi;
+                if (qh[dx + R] == chi) tie |= 1u << (dx + R);
+            }
+            if (gt) { ok = false; break; }
+            while (tie) {                                    // equal high words: the low words decide (ties by raster order)
+                const int dx = __ffs(tie) - 1 - R;
+                tie &= tie - 1u;
+                const unsigned int qlo = (xc + dx >= 0 && xc + dx < W) ? __ldg(rowh + 2 * dx - 1) : 0u;
+                const bool before = (dy < 0) || (dy == 0 && dx < 0);
+                if (before ? (qlo >= clo) : (qlo > clo)) ok = false;
             }
         } else {
             for (int dx = -r; dx <= r; dx++) {
