@@ -589,7 +589,7 @@ struct NmsArgs {
     unsigned int* sup;                 // [F][bm_words] bitmap: pixel lies in the box of a pick
     unsigned int* mem;                 // [F][bm_words] bitmap: undecided entry of the current band (global fallback only)
     unsigned int bm_words;             // words per frame bitmap (H*W/32 + 2: the range helpers read one word ahead)
-    uint4* ent_a;                      // [F][H*W] entries {pixel, key lo, key hi, y << 16 | x} in scan order
+    uint4* ent_a;                      // [F][H*W] entries {pixel, key lo, key hi, -} in scan order
     unsigned int* ent_h;               // [F][H*W] high words of the entries' scores (all the binning pass needs)
     uint4* ent_b;                      // [F][H*W] the same entries ordered by priority bin (filled lazily from the top)
     unsigned long long* pick_key;      // [F][lm_cap]
@@ -700,6 +700,7 @@ harris_nms_scan(NmsArgs a) {
     const unsigned int ti = a.thr_idx[f];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int base = blockIdx.x * (256u * SCAN_PER_THREAD) + threadIdx.x;
+    const unsigned int cta_row = (blockIdx.x * (256u * SCAN_PER_THREAD)) / (unsigned)a.W;   // uniform: row of the CTA's first pixel
     unsigned long long k[SCAN_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < SCAN_PER_THREAD; j++) {            // all loads first (coalesced, 8 in flight per thread)
@@ -748,9 +749,11 @@ harris_nms_scan(NmsArgs a) {
 #pragma unroll
     for (int j = 0; j < SCAN_PER_THREAD; j++)
         if (keep_mask & (1u << j)) {
-            const unsigned int p = base + j * 256u, py = p / (unsigned)a.W;
+            const unsigned int p = base + j * 256u;
+            unsigned int py = cta_row, px = p - cta_row * (unsigned)a.W;   // no division: walk from the CTA's first row
+            while (px >= (unsigned)a.W) { px -= (unsigned)a.W; py++; }
             enth[o] = (unsigned int)(k[j] >> 32);
-            ent[o++] = make_uint4(p, (unsigned int)k[j], (unsigned int)(k[j] >> 32), (py << 16) | (p - py * (unsigned)a.W));
+            ent[o++] = make_uint4(p, (unsigned int)k[j], (unsigned int)(k[j] >> 32), (py << 16) | px);
         }
 }
 
@@ -1093,7 +1096,7 @@ harris_nms_bands(NmsArgs a) {
                         if (!bm_test(M, p)) continue;
                         if (bm_test(S, p)) { atomicAnd(&M[p >> 5], ~(1u << (p & 31u))); continue; }
                         const unsigned long long k = ((unsigned long long)e.z << 32) | e.y;
-                        const int py = (int)(e.w >> 16), px = (int)(e.w & 0xFFFFu);
+                        const int py = (int)(p / (unsigned)W), px = (int)(p - (unsigned)py * W);
                         const int x0 = max(px - r, 0), len = min(px + r, W - 1) - x0 + 1;
                         bool blocked = false;
                         for (int dy = -r; dy <= r && !blocked; dy++) {
