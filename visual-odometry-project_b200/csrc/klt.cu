@@ -87,9 +87,9 @@ pyr_down_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch, si
 __global__ void __launch_bounds__(256)
 copy_level0_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch, size_t sframe,
                    uint8_t* __restrict__ dst, size_t dpitch, size_t dframe) {
-    const int x = (blockIdx.x * 256 + threadIdx.x) * 16;
-    const int y = blockIdx.y;
-    if (x >= W) return;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;      // a block covers several rows when a row needs few threads
+    if (x >= W || y >= H) return;
     const uint8_t* s = src + (size_t)blockIdx.z * sframe + (size_t)y * spitch + x;
     uint8_t* d = dst + (size_t)blockIdx.z * dframe + (size_t)y * dpitch + x;
     if (x + 16 <= W) {
@@ -1095,8 +1095,10 @@ int vo_launch_klt_pyramid(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H
     VO_REQUIRE(klt_layout(H, W, max_level, win, &L) == 0, "klt: max_level must be in [0, %d)", KLT_MAX_LEVELS);
     // level 0: copy unless the caller already placed the frames in the pyramid's level-0 slots
     if (!(d_img == d_pyr && pitch == L.pitch[0] && frame_stride == L.frame_bytes)) {
-        dim3 g(vo_div_up(vo_div_up(W, 16), 256), H, n_frames);
-        copy_level0_kernel<<<g, 256, 0, stream>>>(d_img, H, W, pitch, frame_stride, d_pyr, L.pitch[0], L.frame_bytes);
+        const int chunks = vo_div_up(W, 16);
+        const int bx = chunks >= 256 ? 256 : ((chunks + 31) & ~31), by = 256 / bx > 0 ? 256 / bx : 1;
+        dim3 g(vo_div_up(chunks, bx), vo_div_up(H, by), n_frames), b(bx, by);
+        copy_level0_kernel<<<g, b, 0, stream>>>(d_img, H, W, pitch, frame_stride, d_pyr, L.pitch[0], L.frame_bytes);
         ctx->launches++;
         VO_CHECK_LAUNCH();
     }
