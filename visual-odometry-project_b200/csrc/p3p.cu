@@ -290,11 +290,12 @@ p3p_count_kernel(const double* __restrict__ landmarks, const double* __restrict_
         }
         __syncthreads();
         if (active) {
-            for (int base = 0; base < n; base += 32) {
-                const int i = base + lane;
-                bool in = false;
-                if (i < n) in = reproj_err2(m, sX[i], sY[i], sZ[i], sU[i], sV[i], K) < threshold;
-                c += __popc(__ballot_sync(0xFFFFFFFFu, in));
+            for (int base = 0; base < n; base += 64) {     // two points per lane and step: independent FP64 chains
+                const int i0 = base + lane, i1 = i0 + 32;
+                bool in0 = false, in1 = false;
+                if (i0 < n) in0 = reproj_err2(m, sX[i0], sY[i0], sZ[i0], sU[i0], sV[i0], K) < threshold;
+                if (i1 < n) in1 = reproj_err2(m, sX[i1], sY[i1], sZ[i1], sU[i1], sV[i1], K) < threshold;
+                c += __popc(__ballot_sync(0xFFFFFFFFu, in0)) + __popc(__ballot_sync(0xFFFFFFFFu, in1));
             }
         }
     }
