@@ -12,9 +12,11 @@
 // NMS: the reference repeats {argmax; zero a (2r+1)^2 box} K times (harris.py:148-152).  That
 // sequence equals the first K elements, in priority order (score desc, linear index asc), of the
 // greedy maximal independent set of the "within Chebyshev distance r" graph.  It is computed here
-// by (1) a dense local-maximum pass, (2) a per-frame threshold = K-th best local maximum (nothing
-// below it can be among the first K picks), (3) iterated local-maximum rounds over the still-alive
-// pixels above the threshold, (4) a final select + sort of the K best picks.
+// by (1) a dense local-maximum pass (local maxima are always picks), (2) a per-frame threshold = K-th
+// best local maximum (nothing below it can be among the first K picks) and a bitmap of the boxes of the
+// maxima above it, (3) one scan that lists the pixels above the threshold outside those boxes, (4) a
+// per-frame kernel that walks that list in priority bands -- inside a band, rounds of "no undecided
+// neighbour of higher priority -> pick, suppress the box" -- until K picks are known, then sorts them.
 #include <cuda.h>
 
 #include "common.cuh"
