@@ -112,3 +112,35 @@ def test_frontend_pipelined_matches_sequential(ctx):
             if t == 0 and k in ("tracked", "status", "err"):
                 continue                             # no previous keypoints at the first step
             assert np.array_equal(got[t][k], ref[t][k]), (t, k)
+
+
+def test_frontend_submit_limits(ctx):
+    """at most two submitted steps in flight; step_host refuses to run while submits are pending"""
+    from vo.frontend import Frontend
+    from vo._native import VoNativeError
+    S, H, W, KP, N, Hn, T = 1, 96, 128, 50, 100, 32, 16
+    frame = np.stack([synthetic_image(H, W, seed=3)])
+    g = _inputs(S, H, W, N, Hn, T, seed=2)
+    table = np.full(N + 1, 10 ** 6, np.int32)
+    K9 = np.ascontiguousarray(g["K"].reshape(9))
+    fe = Frontend(S, H, W, num_keypoints=KP, n_corr=N, n_hyp=Hn, p3p_threshold=1.5, n_tri=T, tri_mode=1, ctx=ctx)
+
+    def outs():
+        return dict(kp_xy=np.zeros((S, KP, 2), np.int32), tracked=np.zeros((S, KP, 2), np.float32), status=np.zeros((S, KP), np.uint8),
+                    err=np.zeros((S, KP), np.float32), best4=np.zeros((S, 4), np.int32), inliers=np.zeros((S, N), np.uint8),
+                    pose=np.zeros((S, 12)), tri_out=np.zeros((S * T, 3)))
+
+    args = (frame, g["landmarks"], g["kp2d"], K9, g["samples"], table, 10 ** 6, g["tri_p1"], g["tri_p2"], g["tri_proj1"], g["tri_proj2"])
+    o = [outs() for _ in range(3)]
+    fe.submit_host(*args, o[0])
+    fe.submit_host(*args, o[1])
+    with pytest.raises(VoNativeError):
+        fe.submit_host(*args, o[2])
+    with pytest.raises(VoNativeError):
+        fe.step_host(*args, o[2])
+    fe.wait_host()
+    fe.wait_host()
+    assert np.array_equal(o[0]["kp_xy"], o[1]["kp_xy"])     # same frame twice: same detections
+    fe.step_host(*args, o[2])
+    assert np.array_equal(o[2]["kp_xy"], o[0]["kp_xy"])
+    fe.close()
