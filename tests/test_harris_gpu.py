@@ -141,3 +141,32 @@ def test_nms_large_frame_global_bitmaps(ctx):
     m = uniform_filter(m, 7) * (rng.random((H, W)) > 0.2)
     kp, st = _nms_dev(ctx, m, 700, 5)
     assert np.array_equal(kp[0], oracle.harris_nms(np.ascontiguousarray(m), 700, 5))
+
+
+def test_nms_random_soak(ctx):
+    """100 random (size, radius, K, score-map family) cases against the literal argmax loop: sparse noise, few-valued
+    plateaus, smoothed blobs, 600 decades of dynamic range, quantised ramps"""
+    from scipy.ndimage import uniform_filter
+    rng = np.random.default_rng(2024)
+    n = 0
+    for it in range(100):
+        H, W, r = int(rng.integers(24, 200)), int(rng.integers(24, 260)), int(rng.integers(0, 8))
+        kind = it % 6
+        if kind == 0:
+            m = rng.random((H, W)) * (rng.random((H, W)) > rng.random())
+        elif kind == 1:
+            m = rng.integers(0, int(rng.integers(2, 9)), (H, W)).astype(np.float64)
+        elif kind == 2:
+            m = uniform_filter(rng.random((H, W)) ** 6, int(rng.integers(2, 9))) * (rng.random((H, W)) > 0.1)
+        elif kind == 3:
+            m = 10.0 ** rng.uniform(-300, 300, (H, W)) * (rng.random((H, W)) > 0.4)
+        elif kind == 4:
+            m = np.round(uniform_filter(rng.random((H, W)), 5) * 20) / 20
+        else:
+            m = uniform_filter(rng.random((H, W)) ** 3, 3)
+        K = int(rng.integers(1, max(2, H * W // ((r + 1) ** 2) // 2 + 2)))
+        m = np.ascontiguousarray(m)
+        kp, _ = _nms_dev(ctx, m, K, r)
+        assert np.array_equal(kp[0], oracle.harris_nms(m, K, r)), (it, kind, H, W, r, K)
+        n += 1
+    assert n == 100
