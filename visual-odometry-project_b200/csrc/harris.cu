@@ -692,6 +692,8 @@ __global__ void __launch_bounds__(256, 8)
 harris_nms_scan(NmsArgs a) {
     __shared__ unsigned int s_base;
     __shared__ unsigned int s_warp[8], s_min[8], s_max[8];
+    // per warp: the pixels that pass the cheap test, then the kept ones {pixel, score lo, score hi}
+    __shared__ unsigned int s_qp[8][32 * SCAN_PER_THREAD], s_ql[8][32 * SCAN_PER_THREAD], s_qh[8][32 * SCAN_PER_THREAD];
     const int f = blockIdx.y;
     const unsigned int npx = (unsigned int)a.H * a.W;
     const double* resp = a.resp + (size_t)f * npx;
@@ -701,6 +703,7 @@ harris_nms_scan(NmsArgs a) {
     const unsigned long long tk = a.thr_key[f];
     const unsigned int ti = a.thr_idx[f];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
     const unsigned int base = blockIdx.x * (256u * SCAN_PER_THREAD) + threadIdx.x;
     const unsigned int cta_row = (blockIdx.x * (256u * SCAN_PER_THREAD)) / (unsigned)a.W;   // uniform: row of the CTA's first pixel
     unsigned long long k[SCAN_PER_THREAD];
@@ -709,35 +712,44 @@ harris_nms_scan(NmsArgs a) {
         const unsigned int p = base + j * 256u;
         k[j] = p < npx ? (unsigned long long)__double_as_longlong(__ldg(resp + p)) : 0ull;
     }
-    // cheap test first: only pixels whose high word reaches the threshold's (a fifth of the frame, in blobs) get the
-    // exact comparison and the bitmap lookup, and whole warps skip that when none of their 32 pixels qualifies
+    // Cheap test first (high word against the threshold's): about a fifth of the pixels pass, in blobs, so nearly
+    // every warp has some at every step -- evaluating the exact test under predication would cost all 32 lanes
+    // each time.  The passing pixels are queued per warp instead and the exact comparison, the bitmap lookup and
+    // the emission then run on dense lanes.
     const unsigned int thi = (unsigned int)(tk >> 32);
-    unsigned int keep_mask = 0, cnt = 0, hmin = 0xFFFFFFFFu, hmax = 0u;
+    unsigned int *qp = s_qp[warp], *ql = s_ql[warp], *qh = s_qh[warp];
+    unsigned int nq = 0;
 #pragma unroll
     for (int j = 0; j < SCAN_PER_THREAD; j++) {
-        const unsigned int hi = (unsigned int)(k[j] >> 32);
-        const bool maybe = hi >= thi && k[j] != 0ull;
-        if (__any_sync(0xFFFFFFFFu, maybe)) {
-            const unsigned int p = base + j * 256u;
-            if (maybe && prio_ge(k[j], p, tk, ti) && !((__ldg(sup + (p >> 5)) >> (p & 31u)) & 1u)) {
-                keep_mask |= 1u << j; cnt++;
-                hmin = min(hmin, hi); hmax = max(hmax, hi);
-            }
-        }
+        const bool maybe = (unsigned int)(k[j] >> 32) >= thi && k[j] != 0ull;
+        const unsigned int m = __ballot_sync(0xFFFFFFFFu, maybe);
+        if (maybe) { const unsigned int t = nq + __popc(m & lt); qp[t] = base + j * 256u; ql[t] = (unsigned int)k[j]; qh[t] = (unsigned int)(k[j] >> 32); }
+        nq += __popc(m);
     }
-    // block-wide exclusive offsets: warp scan, then one global atomic per CTA
-    unsigned int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += v;
+    __syncwarp();
+    unsigned int nk = 0, hmin = 0xFFFFFFFFu, hmax = 0u;    // kept entries are compacted to the front of the queue
+    for (unsigned int i0 = 0; i0 < nq; i0 += 32) {
+        const unsigned int i = i0 + lane;
+        uint4 e = make_uint4(0u, 0u, 0u, 0u);
+        bool keep = false;
+        if (i < nq) {
+            e = make_uint4(qp[i], ql[i], qh[i], 0u);
+            keep = prio_ge(((unsigned long long)e.z << 32) | e.y, e.x, tk, ti) && !((__ldg(sup + (e.x >> 5)) >> (e.x & 31u)) & 1u);
+        }
+        const unsigned int m = __ballot_sync(0xFFFFFFFFu, keep);
+        __syncwarp();                                        // all lanes have read their slot before slots <= i0 + 31 are rewritten
+        if (keep) {
+            const unsigned int t = nk + __popc(m & lt);
+            qp[t] = e.x; ql[t] = e.y; qh[t] = e.z;
+            hmin = min(hmin, e.z); hmax = max(hmax, e.z);
+        }
+        nk += __popc(m);
     }
     hmin = __reduce_min_sync(0xFFFFFFFFu, hmin);
     hmax = __reduce_max_sync(0xFFFFFFFFu, hmax);
-    if (lane == 31) s_warp[warp] = incl;
-    if (lane == 0) { s_min[warp] = hmin; s_max[warp] = hmax; }
+    if (lane == 0) { s_warp[warp] = nk; s_min[warp] = hmin; s_max[warp] = hmax; }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {                                  // one global atomic per CTA
         unsigned int t = 0, mn = 0xFFFFFFFFu, mx = 0u;
         for (int w = 0; w < 8; w++) {
             const unsigned int c = s_warp[w]; s_warp[w] = t; t += c;
@@ -747,16 +759,14 @@ harris_nms_scan(NmsArgs a) {
         if (t) { atomicMin(&a.counters[f * 4 + 2], mn); atomicMax(&a.counters[f * 4 + 3], mx); }
     }
     __syncthreads();
-    unsigned int o = s_base + s_warp[warp] + incl - cnt;
-#pragma unroll
-    for (int j = 0; j < SCAN_PER_THREAD; j++)
-        if (keep_mask & (1u << j)) {
-            const unsigned int p = base + j * 256u;
-            unsigned int py = cta_row, px = p - cta_row * (unsigned)a.W;   // no division: walk from the CTA's first row
-            while (px >= (unsigned)a.W) { px -= (unsigned)a.W; py++; }
-            enth[o] = (unsigned int)(k[j] >> 32);
-            ent[o++] = make_uint4(p, (unsigned int)k[j], (unsigned int)(k[j] >> 32), (py << 16) | px);
-        }
+    const unsigned int o = s_base + s_warp[warp];
+    for (unsigned int i = lane; i < nk; i += 32) {
+        const uint4 e = make_uint4(qp[i], ql[i], qh[i], 0u);
+        unsigned int py = cta_row, px = e.x - cta_row * (unsigned)a.W;   // no division: walk from the CTA's first row
+        while (px >= (unsigned)a.W) { px -= (unsigned)a.W; py++; }
+        enth[o + i] = e.z;
+        ent[o + i] = make_uint4(e.x, e.y, e.z, (py << 16) | px);
+    }
 }
 
 // ---- NMS step 4 (one CTA per frame): the entries are ordered into priority bins (high word of the score, 2048
