@@ -208,6 +208,28 @@ def cpu_pipeline_fps(n_frames, steps, warmup, Hn, threads):
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_near_gpu(local_rank):
+    """Pin this process to the CPUs NVML names as closest to its GPU, so that the pinned staging buffers are allocated on
+    that socket and uploads do not cross the inter-socket link.  Best effort: returns a short description."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].strip().isdigit() else local_rank
+        h = nv.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return f"bound to {len(use)} cpus near gpu {phys}"
+        return f"no binding ({len(cpus)} ideal cpus, {len(allowed)} allowed)"
+    except Exception as ex:   # NVML or the affinity call not available: run unbound
+        return f"no binding ({type(ex).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -256,6 +278,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_near_gpu(local_rank)         # host thread + pinned buffers on the GPU's own socket (matters from 4 GPUs up)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = nat.Context(local_rank)
@@ -455,7 +478,7 @@ def main():
                        "sequences_per_gpu": S, "frames_per_step": world * S,
                        "l2_policy": f"inputs larger than L2: {P} frame sets of {S} frames cycled "
                                     f"({P * S * H * pitch / 1e6:.0f} MB) + {S * H * W * 8 / 1e6:.0f} MB score maps per step",
-                       "parallelism": f"{world} x independent sequence shards, no collective"},
+                       "parallelism": f"{world} x independent sequence shards, no collective", "host_binding": numa},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "vo_frontend_prefetch_host + vo_frontend_submit_host + vo_frontend_wait_host (pinned host buffers in, results out on the host, every step; two steps in flight: the upload of step t+1 and the download of step t-1 overlap the compute of step t)"},
             "gpu_launches": int(launches) * world,
