@@ -14,6 +14,10 @@
  *  - Images are uint8, row-major, `pitch` bytes between rows, `frame_stride` bytes between the
  *    frames of a batch.  Points are (x, y) = (column, row), as in the reference's (N, 2, 1) arrays.
  *  - There is no CPU fallback: without a CUDA device vo_ctx_create fails.
+ *  - A vo_ctx belongs to one device and owns the working memory its launchers carve from: calls that share a
+ *    context must be ordered on ONE stream (use one context per stream).  Resident objects (vo_frontend,
+ *    vo_pipeline) reserve their working memory at creation; a `_dev` call that would have to grow it while its
+ *    stream is being captured into a CUDA graph fails with a clear error instead of allocating.
  */
 #ifndef VO_B200_H
 #define VO_B200_H
@@ -99,12 +103,13 @@ int vo_klt_track_host(vo_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next,
 /* ---- P3P + RANSAC: src/vo/pose_estimation/p3p.py:51-108, src/vo/algorithms/ransac.py:69-129 --- */
 /* For every hypothesis h (4 sample indices: 3 for P3P, the 4th disambiguates, as cv2.solvePnP with
  * SOLVEPNP_P3P does) solve the pose, count reprojection inliers (squared pixel error < threshold,
- * p3p.py:104-108 / ransac.py:104-106), and return per-hypothesis models, validity and counts.
+ * p3p.py:104-108 / ransac.py:104-106; with inclusive != 0 `<=`, the rule of cv2.solvePnPRansac that the
+ * reference's use_opencv=True path applies, p3p.py:142-151), and return per-hypothesis models, validity and counts.
  * landmarks float64 [n_frames][N][3], keypoints float64 [n_frames][N][2], K9 float64 [9] row-major (HOST pointer),
  * sample_idx int32 [n_frames][n_hyp][4].  models float64 [n_frames][n_hyp][12] = R (row-major) | t. */
 int vo_p3p_ransac_score_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
                             int N, const double* K9, const int32_t* d_sample_idx, int n_hyp, double threshold,
-                            double* d_models, uint8_t* d_valid, int32_t* d_counts, void* stream);
+                            int inclusive, double* d_models, uint8_t* d_valid, int32_t* d_counts, void* stream);
 /* ransac.py:90-121 sequential scan with the adaptive iteration count.  d_iters_for_count is the
  * host-computed table n_iterations(best_n_inliers), best_n_inliers = 0..N (ransac.py:58-67,115-120);
  * initial_iters / start_n / start_best carry the loop state in (ransac.py:56,81,84; start_best = -1
@@ -114,13 +119,13 @@ int vo_p3p_ransac_score_dev(vo_ctx* ctx, const double* d_landmarks, const double
  * invalid, i.e. RNG draws); d_iters_out = n_iterations at exit; inlier mask uint8 [N]; model [12]. */
 int vo_p3p_ransac_select_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
                              int N, const double* K9, const double* d_models, const uint8_t* d_valid,
-                             const int32_t* d_counts, int n_hyp, double threshold, const int32_t* d_iters_for_count,
+                             const int32_t* d_counts, int n_hyp, double threshold, int inclusive, const int32_t* d_iters_for_count,
                              int initial_iters, int start_n, int start_best, int32_t* d_best4, int32_t* d_consumed,
                              int32_t* d_iters_out, uint8_t* d_inliers, double* d_best_model, void* stream);
 /* Host-buffer variant: score + select.  h_counts / h_valid / h_models may be NULL.  K9 and
  * h_iters_for_count (int32 [N+1]) are host pointers in every variant.                           */
 int vo_p3p_ransac_host(vo_ctx* ctx, const double* h_landmarks, const double* h_keypoints, int n_frames, int N,
-                       const double* K9, const int32_t* h_sample_idx, int n_hyp, double threshold,
+                       const double* K9, const int32_t* h_sample_idx, int n_hyp, double threshold, int inclusive,
                        const int32_t* h_iters_for_count, int initial_iters, int start_n, int start_best,
                        int32_t* h_best4, int32_t* h_consumed, int32_t* h_iters_out, uint8_t* h_inliers,
                        double* h_best_model, int32_t* h_counts, uint8_t* h_valid, double* h_models);

@@ -126,7 +126,7 @@ def test_abi_exports_every_declared_symbol():
     L = nat.lib()
     missing = [n for n in sorted(names) if not hasattr(L, n)]
     assert not missing, missing
-    assert L.vo_abi_version() == 1
+    assert L.vo_abi_version() == 2
     out = subprocess.run(["nm", "-D", "--defined-only", nat.LIB_PATH], capture_output=True, text=True).stdout
     for n in names:
         assert f" T {n}" in out, n

@@ -1,5 +1,6 @@
 // extern "C" boundary of libvo_b200.so -- see include/vo_b200.h for the contract.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/vo_b200.h"
 #include "common.cuh"
@@ -14,8 +15,17 @@ void vo_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int vo_buf_reserve(VoBuf* b, size_t bytes) {
+// Growing a scratch buffer frees and reallocates (a device-wide synchronisation, illegal under stream capture):
+// resident objects (vo_frontend / vo_pipeline) reserve their worst case at creation so that steps never get here.
+int vo_buf_reserve(VoBuf* b, size_t bytes, cudaStream_t launch_stream) {
     if (bytes <= b->cap) return VO_OK;
+    if (launch_stream) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(launch_stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+            vo_set_error("scratch growth to %zu bytes requested during stream capture: reserve it before capturing", bytes);
+            return VO_ERR_CAPACITY;
+        }
+    }
     if (b->p) VO_CUDA(cudaFree(b->p));
     b->p = nullptr;
     b->cap = 0;
@@ -42,7 +52,7 @@ static inline cudaStream_t pick_stream(vo_ctx* ctx, void* stream) {
 
 extern "C" {
 
-int vo_abi_version(void) { return 1; }
+int vo_abi_version(void) { return 2; }
 const char* vo_last_error(void) { return g_err; }
 
 int vo_ctx_create(vo_ctx** out, int device) {
@@ -63,7 +73,18 @@ int vo_ctx_create(vo_ctx** out, int device) {
     vo_ctx* c = new vo_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    VO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // environment switches are read here, once; launch paths only look at the context
+        const char* e;
+        c->env_harris_no_tma = (e = getenv("VO_HARRIS_NO_TMA")) && e[0] == '1';
+        c->env_klt_generic = (e = getenv("VO_KLT_GENERIC")) && e[0] == '1';
+        c->env_frontend_serial = (e = getenv("VO_FRONTEND_SERIAL")) && e[0] == '1';
+        c->nms_band = (e = getenv("VO_NMS_BAND")) ? atoi(e) : 0;
+    }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        vo_set_error("vo_ctx_create: cudaStreamCreate failed");
+        delete c;
+        return VO_ERR_CUDA;
+    }
     *out = c;
     return VO_OK;
 }
@@ -291,17 +312,17 @@ int vo_klt_track_host(vo_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next,
 // ------------------------------------------------------------------------------------------
 int vo_p3p_ransac_score_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
                             int N, const double* K9, const int32_t* d_sample_idx, int n_hyp, double threshold,
-                            double* d_models, uint8_t* d_valid, int32_t* d_counts, void* stream) {
+                            int inclusive, double* d_models, uint8_t* d_valid, int32_t* d_counts, void* stream) {
     VO_REQUIRE(ctx && d_landmarks && d_keypoints && K9 && d_sample_idx && d_models && d_valid && d_counts,
                "vo_p3p_ransac_score_dev: null argument");
     VO_CUDA(cudaSetDevice(ctx->device));
-    return vo_launch_p3p_score(ctx, d_landmarks, d_keypoints, n_frames, N, K9, d_sample_idx, n_hyp, threshold,
+    return vo_launch_p3p_score(ctx, d_landmarks, d_keypoints, n_frames, N, K9, d_sample_idx, n_hyp, threshold, inclusive,
                                d_models, d_valid, d_counts, pick_stream(ctx, stream));
 }
 
 int vo_p3p_ransac_select_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
                              int N, const double* K9, const double* d_models, const uint8_t* d_valid,
-                             const int32_t* d_counts, int n_hyp, double threshold, const int32_t* d_iters_for_count,
+                             const int32_t* d_counts, int n_hyp, double threshold, int inclusive, const int32_t* d_iters_for_count,
                              int initial_iters, int start_n, int start_best, int32_t* d_best4, int32_t* d_consumed,
                              int32_t* d_iters_out, uint8_t* d_inliers, double* d_best_model, void* stream) {
     VO_REQUIRE(ctx && d_landmarks && d_keypoints && K9 && d_models && d_valid && d_counts && d_iters_for_count &&
@@ -309,12 +330,12 @@ int vo_p3p_ransac_select_dev(vo_ctx* ctx, const double* d_landmarks, const doubl
                "vo_p3p_ransac_select_dev: null argument");
     VO_CUDA(cudaSetDevice(ctx->device));
     return vo_launch_p3p_select(ctx, d_landmarks, d_keypoints, n_frames, N, K9, d_models, d_valid, d_counts, n_hyp,
-                                threshold, d_iters_for_count, initial_iters, start_n, start_best, d_best4, d_consumed,
+                                threshold, inclusive, d_iters_for_count, initial_iters, start_n, start_best, d_best4, d_consumed,
                                 d_iters_out, d_inliers, d_best_model, pick_stream(ctx, stream));
 }
 
 int vo_p3p_ransac_host(vo_ctx* ctx, const double* h_landmarks, const double* h_keypoints, int n_frames, int N,
-                       const double* K9, const int32_t* h_sample_idx, int n_hyp, double threshold,
+                       const double* K9, const int32_t* h_sample_idx, int n_hyp, double threshold, int inclusive,
                        const int32_t* h_iters_for_count, int initial_iters, int start_n, int start_best,
                        int32_t* h_best4, int32_t* h_consumed, int32_t* h_iters_out, uint8_t* h_inliers,
                        double* h_best_model, int32_t* h_counts, uint8_t* h_valid, double* h_models) {
@@ -338,9 +359,9 @@ int vo_p3p_ransac_host(vo_ctx* ctx, const double* h_landmarks, const double* h_k
     VO_CUDA(cudaMemcpyAsync(b + o_s, h_sample_idx, F * n_hyp * 16, cudaMemcpyHostToDevice, s));
     VO_CUDA(cudaMemcpyAsync(b + o_t, h_iters_for_count, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, s));
     if ((rc = vo_launch_p3p_score(ctx, (double*)(b + o_l), (double*)(b + o_k), n_frames, N, K9, (int*)(b + o_s), n_hyp,
-                                  threshold, (double*)(b + o_m), b + o_v, (int*)(b + o_c), s))) return rc;
+                                  threshold, inclusive, (double*)(b + o_m), b + o_v, (int*)(b + o_c), s))) return rc;
     if ((rc = vo_launch_p3p_select(ctx, (double*)(b + o_l), (double*)(b + o_k), n_frames, N, K9, (double*)(b + o_m),
-                                   b + o_v, (int*)(b + o_c), n_hyp, threshold, (int*)(b + o_t), initial_iters, start_n,
+                                   b + o_v, (int*)(b + o_c), n_hyp, threshold, inclusive, (int*)(b + o_t), initial_iters, start_n,
                                    start_best, (int*)(b + o_b), (int*)(b + o_con), (int*)(b + o_it), b + o_in,
                                    (double*)(b + o_bm), s))) return rc;
     VO_CUDA(cudaMemcpyAsync(h_best4, b + o_b, F * 16, cudaMemcpyDeviceToHost, s));

@@ -46,9 +46,26 @@ struct vo_ctx {
     VoBuf scratch[16];
     VoBuf pinned[4];
     unsigned long long launches = 0;  // kernels launched through this context
+    // One-time opt-ins (cudaFuncSetAttribute is per device): a bit per kernel family, set by vo_ctx_once().
+    unsigned attr_done = 0;
+    // Environment switches, read once in vo_ctx_create (never in a launch path).
+    bool env_harris_no_tma = false;   // VO_HARRIS_NO_TMA=1: generic three-stage response kernel
+    bool env_klt_generic = false;     // VO_KLT_GENERIC=1: runtime-window tracker for every window size
+    bool env_frontend_serial = false; // VO_FRONTEND_SERIAL=1: no fork/join across streams
+    int nms_band = 0;                 // VO_NMS_BAND (0 = built-in default)
 };
 
-int vo_buf_reserve(VoBuf* b, size_t bytes);
+// A context is bound to ONE device and its launchers carve working memory from ctx-owned scratch: calls that
+// share a vo_ctx must be ordered on one stream (or be externally serialised).  Use one vo_ctx per stream.
+enum { VO_ATTR_HARRIS_FAST = 1, VO_ATTR_HARRIS_TILED = 2, VO_ATTR_NMS = 4, VO_ATTR_KLT = 8, VO_ATTR_MATCH = 16,
+       VO_ATTR_GFTT = 32, VO_ATTR_PIPE = 64 };
+static inline bool vo_ctx_once(vo_ctx* ctx, unsigned bit) {
+    if (ctx->attr_done & bit) return false;
+    ctx->attr_done |= bit;
+    return true;
+}
+
+int vo_buf_reserve(VoBuf* b, size_t bytes, cudaStream_t launch_stream = nullptr);
 int vo_pinned_reserve(VoBuf* b, size_t bytes);
 
 static inline int vo_div_up(int a, int b) { return (a + b - 1) / b; }

@@ -8,6 +8,7 @@
 // one stream, so the whole step is capturable in a CUDA graph.
 #include "../../include/vo_b200.h"
 #include <cstdlib>
+#include <initializer_list>
 
 #include "common.cuh"
 #include "launchers.cuh"
@@ -85,6 +86,8 @@ int vo_frontend_create(vo_ctx* ctx, const vo_frontend_params* prm, vo_frontend**
         delete fe;
         return VO_ERR_CUDA;
     }
+    // everything below may fail half way: the lambda returns the error and vo_frontend_destroy releases what exists
+    auto finish = [&]() -> int {
     unsigned char* b = fe->base;
     VO_CUDA(cudaMemsetAsync(b, 0, off, ctx->stream));
     fe->pyr[0] = b + o_p0; fe->pyr[1] = b + o_p1; fe->resp = (double*)(b + o_resp);
@@ -128,28 +131,34 @@ int vo_frontend_create(vo_ctx* ctx, const vo_frontend_params* prm, vo_frontend**
     VO_CUDA(cudaEventCreateWithFlags(&fe->ev_level0, cudaEventDisableTiming));
     VO_CUDA(cudaEventCreateWithFlags(&fe->ev_harris, cudaEventDisableTiming));
     VO_CUDA(cudaEventCreateWithFlags(&fe->ev_pose, cudaEventDisableTiming));
-    {
-        const char* e = getenv("VO_FRONTEND_SERIAL");
-        fe->overlap = !(e && e[0] == '1');
-    }
+    fe->overlap = !ctx->env_frontend_serial;
+    // the detector's working memory is reserved now: a step never allocates (and is capturable into a CUDA graph)
+    { const int rc2 = vo_harris_nms_reserve(ctx, p.n_seq, p.H, p.W, p.nms_radius, p.num_keypoints); if (rc2) return rc2; }
     VO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return VO_OK;
+    };
+    rc = finish();
+    if (rc) { vo_frontend_destroy(fe); return rc; }
     *out = fe;
     return VO_OK;
 }
 
+// Tolerates a partially constructed object (vo_frontend_create's failure path): every handle is checked.
 void vo_frontend_destroy(vo_frontend* fe) {
     if (!fe) return;
     cudaSetDevice(fe->ctx->device);
     cudaStreamSynchronize(fe->ctx->stream);
-    cudaStreamSynchronize(fe->copy_stream);
-    for (int i = 0; i < 8; i++) { cudaEventDestroy(fe->ev_up[i]); cudaEventDestroy(fe->ev_done[i]); }
-    for (int i = 0; i < 2; i++) { cudaStreamSynchronize(fe->side[i]); cudaStreamDestroy(fe->side[i]); }
-    cudaEventDestroy(fe->ev_fork); cudaEventDestroy(fe->ev_level0); cudaEventDestroy(fe->ev_harris); cudaEventDestroy(fe->ev_pose);
-    cudaStreamSynchronize(fe->down_stream); cudaStreamDestroy(fe->down_stream);
-    for (int i = 0; i < 2; i++) cudaEventDestroy(fe->ev_res[i]);
-    cudaStreamDestroy(fe->copy_stream);
-    cudaFree(fe->stage[0]); cudaFree(fe->stage[1]);
-    cudaFree(fe->base);
+    if (fe->copy_stream) cudaStreamSynchronize(fe->copy_stream);
+    for (int i = 0; i < 8; i++) { if (fe->ev_up[i]) cudaEventDestroy(fe->ev_up[i]); if (fe->ev_done[i]) cudaEventDestroy(fe->ev_done[i]); }
+    for (int i = 0; i < 2; i++) if (fe->side[i]) { cudaStreamSynchronize(fe->side[i]); cudaStreamDestroy(fe->side[i]); }
+    for (cudaEvent_t ev : {fe->ev_fork, fe->ev_level0, fe->ev_harris, fe->ev_pose}) if (ev) cudaEventDestroy(ev);
+    if (fe->down_stream) { cudaStreamSynchronize(fe->down_stream); cudaStreamDestroy(fe->down_stream); }
+    for (int i = 0; i < 2; i++) if (fe->ev_res[i]) cudaEventDestroy(fe->ev_res[i]);
+    if (fe->copy_stream) cudaStreamDestroy(fe->copy_stream);
+    if (fe->stage[0]) cudaFree(fe->stage[0]);
+    if (fe->stage[1]) cudaFree(fe->stage[1]);
+    if (fe->base) cudaFree(fe->base);
+    (void)cudaGetLastError();
     delete fe;
 }
 
@@ -208,12 +217,12 @@ static int frontend_run_range(vo_frontend* fe, int s0, int n, const uint8_t* d_f
                                    fe->kp + (size_t)s0 * K * 2, nullptr, sh))) return rc;
     // 4. P3P + RANSAC (p3p.py:123-186 with use_opencv=False)
     if ((rc = vo_launch_p3p_score(ctx, d_landmarks + (size_t)s0 * N * 3, d_kp2d + (size_t)s0 * N * 2, n, p.n_corr, K9,
-                                  d_sample_idx + (size_t)s0 * Hn * 4, p.n_hyp, p.p3p_threshold,
+                                  d_sample_idx + (size_t)s0 * Hn * 4, p.n_hyp, p.p3p_threshold, 0,
                                   fe->models + (size_t)s0 * Hn * 12, fe->valid + (size_t)s0 * Hn,
                                   fe->counts + (size_t)s0 * Hn, sp))) return rc;
     if ((rc = vo_launch_p3p_select(ctx, d_landmarks + (size_t)s0 * N * 3, d_kp2d + (size_t)s0 * N * 2, n, p.n_corr, K9,
                                    fe->models + (size_t)s0 * Hn * 12, fe->valid + (size_t)s0 * Hn,
-                                   fe->counts + (size_t)s0 * Hn, p.n_hyp, p.p3p_threshold, d_iters_table, initial_iters, 0, -1,
+                                   fe->counts + (size_t)s0 * Hn, p.n_hyp, p.p3p_threshold, 0, d_iters_table, initial_iters, 0, -1,
                                    fe->best4 + (size_t)s0 * 4, fe->consumed + s0, fe->iters_out + s0,
                                    fe->inliers + (size_t)s0 * N, fe->pose + (size_t)s0 * 12, sp))) return rc;
     // 5. triangulation of new landmarks (triangulation.py:38-86)

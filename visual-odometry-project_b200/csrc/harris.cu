@@ -1385,7 +1385,7 @@ int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, i
     // fast path: 9x9 patch, 16-byte aligned base / pitch / frame stride (what TMA requires)
     const bool tma_ok = patch_size == 9 && ((uintptr_t)d_img % 16 == 0) && pitch % 16 == 0 &&
                         (frame_stride % 16 == 0 || n_frames == 1) && n_frames <= 65535 && tmap_encoder() != nullptr &&
-                        !getenv("VO_HARRIS_NO_TMA");
+                        !ctx->env_harris_no_tma;
     if (tma_ok) {
         CUtensorMap tmap;
         const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n_frames};
@@ -1396,11 +1396,8 @@ int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, i
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r == CUDA_SUCCESS) {
-            static bool attr_fast = false;
-            if (!attr_fast) {
+            if (vo_ctx_once(ctx, VO_ATTR_HARRIS_FAST))
                 VO_CUDA(cudaFuncSetAttribute(harris_response_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-                attr_fast = true;
-            }
             const int tiles_x = vo_div_up(W + FT_XSHIFT, FT_W), tiles_y = vo_div_up(H, FT_H);
             const long long n_tiles = (long long)tiles_x * tiles_y * n_frames;
             VO_REQUIRE(n_tiles < (1ll << 31), "harris: too many tiles");
@@ -1413,11 +1410,8 @@ int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, i
     }
     const int pw = RT_W + 2 * pr, ph = RT_H + 2 * pr;
     const size_t smem = (size_t)3 * ph * pw * 4 + (size_t)3 * ph * RT_W * 4 + (size_t)(RT_W + 2 * pad) * (RT_H + 2 * pad);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (vo_ctx_once(ctx, VO_ATTR_HARRIS_TILED))
         VO_CUDA(cudaFuncSetAttribute(harris_response_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-    }
     dim3 grid(vo_div_up(W, RT_W), vo_div_up(H, RT_H), n_frames);
     harris_response_tiled<<<grid, R_THREADS, smem, stream>>>(d_img, pitch, frame_stride, H, W, pr, kappa, d_resp);
     ctx->launches++;
@@ -1430,15 +1424,14 @@ size_t vo_harris_lm_cap(int H, int W, int r) {
 }
 
 // scratch layout for NMS (per call, n_frames frames)
-int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H, int W, int radius,
-                         int num_keypoints, int* d_kp_xy, unsigned int* d_stats_or_null, cudaStream_t stream) {
-    VO_REQUIRE(radius >= 0 && radius <= 15, "harris nms: radius must be in [0, 15] (got %d)", radius);
-    VO_REQUIRE(num_keypoints >= 1 && num_keypoints <= 16384, "harris nms: num_keypoints must be in [1, 16384]");
-    VO_REQUIRE(H >= 2 * radius + 1 && W >= 2 * radius + 1, "harris nms: image smaller than the suppression box");
-    VO_REQUIRE(H < 65536 && W < 65536, "harris nms: frame sides must be below 65536");
-    const size_t npx = (size_t)H * W;
+struct NmsCarve {
+    size_t npx, lm_cap, bm_words, smem_bands, total;
+    bool bm_smem;
+    size_t o_lmk, o_lmi, o_cnt, o_sup, o_mem, o_ea, o_eb, o_eh, o_pk, o_pi, o_stats, o_tk, o_ti, o_ctr;
+};
+static void nms_carve(int n_frames, int H, int W, int radius, int num_keypoints, NmsCarve* c) {
+    const size_t npx = (size_t)H * W, F = n_frames;
     const size_t lm_cap = vo_harris_lm_cap(H, W, radius);
-    const size_t F = n_frames;
     const size_t bm_words = npx / 32 + 2;
     unsigned int P2 = 1;
     while (P2 < (unsigned)num_keypoints) P2 <<= 1;
@@ -1448,27 +1441,49 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     const bool bm_smem = smem_tables + 2 * bm_words * 4 <= 220 * 1024;
     size_t smem_bands = smem_tables + (bm_smem ? 2 * bm_words * 4 : 0);
     if ((size_t)P2 * 12 > smem_bands) smem_bands = (size_t)P2 * 12;
-    // carve scratch
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_lmk = carve(F * lm_cap * 8), o_lmi = carve(F * lm_cap * 4), o_cnt = carve(F * 4);
-    const size_t o_sup = carve(F * bm_words * 4), o_mem = carve(bm_smem ? 0 : F * bm_words * 4);
-    const size_t o_ea = carve(F * npx * 16), o_eb = carve(F * npx * 16), o_eh = carve(F * npx * 4);
-    const size_t o_pk = carve(F * lm_cap * 8), o_pi = carve(F * lm_cap * 4);
-    const size_t o_stats = carve(F * 16);
-    const size_t o_tk = carve(F * 8), o_ti = carve(F * 4), o_ctr = carve(F * 16);
-    int rc = vo_buf_reserve(&ctx->scratch[0], off);
+    c->npx = npx; c->lm_cap = lm_cap; c->bm_words = bm_words; c->smem_bands = smem_bands; c->bm_smem = bm_smem;
+    c->o_lmk = carve(F * lm_cap * 8); c->o_lmi = carve(F * lm_cap * 4); c->o_cnt = carve(F * 4);
+    c->o_sup = carve(F * bm_words * 4); c->o_mem = carve(bm_smem ? 0 : F * bm_words * 4);
+    c->o_ea = carve(F * npx * 16); c->o_eb = carve(F * npx * 16); c->o_eh = carve(F * npx * 4);
+    c->o_pk = carve(F * lm_cap * 8); c->o_pi = carve(F * lm_cap * 4);
+    c->o_stats = carve(F * 16);
+    c->o_tk = carve(F * 8); c->o_ti = carve(F * 4); c->o_ctr = carve(F * 16);
+    c->total = off;
+}
+
+// Reserve the NMS working memory ahead of time (resident objects call this at creation, so that their steps never
+// allocate and stay capturable into a CUDA graph).
+int vo_harris_nms_reserve(vo_ctx* ctx, int n_frames, int H, int W, int radius, int num_keypoints) {
+    NmsCarve cv;
+    nms_carve(n_frames, H, W, radius, num_keypoints, &cv);
+    return vo_buf_reserve(&ctx->scratch[0], cv.total);
+}
+
+int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H, int W, int radius,
+                         int num_keypoints, int* d_kp_xy, unsigned int* d_stats_or_null, cudaStream_t stream) {
+    VO_REQUIRE(radius >= 0 && radius <= 15, "harris nms: radius must be in [0, 15] (got %d)", radius);
+    VO_REQUIRE(num_keypoints >= 1 && num_keypoints <= 16384, "harris nms: num_keypoints must be in [1, 16384]");
+    VO_REQUIRE(H >= 2 * radius + 1 && W >= 2 * radius + 1, "harris nms: image smaller than the suppression box");
+    VO_REQUIRE(H < 65536 && W < 65536, "harris nms: frame sides must be below 65536");
+    NmsCarve cv;
+    nms_carve(n_frames, H, W, radius, num_keypoints, &cv);
+    const size_t npx = cv.npx, lm_cap = cv.lm_cap, F = n_frames, bm_words = cv.bm_words, smem_bands = cv.smem_bands, off = cv.total;
+    const bool bm_smem = cv.bm_smem;
+    const size_t o_lmk = cv.o_lmk, o_lmi = cv.o_lmi, o_cnt = cv.o_cnt, o_sup = cv.o_sup, o_mem = cv.o_mem, o_ea = cv.o_ea,
+                 o_eb = cv.o_eb, o_eh = cv.o_eh, o_pk = cv.o_pk, o_pi = cv.o_pi, o_stats = cv.o_stats, o_tk = cv.o_tk,
+                 o_ti = cv.o_ti, o_ctr = cv.o_ctr;
+    int rc = vo_buf_reserve(&ctx->scratch[0], off, stream);
     if (rc) return rc;
     unsigned char* base = (unsigned char*)ctx->scratch[0].p;
     VO_CUDA(cudaMemsetAsync(base + o_cnt, 0, F * 4, stream));
     VO_CUDA(cudaMemsetAsync(base + o_sup, 0, F * bm_words * 4, stream));
     if (!bm_smem) VO_CUDA(cudaMemsetAsync(base + o_mem, 0, F * bm_words * 4, stream));
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (vo_ctx_once(ctx, VO_ATTR_NMS)) {
         VO_CUDA(cudaFuncSetAttribute(harris_nms_bands<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         VO_CUDA(cudaFuncSetAttribute(harris_nms_bands<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        attr_set = true;
     }
     {
         unsigned long long* lmk = (unsigned long long*)(base + o_lmk);
@@ -1498,11 +1513,7 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     a.counters = (unsigned int*)(base + o_ctr);
     a.bitmaps_in_smem = bm_smem ? 1 : 0;
     a.smem_bytes = (unsigned)smem_bands;
-    {
-        static int band = 0;
-        if (!band) { const char* e = getenv("VO_NMS_BAND"); band = e ? atoi(e) : NMS_BAND; if (band < 32 || band > N_THREADS) band = NMS_BAND; }
-        a.band = (unsigned)band;
-    }
+    a.band = (unsigned)((ctx->nms_band >= 32 && ctx->nms_band <= N_THREADS) ? ctx->nms_band : NMS_BAND);
     harris_nms_select<<<n_frames, N_THREADS, NMS_SELECT_SMEM * 12, stream>>>(a);
     ctx->launches++;
     VO_CHECK_LAUNCH();

@@ -557,194 +557,8 @@ klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__
     }
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// Compact variant of the fast path: identical arithmetic, but the window values live in shared memory
-// (I as int16, (Ix, Iy) packed in one 32-bit word) and the pixel loops are rolled with incremental
-// row/column counters.  The body is ~5x smaller than the register version (no instruction-cache
-// misses), needs about half the registers and therefore runs at twice the occupancy.
-// ---------------------------------------------------------------------------------------------
 constexpr int KLT_SWARPS = 8;
 
-template <int WIN>
-__global__ void __launch_bounds__(KLT_SWARPS * 32, 3)
-klt_track_small(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__ pyr_next, PyrLayout lay,
-                int max_iters, double eps2, double min_eig, const float* __restrict__ prev_pts, int n_pts,
-                float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
-    constexpr int W2 = WIN * WIN, PN = WIN + 3, DN = WIN + 1;
-    constexpr int PATCH_BYTES = (PN * PN + 15) & ~15;
-    constexpr int IV_BYTES = (W2 * 2 + 15) & ~15;
-    constexpr int PER_WARP = (PATCH_BYTES + DN * DN * 4 + IV_BYTES + W2 * 4 + 15) & ~15;
-    __shared__ __align__(16) unsigned char smem[KLT_SWARPS * PER_WARP];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pt = blockIdx.x * KLT_SWARPS + warp;
-    const int f = blockIdx.y;
-    if (pt >= n_pts) return;
-    uint8_t* patch = smem + warp * PER_WARP;                                  // I (PN^2), later J (DN^2)
-    short* dpatch = reinterpret_cast<short*>(patch + PATCH_BYTES);             // [DN*DN][2]
-    short* Iw = reinterpret_cast<short*>(patch + PATCH_BYTES + DN * DN * 4);   // [W2]
-    int* Gw = reinterpret_cast<int*>(patch + PATCH_BYTES + DN * DN * 4 + IV_BYTES);   // [W2]  (Ix | Iy << 16)
-
-    const uint8_t* Ip = pyr_prev + (size_t)f * lay.frame_bytes;
-    const uint8_t* Jp = pyr_next + (size_t)f * lay.frame_bytes;
-    const size_t pidx = (size_t)f * n_pts + pt;
-    const float px0 = prev_pts[2 * pidx], py0 = prev_pts[2 * pidx + 1];
-    const float half = (float)(WIN - 1) * 0.5f;
-    const float FLT_SCALE = 1.f / (1 << 20);
-    const int top = lay.n_levels - 1;
-    const int ly0 = lane / WIN, lx0 = lane - ly0 * WIN;      // window coordinates of this lane's first pixel
-    bool st = true;
-    float e_out = 0.f;
-    float outx = 0.f, outy = 0.f;
-
-    for (int level = top; level >= 0; level--) {
-        const int cols = lay.w[level], rows = lay.h[level];
-        const size_t pitch = lay.pitch[level];
-        const uint8_t* I = Ip + lay.offset[level];
-        const uint8_t* J = Jp + lay.offset[level];
-        const float sc = (float)(1. / (1 << level));
-        float prx = px0 * sc, pry = py0 * sc;
-        float nx, ny;
-        if (level == top) { nx = prx; ny = pry; }
-        else { nx = outx * 2.f; ny = outy * 2.f; }
-        outx = nx; outy = ny;
-        prx -= half; pry -= half;
-        const int ipx = (int)floorf(prx), ipy = (int)floorf(pry);
-        if (ipx < -WIN || ipx >= cols || ipy < -WIN || ipy >= rows) {
-            if (level == 0) { st = false; e_out = 0.f; }
-            continue;
-        }
-        float a = prx - ipx, b = pry - ipy;
-        int iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS));
-        int iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
-        int iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
-        int iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
-
-        __syncwarp();
-        stage_patch_fast<PN>(I, rows, cols, pitch, ipx - 1, ipy - 1, patch, lane);
-        __syncwarp();
-        {
-            int qy = lane / DN, qx = lane - qy * DN;
-#pragma unroll 2
-            for (int i = lane; i < DN * DN; i += 32) {
-                const int gx = ipx + qx, gy = ipy + qy;
-                int dx = 0, dy = 0;
-                if (gx >= 0 && gx < cols && gy >= 0 && gy < rows) {
-                    const uint8_t* r0 = patch + qy * PN + qx;
-                    const uint8_t* r1 = r0 + PN;
-                    const uint8_t* r2 = r1 + PN;
-                    const int t0m = ((int)r0[0] + (int)r2[0]) * 3 + (int)r1[0] * 10;
-                    const int t0p = ((int)r0[2] + (int)r2[2]) * 3 + (int)r1[2] * 10;
-                    const int t1m = (int)r2[0] - (int)r0[0], t1c = (int)r2[1] - (int)r0[1], t1p = (int)r2[2] - (int)r0[2];
-                    dx = t0p - t0m;
-                    dy = (t1p + t1m) * 3 + t1c * 10;
-                }
-                dpatch[2 * i] = (short)dx;
-                dpatch[2 * i + 1] = (short)dy;
-                qx += 32 % DN; qy += 32 / DN;
-                if (qx >= DN) { qx -= DN; qy++; }
-            }
-        }
-        __syncwarp();
-        int sA11 = 0, sA12 = 0, sA22 = 0;
-        {
-            int y = ly0, x = lx0;
-#pragma unroll 2
-            for (int i = lane; i < W2; i += 32) {
-                const uint8_t* s0 = patch + (y + 1) * PN + (x + 1);
-                const int iv = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[PN] * iw10 + (int)s0[PN + 1] * iw11, W_BITS - 5);
-                const short* d0 = dpatch + 2 * (y * DN + x);
-                const short* d1 = d0 + 2 * DN;
-                const int ix = descale((int)d0[0] * iw00 + (int)d0[2] * iw01 + (int)d1[0] * iw10 + (int)d1[2] * iw11, W_BITS);
-                const int iy = descale((int)d0[1] * iw00 + (int)d0[3] * iw01 + (int)d1[1] * iw10 + (int)d1[3] * iw11, W_BITS);
-                Iw[i] = (short)iv;
-                Gw[i] = (ix & 0xFFFF) | (iy << 16);
-                sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
-                x += 32 % WIN; y += 32 / WIN;
-                if (x >= WIN) { x -= WIN; y++; }
-            }
-        }
-        const long long iA11 = warp_sum_exact(sA11), iA12 = warp_sum_exact(sA12), iA22 = warp_sum_exact(sA22);
-        const float A11 = (float)iA11 * FLT_SCALE, A12 = (float)iA12 * FLT_SCALE, A22 = (float)iA22 * FLT_SCALE;
-        float D = A11 * A22 - A12 * A12;
-        const float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
-        if ((double)minEig < min_eig || D < 1.1920928955078125e-07f) {
-            if (level == 0) st = false;
-            continue;
-        }
-        D = 1.f / D;
-        nx -= half; ny -= half;
-        float pdx = 0.f, pdy = 0.f;
-        int sx = 0x7fffffff, sy = 0x7fffffff;                 // integer position of the staged J patch
-        // j == max_iters is the extra pass that measures the final patch error (level 0 only)
-        bool want_err = false;
-        for (int j = 0; j <= max_iters; j++) {
-            float fx = nx, fy = ny;
-            if (j == max_iters || want_err) {
-                if (!(st && level == 0)) break;
-                want_err = true;
-                fx = outx - half; fy = outy - half;
-            }
-            const int inx = (int)floorf(fx), iny = (int)floorf(fy);
-            if (inx < -WIN || inx >= cols || iny < -WIN || iny >= rows) {
-                if (level == 0) st = false;
-                break;
-            }
-            a = fx - inx; b = fy - iny;
-            iw00 = __float2int_rn((1.f - a) * (1.f - b) * (1 << W_BITS));
-            iw01 = __float2int_rn(a * (1.f - b) * (1 << W_BITS));
-            iw10 = __float2int_rn((1.f - a) * b * (1 << W_BITS));
-            iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
-            if (inx != sx || iny != sy) {
-                __syncwarp();
-                stage_patch_fast<DN>(J, rows, cols, pitch, inx, iny, patch, lane);
-                __syncwarp();
-                sx = inx; sy = iny;
-            }
-            int sb1 = 0, sb2 = 0, se = 0;
-            {
-                int y = ly0, x = lx0;
-#pragma unroll 2
-                for (int i = lane; i < W2; i += 32) {
-                    const uint8_t* s0 = patch + y * DN + x;
-                    const int diff = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[DN] * iw10 + (int)s0[DN + 1] * iw11,
-                                             W_BITS - 5) - (int)Iw[i];
-                    const int g = Gw[i];
-                    sb1 += diff * (int)(short)(g & 0xFFFF);
-                    sb2 += diff * (g >> 16);
-                    se += diff < 0 ? -diff : diff;
-                    x += 32 % WIN; y += 32 / WIN;
-                    if (x >= WIN) { x -= WIN; y++; }
-                }
-            }
-            if (want_err) {
-                const long long e = warp_sum_exact(se);
-                e_out = (float)e * 1.f / (float)(32 * WIN * WIN);
-                break;
-            }
-            const long long ib1 = warp_sum_exact(sb1), ib2 = warp_sum_exact(sb2);
-            const float b1 = (float)ib1 * FLT_SCALE, b2 = (float)ib2 * FLT_SCALE;
-            const float dx = (float)((A12 * b2 - A22 * b1) * D);
-            const float dy = (float)((A12 * b1 - A11 * b2) * D);
-            nx += dx; ny += dy;
-            outx = nx + half; outy = ny + half;
-            if ((double)dx * dx + (double)dy * dy <= eps2) { want_err = true; continue; }
-            if (j > 0 && fabs((double)(dx + pdx)) < 0.01 && fabs((double)(dy + pdy)) < 0.01) {
-                outx -= dx * 0.5f;
-                outy -= dy * 0.5f;
-                want_err = true;
-                continue;
-            }
-            pdx = dx; pdy = dy;
-        }
-    }
-    if (lane == 0) {
-        next_pts[2 * pidx] = outx;
-        next_pts[2 * pidx + 1] = outy;
-        status[pidx] = st ? 1 : 0;
-        err[pidx] = e_out;
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // Packed variant of the compact path: identical arithmetic, but the iteration loop (the bulk of the work)
@@ -1131,13 +945,13 @@ int vo_launch_klt_track(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d
     size_t per_warp = (size_t)((pn * pn + 15) & ~15) + (size_t)dn * dn * 4 + (size_t)w2 * 2 + (size_t)w2 * 4;
     per_warp = (per_warp + 15) & ~(size_t)15;
     const size_t smem = per_warp * KLT_WARPS;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (vo_ctx_once(ctx, VO_ATTR_KLT))
         VO_CUDA(cudaFuncSetAttribute(klt_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
-    }
     dim3 g(vo_div_up(n_pts, KLT_WARPS), n_frames);
-    if (win == 17 && !getenv("VO_KLT_GENERIC") && !getenv("VO_KLT_REGS") && !getenv("VO_KLT_SMALL")) {
+    // The specialised kernels stage patches with a single reflection (reflect1), which is only valid while every
+    // level is wider than the patch: levels >= 1 are by construction (klt_layout), level 0 is checked here.
+    const bool roomy = H > win + 3 && W > win + 3;
+    if (win == 17 && roomy && !ctx->env_klt_generic) {
         dim3 gs(vo_div_up(n_pts, KLT_SWARPS), n_frames);
         klt_track_packed<17><<<gs, KLT_SWARPS * 32, 0, stream>>>(d_pyr_prev, d_pyr_next, L, max_iters, epsilon * epsilon, min_eig,
                                                                   d_prev_pts, n_pts, d_next_pts, d_status, d_err);
@@ -1145,21 +959,9 @@ int vo_launch_klt_track(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d
         VO_CHECK_LAUNCH();
         return VO_OK;
     }
-    if (win == 17 && !getenv("VO_KLT_GENERIC") && !getenv("VO_KLT_REGS")) {
-        dim3 gs(vo_div_up(n_pts, KLT_SWARPS), n_frames);
-        klt_track_small<17><<<gs, KLT_SWARPS * 32, 0, stream>>>(d_pyr_prev, d_pyr_next, L, max_iters, epsilon * epsilon, min_eig,
-                                                                 d_prev_pts, n_pts, d_next_pts, d_status, d_err);
-        ctx->launches++;
-        VO_CHECK_LAUNCH();
-        return VO_OK;
-    }
-    if ((win == 17 || win == 21) && !getenv("VO_KLT_GENERIC")) {
-        if (win == 17)
-            klt_track_fast<17><<<g, KLT_WARPS * 32, 0, stream>>>(d_pyr_prev, d_pyr_next, L, max_iters, epsilon * epsilon, min_eig,
-                                                                  d_prev_pts, n_pts, d_next_pts, d_status, d_err);
-        else
-            klt_track_fast<21><<<g, KLT_WARPS * 32, 0, stream>>>(d_pyr_prev, d_pyr_next, L, max_iters, epsilon * epsilon, min_eig,
-                                                                  d_prev_pts, n_pts, d_next_pts, d_status, d_err);
+    if (win == 21 && roomy && !ctx->env_klt_generic) {
+        klt_track_fast<21><<<g, KLT_WARPS * 32, 0, stream>>>(d_pyr_prev, d_pyr_next, L, max_iters, epsilon * epsilon, min_eig,
+                                                              d_prev_pts, n_pts, d_next_pts, d_status, d_err);
         ctx->launches++;
         VO_CHECK_LAUNCH();
         return VO_OK;

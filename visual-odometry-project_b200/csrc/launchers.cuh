@@ -9,6 +9,7 @@ int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, i
 size_t vo_harris_lm_cap(int H, int W, int r);
 int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H, int W, int radius,
                          int num_keypoints, int* d_kp_xy, unsigned int* d_stats_or_null, cudaStream_t stream);
+int vo_harris_nms_reserve(vo_ctx* ctx, int n_frames, int H, int W, int radius, int num_keypoints);
 int vo_launch_harris_descriptors(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,
                                  size_t frame_stride, const int* d_kp_xy, int K, int r, uint8_t* d_desc,
                                  cudaStream_t stream);
@@ -24,11 +25,11 @@ int vo_launch_klt_track(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d
                         cudaStream_t stream);
 // p3p.cu
 int vo_launch_p3p_score(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames, int N,
-                        const double* K9, const int* d_sample_idx, int n_hyp, double threshold, double* d_models,
+                        const double* K9, const int* d_sample_idx, int n_hyp, double threshold, int inclusive, double* d_models,
                         unsigned char* d_valid, int* d_counts, cudaStream_t stream);
 int vo_launch_p3p_select(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames, int N,
                          const double* K9, const double* d_models, const unsigned char* d_valid, const int* d_counts,
-                         int n_hyp, double threshold, const int* d_iters_for_count, int initial_iters, int start_n,
+                         int n_hyp, double threshold, int inclusive, const int* d_iters_for_count, int initial_iters, int start_n,
                          int start_best, int* d_best4, int* d_consumed, int* d_iters_out, unsigned char* d_inliers,
                          double* d_best_model, cudaStream_t stream);
 // triangulation.cu

@@ -190,11 +190,8 @@ int vo_launch_match(vo_ctx* ctx, const uint8_t* d_q, const uint8_t* d_t, int n_f
     VO_REQUIRE(n_frames >= 1 && Q >= 1 && T >= 1 && D >= 1 && (D + 3) / 4 <= M_DW_MAX, "match: bad sizes (descriptor length <= %d bytes)", 4 * M_DW_MAX);
     const int DW = (D + 3) / 4, P = DW | 1;
     const size_t smem = (size_t)(MQ + MT) * P * 4 + (MQ + MT) * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (vo_ctx_once(ctx, VO_ATTR_MATCH))
         VO_CUDA(cudaFuncSetAttribute(knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        attr_set = true;
-    }
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_best = carve((size_t)n_frames * Q * 16), o_win = carve((size_t)n_frames * T * 4);

@@ -212,6 +212,12 @@ __device__ __forceinline__ double reproj_err2(const double* m, double X0, double
     return du * du + dv * dv;
 }
 
+// ransac.py:105 `errors < inlier_threshold`; with inclusive != 0 OpenCV's rule `err <= t` (findInliers of
+// cv2.solvePnPRansac, the reference's use_opencv=True path, p3p.py:142-151)
+__device__ __forceinline__ bool is_inlier(double e, double thr, int inclusive) {
+    return inclusive ? (e <= thr) : (e < thr);
+}
+
 // one thread per (frame, hypothesis)
 __global__ void __launch_bounds__(128)
 p3p_solve_kernel(const double* __restrict__ landmarks, const double* __restrict__ keypoints, int N, Intr K,
@@ -267,7 +273,7 @@ constexpr int COUNT_CHUNK = 1024;       // correspondences staged at a time (40 
 __global__ void __launch_bounds__(COUNT_WARPS * 32)
 p3p_count_kernel(const double* __restrict__ landmarks, const double* __restrict__ keypoints, int N, Intr K,
                  const double* __restrict__ models, const unsigned char* __restrict__ valid, int n_hyp,
-                 double threshold, int* __restrict__ counts) {
+                 double threshold, int inclusive, int* __restrict__ counts) {
     __shared__ double sX[COUNT_CHUNK], sY[COUNT_CHUNK], sZ[COUNT_CHUNK], sU[COUNT_CHUNK], sV[COUNT_CHUNK];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.x * COUNT_WARPS + warp;
@@ -293,8 +299,8 @@ p3p_count_kernel(const double* __restrict__ landmarks, const double* __restrict_
             for (int base = 0; base < n; base += 64) {     // two points per lane and step: independent FP64 chains
                 const int i0 = base + lane, i1 = i0 + 32;
                 bool in0 = false, in1 = false;
-                if (i0 < n) in0 = reproj_err2(m, sX[i0], sY[i0], sZ[i0], sU[i0], sV[i0], K) < threshold;
-                if (i1 < n) in1 = reproj_err2(m, sX[i1], sY[i1], sZ[i1], sU[i1], sV[i1], K) < threshold;
+                if (i0 < n) in0 = is_inlier(reproj_err2(m, sX[i0], sY[i0], sZ[i0], sU[i0], sV[i0], K), threshold, inclusive);
+                if (i1 < n) in1 = is_inlier(reproj_err2(m, sX[i1], sY[i1], sZ[i1], sU[i1], sV[i1], K), threshold, inclusive);
                 c += __popc(__ballot_sync(0xFFFFFFFFu, in0)) + __popc(__ballot_sync(0xFFFFFFFFu, in1));
             }
         }
@@ -306,7 +312,7 @@ p3p_count_kernel(const double* __restrict__ landmarks, const double* __restrict_
 __global__ void __launch_bounds__(256)
 p3p_select_kernel(const double* __restrict__ landmarks, const double* __restrict__ keypoints, int N, Intr K,
                   const double* __restrict__ models, const unsigned char* __restrict__ valid,
-                  const int* __restrict__ counts, int n_hyp, double threshold,
+                  const int* __restrict__ counts, int n_hyp, double threshold, int inclusive,
                   const int* __restrict__ iters_for_count, int initial_iters, int start_n, int start_best,
                   int* __restrict__ best_out, int* __restrict__ consumed_out, int* __restrict__ iters_out,
                   unsigned char* __restrict__ inliers, double* __restrict__ best_model) {
@@ -348,7 +354,7 @@ p3p_select_kernel(const double* __restrict__ landmarks, const double* __restrict
     const double* L = landmarks + (size_t)f * N * 3;
     const double* P = keypoints + (size_t)f * N * 2;
     for (int i = threadIdx.x; i < N; i += blockDim.x)
-        in[i] = reproj_err2(m, L[3 * i], L[3 * i + 1], L[3 * i + 2], P[2 * i], P[2 * i + 1], K) < threshold ? 1 : 0;
+        in[i] = is_inlier(reproj_err2(m, L[3 * i], L[3 * i + 1], L[3 * i + 2], P[2 * i], P[2 * i + 1], K), threshold, inclusive) ? 1 : 0;
 }
 
 }  // namespace
@@ -356,7 +362,7 @@ p3p_select_kernel(const double* __restrict__ landmarks, const double* __restrict
 static Intr make_intr(const double* K9) { return Intr{K9[0], K9[4], K9[2], K9[5]}; }
 
 int vo_launch_p3p_score(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames, int N,
-                        const double* K9, const int* d_sample_idx, int n_hyp, double threshold, double* d_models,
+                        const double* K9, const int* d_sample_idx, int n_hyp, double threshold, int inclusive, double* d_models,
                         unsigned char* d_valid, int* d_counts, cudaStream_t stream) {
     VO_REQUIRE(n_frames >= 1 && N >= 4 && n_hyp >= 1, "p3p: need n_frames >= 1, N >= 4, n_hyp >= 1");
     VO_REQUIRE(K9[0] != 0.0 && K9[4] != 0.0, "p3p: singular intrinsic matrix");
@@ -367,7 +373,7 @@ int vo_launch_p3p_score(vo_ctx* ctx, const double* d_landmarks, const double* d_
     VO_CHECK_LAUNCH();
     dim3 g2(vo_div_up(n_hyp, COUNT_WARPS), n_frames);
     p3p_count_kernel<<<g2, COUNT_WARPS * 32, 0, stream>>>(d_landmarks, d_keypoints, N, K, d_models, d_valid, n_hyp,
-                                                          threshold, d_counts);
+                                                          threshold, inclusive, d_counts);
     ctx->launches++;
     VO_CHECK_LAUNCH();
     return VO_OK;
@@ -375,13 +381,13 @@ int vo_launch_p3p_score(vo_ctx* ctx, const double* d_landmarks, const double* d_
 
 int vo_launch_p3p_select(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames, int N,
                          const double* K9, const double* d_models, const unsigned char* d_valid, const int* d_counts,
-                         int n_hyp, double threshold, const int* d_iters_for_count, int initial_iters, int start_n,
+                         int n_hyp, double threshold, int inclusive, const int* d_iters_for_count, int initial_iters, int start_n,
                          int start_best, int* d_best4, int* d_consumed, int* d_iters_out, unsigned char* d_inliers,
                          double* d_best_model, cudaStream_t stream) {
     VO_REQUIRE(n_frames >= 1 && N >= 4 && n_hyp >= 1, "p3p select: bad sizes");
     const Intr K = make_intr(K9);
     p3p_select_kernel<<<n_frames, 256, 0, stream>>>(d_landmarks, d_keypoints, N, K, d_models, d_valid, d_counts, n_hyp,
-                                                    threshold, d_iters_for_count, initial_iters, start_n, start_best,
+                                                    threshold, inclusive, d_iters_for_count, initial_iters, start_n, start_best,
                                                     d_best4, d_consumed, d_iters_out, d_inliers, d_best_model);
     ctx->launches++;
     VO_CHECK_LAUNCH();

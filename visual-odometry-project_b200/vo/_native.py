@@ -57,10 +57,10 @@ def lib():
             "vo_klt_build_pyramid_dev": (i32, [vp, vp, i32, i32, i32, sz, sz, i32, i32, vp, vp]),
             "vo_klt_track_dev": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, dbl, dbl, vp, i32, vp, vp, vp, vp]),
             "vo_klt_track_host": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, dbl, dbl, vp, i32, vp, vp, vp]),
-            "vo_p3p_ransac_score_dev": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, dbl, vp, vp, vp, vp]),
-            "vo_p3p_ransac_select_dev": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, dbl, vp, i32, i32, i32,
+            "vo_p3p_ransac_score_dev": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, dbl, i32, vp, vp, vp, vp]),
+            "vo_p3p_ransac_select_dev": (i32, [vp, vp, vp, i32, i32, vp, vp, vp, vp, i32, dbl, i32, vp, i32, i32, i32,
                                                vp, vp, vp, vp, vp, vp]),
-            "vo_p3p_ransac_host": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, dbl, vp, i32, i32, i32,
+            "vo_p3p_ransac_host": (i32, [vp, vp, vp, i32, i32, vp, vp, i32, dbl, i32, vp, i32, i32, i32,
                                          vp, vp, vp, vp, vp, vp, vp, vp]),
             "vo_triangulate_dev": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp, vp]),
             "vo_triangulate_host": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp]),

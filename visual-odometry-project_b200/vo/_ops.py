@@ -82,10 +82,11 @@ def klt_track(prev, nxt, pts, win=17, max_level=2, max_iters=10, epsilon=0.03, m
 # P3P + RANSAC  (reference: src/vo/pose_estimation/p3p.py, src/vo/algorithms/ransac.py)
 # ------------------------------------------------------------------------------------------------
 def p3p_ransac(landmarks, keypoints, K, sample_idx, threshold, iters_for_count, initial_iters, start_n=0,
-               start_best=-1, want_all=False, ctx=None):
+               start_best=-1, want_all=False, inclusive=False, ctx=None):
     """Score every 4-index sample set and replay the reference's adaptive loop over them.
 
     landmarks (N, 3) / keypoints (N, 2) or batched (F, N, .); sample_idx (H, 4) or (F, H, 4) int32.
+    inclusive: count squared errors equal to the threshold as inliers (cv2.solvePnPRansac's rule).
     Returns a dict with best (index or -1), best_count, n, exhausted, consumed, n_iterations,
     inliers (bool), R, t and, with want_all, counts / valid / models for every hypothesis."""
     ctx = _ctx(ctx)
@@ -111,7 +112,8 @@ def p3p_ransac(landmarks, keypoints, K, sample_idx, threshold, iters_for_count, 
     valid = np.zeros((F, Hn), dtype=np.uint8) if want_all else None
     models = np.zeros((F, Hn, 12), dtype=np.float64) if want_all else None
     rc = nat.lib().vo_p3p_ransac_host(
-        ctx.handle, nat.ptr(L), nat.ptr(P), F, N, nat.ptr(K9), nat.ptr(S), Hn, C.c_double(threshold), nat.ptr(table),
+        ctx.handle, nat.ptr(L), nat.ptr(P), F, N, nat.ptr(K9), nat.ptr(S), Hn, C.c_double(threshold), int(bool(inclusive)),
+        nat.ptr(table),
         int(initial_iters), int(start_n), int(start_best), nat.ptr(best4), nat.ptr(consumed), nat.ptr(iters_out),
         nat.ptr(inl), nat.ptr(bm), nat.ptr(counts) if want_all else None, nat.ptr(valid) if want_all else None,
         nat.ptr(models) if want_all else None)

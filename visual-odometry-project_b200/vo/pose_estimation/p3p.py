@@ -4,8 +4,11 @@ estimate_pose runs the P3P minimal solver and the reprojection inlier count for 
 RANSAC hypotheses on the GPU (vo_p3p_ransac_* in include/vo_b200.h) and replays the reference's
 sequential, adaptive RANSAC loop over them, so the rng stream, the iteration count, the winning
 model and the inlier mask are those of the reference's `use_opencv=False` path.  With
-`use_opencv=True` the reference hands the whole problem to cv2.solvePnPRansac (its own RNG); here
-that flag only switches the inlier rule to OpenCV's (squared error <= reprojectionError^2)."""
+`use_opencv=True` the reference hands the whole problem to cv2.solvePnPRansac (its own RNG and
+sampler); here that flag only switches the inlier rule to OpenCV's (squared error <=
+reprojectionError^2, inclusive): the default-path result is an APPROXIMATION of the reference's
+(same model class, same inlier rule, different sample stream), pinned by tolerance after the
+refinement (tests/test_loop_gpu.py), not by equality."""
 import numpy as np
 from scipy.optimize import least_squares
 
@@ -55,13 +58,19 @@ class P3PPoseEstimator:
         thr = self.inlier_threshold ** 2 if self._use_opencv else self.inlier_threshold
         n, best_count, best = 0, -1, None
         batch = self.FIRST_BATCH
+        drawn, draw_cap = 0, 10 * int(min(self.max_iterations, 1 << 24)) + 4096
         while n < rs.n_iterations:
+            if drawn >= draw_cap:
+                # ransac.py:90-103 would spin forever when no sample yields a model (degenerate landmarks);
+                # here that would be an endless stream of GPU round trips, so give up loudly instead.
+                raise RuntimeError(f"P3P-RANSAC: {drawn} samples drawn, {n} valid models: degenerate correspondences")
             state0 = rs.rng.bit_generator.state
             want = int(min(batch, max(1, rs.n_iterations - n)))
             samples = np.stack([rs.draw(N) for _ in range(want)]).astype(np.int32)
             r = _ops.p3p_ransac(points_3d, points_2d, self.intrinsic_matrix, samples, thr, table,
-                                rs.n_iterations, start_n=n, start_best=best_count)
+                                rs.n_iterations, start_n=n, start_best=best_count, inclusive=self._use_opencv)
             n, consumed = int(r["n"]), int(r["consumed"])
+            drawn += consumed
             if int(r["best"]) >= 0:
                 best_count = int(r["best_count"])
                 best = ((r["R"].copy(), r["t"].copy()), r["inliers"].copy())
