@@ -207,6 +207,81 @@ int vo_frontend_submit_host(vo_frontend* fe, const uint8_t* h_frames, const doub
 int vo_frontend_wait_host(vo_frontend* fe);
 
 
+/* ---- The chained, device-resident pipeline: src/main.py:248-287 with the reference's data flow --------------- */
+/* One feature table per sequence stays in HBM (rows: keypoint, landmark, state, track start, start pose, candidate
+ * flag -- the columns of src/vo/primitives/features.py).  One step advances every sequence by one frame:
+ *   re-detection rule + append (klt.py:207-230) -> pyramidal LK (klt.py:233-239) -> status / error filter
+ *   (klt.py:244-249) -> Matches regrouping (matches.py) -> P3P-RANSAC on the triangulated rows with the numpy
+ *   PCG64(2023) sample stream, adaptive stop and carried state (ransac.py:69-129, p3p.py:123-186) -> pose refinement
+ *   (p3p.py:188-213; damped Gauss-Newton to the minimum of the same cost) -> State.update_with_world_pose,
+ *   reset_outliers, compute_candidates (state.py:39-178) -> triangulate_candidates (triangulation.py:38-86) ->
+ *   update_with_world_landmarks + _check_landmarks (state.py:70-110).
+ * Only the frames are uploaded; a step returns, per sequence, the pose and a few counters.                       */
+typedef struct vo_pipeline vo_pipeline;
+#define VO_DETECTOR_NONE 0     /* the host appends corners itself (vo_pipeline_write_table_host)                 */
+#define VO_DETECTOR_HARRIS 1   /* HarrisCornerDetector.extractKeypoints (harris.py:86-158) on every new frame    */
+#define VO_PIPE_NCOUNTS 12
+#define VO_PIPE_SUMMARY_DOUBLES 18   /* per sequence: 12 doubles pose + VO_PIPE_NCOUNTS int32 counters            */
+/* counters: 0 rows after the step, 1 rows tracked, 2 rows kept by the status/error filter, 3 P3P population,
+ * 4 inliers of the winning model, 5 candidates triangulated, 6 triangulated rows after the step,
+ * 7 flags (1 re-detected, 2 no pose: fewer than 4 landmarks or no model, 4 table full on append, 8 sample cap hit),
+ * 8 RANSAC n_iterations after the step, 9 samples drawn, 10 landmarks dropped behind a camera, 11 refinement steps */
+typedef struct {
+    int n_seq, H, W;
+    int capacity;                                    /* table rows per sequence, multiple of 32                    */
+    int klt_win, klt_max_level, klt_max_iters;       /* klt.py:29-33                                               */
+    double klt_epsilon, klt_min_eig;
+    float klt_error_threshold;                       /* klt.py:36  _error_threshold                                */
+    double redetect_fraction;                        /* klt.py:211 (0.8)                                           */
+    int detector, det_max_corners;                   /* VO_DETECTOR_*; corners per detection                       */
+    int patch_size; double kappa; int nms_radius;    /* harris.py:16-34                                            */
+    double K[9], Kinv[9];                            /* intrinsics and their inverse AS THE HOST COMPUTES IT
+                                                        (camera.py:92: np.linalg.inv in K's own dtype)             */
+    double p3p_threshold; int p3p_inclusive;         /* p3p.py:20 / ransac.py:105; inclusive = cv2's `<=` rule     */
+    double ransac_confidence, ransac_outlier_ratio;  /* p3p.py:22-23                                               */
+    double ransac_log1mconf;                         /* log(1 - confidence) as the host evaluates it (0 = compute) */
+    int ransac_max_iterations, ransac_initial_iterations; /* p3p.py:24; 0 = derive from the outlier ratio          */
+    int refine;                                      /* p3p.py:25 nonlinear_refinement                             */
+    double bearing_threshold;                        /* state.py:9                                                 */
+    int tri_mode;                                    /* 1 = cv2.triangulatePoints' system (use_opencv=True), 0 = reference's */
+} vo_pipeline_params;
+int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* params, vo_pipeline** out);
+void vo_pipeline_destroy(vo_pipeline* pl);
+/* Make `frames` the current frame of every sequence (pyramid + detector).  init_tables != 0 also starts every table
+ * from the detected corners, all unmatched (KLTTracker.__init__, klt.py:40-50).                                  */
+int vo_pipeline_prime_dev(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, size_t frame_stride, int init_tables, void* stream);
+int vo_pipeline_prime_host(vo_pipeline* pl, const uint8_t* h_frames, int init_tables);
+/* Device-resident step (asynchronous): d_frames uint8 [n_seq] frames.  The summary [n_seq][VO_PIPE_SUMMARY_DOUBLES]
+ * of the last step_dev is at vo_pipeline_summary_dev().                                                          */
+int vo_pipeline_step_dev(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, size_t frame_stride, void* stream);
+const double* vo_pipeline_summary_dev(vo_pipeline* pl);
+/* Host-buffer steps, pipelined like vo_frontend_*: prefetch uploads the NEXT step's frames (tightly packed) under the
+ * current step, submit enqueues the step and the download of its summary, wait blocks for the oldest submitted step. */
+int vo_pipeline_prefetch_host(vo_pipeline* pl, const uint8_t* h_frames);
+int vo_pipeline_submit_host(vo_pipeline* pl, const uint8_t* h_frames, double* h_summary);
+int vo_pipeline_wait_host(vo_pipeline* pl);
+int vo_pipeline_step_host(vo_pipeline* pl, const uint8_t* h_frames, double* h_summary);
+/* Table access (synchronous; bootstrap hand-over, tests, the Python mirror of Features).  Columns: kp float32 [n][2],
+ * land float64 [n][3], state uint8 [n], track float32 [n][2], pose float64 [n][12] (camera-to-world, row-major 3x4),
+ * cand uint8 [n]; h_c2w float64 [48] = current and previous camera-to-world pose (3x4), the estimator's world-to-camera
+ * pose and the unrefined RANSAC model (both R row-major | t); h_scalars int32 [3 + VO_PIPE_NCOUNTS] = {num_features,
+ * n_iterations, P3P population, counters}; h_inliers uint8 [P3P population]; h_rng uint64 [6].  Any may be NULL.    */
+int vo_pipeline_read_table_host(vo_pipeline* pl, int seq, int* n_rows, float* h_kp, double* h_land, uint8_t* h_state, float* h_track,
+                                double* h_pose, uint8_t* h_cand, double* h_c2w, int32_t* h_scalars, uint8_t* h_inliers,
+                                uint64_t* h_rng);
+/* Replace a sequence's table (e.g. after the host-side two-view bootstrap, main.py:203-231); n_rows < 0 keeps the
+ * rows and only sets the scalars that are given.  num_features < 0 and
+ * n_iterations <= 0 keep the current values; h_c2w (3x4) and h_rng (numpy PCG64 state: state hi/lo, inc hi/lo,
+ * has_uint32, uinteger) may be NULL.                                                                              */
+int vo_pipeline_write_table_host(vo_pipeline* pl, int seq, int n_rows, const float* h_kp, const double* h_land, const uint8_t* h_state,
+                                 const float* h_track, const double* h_pose, const double* h_c2w, int num_features, int n_iterations,
+                                 const uint64_t* h_rng);
+int vo_pipeline_read_detections_host(vo_pipeline* pl, int seq, int32_t* h_xy, int* n);
+/* Test hook: n_draws samples of numpy's Generator(PCG64).choice(arange(N), size=4, replace=False) (ransac.py:92-94)
+ * from the given generator state; the state is advanced in place.                                                 */
+int vo_test_pcg64_choice4_host(vo_ctx* ctx, uint64_t* state6, int N, int n_draws, int32_t* h_out);
+
+
 #ifdef __cplusplus
 }
 #endif

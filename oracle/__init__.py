@@ -259,8 +259,9 @@ class RansacP3P:
     model_fn / error_fn of p3p.py:51-108, including the state the reference keeps between calls
     (rng stream seeded with 2023, outlier_ratio, n_iterations)."""
 
-    def __init__(self, K, inlier_threshold, outlier_ratio=0.9, confidence=0.99, max_iterations=np.inf):
+    def __init__(self, K, inlier_threshold, outlier_ratio=0.9, confidence=0.99, max_iterations=np.inf, inclusive=False):
         self.K = np.asarray(K, dtype=np.float64)
+        self.inclusive = inclusive          # True: `<=` (cv2.solvePnPRansac's rule, see vo_b200.h), False: ransac.py:105
         self.s = 4
         self.inlier_threshold = inlier_threshold
         self.outlier_ratio = outlier_ratio
@@ -285,7 +286,8 @@ class RansacP3P:
             model = p3p_solve4(L[idxs], P[idxs], self.K)
             if model is None:
                 continue
-            inl = reproj_errors(model[0], model[1], L, P, self.K) < self.inlier_threshold
+            e = reproj_errors(model[0], model[1], L, P, self.K)
+            inl = (e <= self.inlier_threshold) if self.inclusive else (e < self.inlier_threshold)
             c = inl.sum()
             if c > best_n:
                 best_n, best_inl, best_model = c, inl, model

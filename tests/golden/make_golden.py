@@ -268,12 +268,119 @@ def make_bookkeeping():
     print("bookkeeping.npz", {k: np.shape(v) for k, v in out.items()})
 
 
+def _ref_loop(p3p_opencv, mode="klt", refine=True, n_frames=6):
+    """The reference's src/main.py:185-287 without the plotting: bootstrap on frames 0 and 2, then the loop body for
+    the remaining frames.  Returns the bootstrap table and one record per loop frame."""
+    from vo.features import Tracker
+    from vo.landmarks import LandmarksTriangulator
+    from vo.pose_estimation import P3PPoseEstimator
+    from vo.primitives import Features, Frame, State
+    from vo.sensors import Camera
+
+    vals = open(f"{REF}/tests/test_data/kitti/05/calib.txt").readlines()[1].split(" ")[1:]      # loader.py:86-96
+    K = np.array([np.float32(v) for v in vals]).reshape(3, 4)[:, :3]
+    camera = Camera(intrinsic_matrix=K)
+    frames = []
+    for i in range(n_frames):
+        f = Frame(cv2.imread(f"{REF}/tests/test_data/kitti/05/image_0/{i:06d}.png"), sensor=camera, intrinsics=K)
+        f.frame_id = i
+        frames.append(f)
+    np.random.seed(0)                                # uids only (klt.py:70-72)
+    triangulator = LandmarksTriangulator(camera1=camera, camera2=camera, use_ransac=True, use_opencv=True,
+                                         outlier_ratio=0.9, ransac_threshold=0.25, ransac_confidence=0.999)   # main.py:185-193
+    pose_estimator = P3PPoseEstimator(use_opencv=p3p_opencv, intrinsic_matrix=K, inlier_threshold=1.25,
+                                      outlier_ratio=0.9, confidence=0.9999, nonlinear_refinement=refine)      # main.py:194-201
+    it = iter(frames)
+    init_frame = next(it)
+    state = State(init_frame)
+    next(it)
+    new_frame = next(it)
+    tracker = Tracker(init_frame, mode=mode)
+    init_kp = init_frame.features.keypoints.reshape(-1, 2).copy()
+    matches = tracker.trackFeatures(state.curr_frame, new_frame)
+    state.update_from_matches(matches)
+    M, landmarks, inliers = triangulator.triangulate_matches(matches)
+    outliers = np.zeros(shape=(matches.frame2.features.length,), dtype=bool)
+    outliers[matches.frame2.features.match_inliers] = ~inliers
+    state.update_with_local_pose(M)
+    inliers_mask = np.zeros_like(matches.frame2.features.matched_candidate_inliers).astype(bool)
+    inliers_mask[matches.frame2.features.matched_candidate_inliers] = inliers
+    state.update_with_local_landmarks(landmarks[inliers], inliers_mask)
+    state.reset_outliers(outliers)
+
+    def table(prefix):
+        f = state.curr_frame.features
+        return {prefix + "kp": f.keypoints.reshape(-1, 2).copy(), prefix + "land": f.landmarks.reshape(-1, 3).copy(),
+                prefix + "state": f.state.astype(np.int8), prefix + "track": f.tracks.reshape(-1, 2).copy(),
+                prefix + "pose": f.poses.copy(), prefix + "cand": f.candidate_mask.copy(),
+                prefix + "curr_pose": state.get_pose().copy()}
+    out = {"K": K, "init_kp": init_kp, "num_features": tracker._tracker._num_features}
+    out.update(table("boot_"))
+    for new_frame in it:
+        matches = tracker.trackFeatures(state.curr_frame, new_frame)
+        (rmatrix, tvec), inl = pose_estimator.estimate_pose(Features(
+            keypoints=matches.frame2.features.triangulated_inliers_keypoints,
+            landmarks=matches.frame2.features.triangulated_inliers_landmarks))
+        outliers = np.zeros(shape=(matches.frame2.features.length,), dtype=bool)
+        outliers[matches.frame2.features.triangulate_inliers] = ~inl
+        state.update_from_matches(matches)
+        state.update_with_world_pose(np.concatenate((rmatrix, tvec), axis=1))
+        state.reset_outliers(outliers)
+        state.compute_candidates()
+        n_candidates = np.sum(state.curr_frame.features.candidate_mask)
+        if n_candidates > 0:
+            lw = triangulator.triangulate_candidates(state.curr_frame.features, current_pose=state.get_pose())
+            state.update_with_world_landmarks(lw, matches.frame2.features.candidate_mask)
+        pre = f"f{new_frame.frame_id}_"
+        out.update(table(pre))
+        out[pre + "inliers"] = np.asarray(inl).copy()
+        out[pre + "R"], out[pre + "t"] = np.asarray(rmatrix).copy(), np.asarray(tvec).reshape(3).copy()
+        out[pre + "n_candidates"] = int(n_candidates)
+        if not p3p_opencv:
+            out[pre + "n_iterations"] = pose_estimator.ransac.n_iterations
+    return out
+
+
+def make_loop():
+    """The end-to-end pin (BASELINE configs[0]): the reference's main loop, KLT tracker mode, on the six KITTI frames it
+    ships.  `loop.npz` holds the run with use_opencv=False for P3P (reproducible: numpy rng 2023), `cv_*` keys the final
+    poses / inlier masks of the use_opencv=True run main.py itself uses (cv2.solvePnPRansac, tolerance pin only).
+    The frames are copied next to the fixtures so the GPU box (no /root/reference) can replay the loop."""
+    import shutil
+    dst = os.path.join(OUT, "kitti05")
+    os.makedirs(dst, exist_ok=True)
+    for i in range(6):
+        shutil.copyfile(f"{REF}/tests/test_data/kitti/05/image_0/{i:06d}.png", os.path.join(dst, f"{i:06d}.png"))
+    out = _ref_loop(p3p_opencv=False)
+    cvrun = _ref_loop(p3p_opencv=True)
+    for k, v in cvrun.items():
+        if k.startswith("f") and k.split("_", 1)[1] in ("inliers", "R", "t", "curr_pose", "n_candidates", "state"):
+            out["cv_" + k] = v
+    norefine = _ref_loop(p3p_opencv=False, refine=False)
+    for k, v in norefine.items():
+        if k.startswith("f") and k.split("_", 1)[1] in ("R", "t", "curr_pose", "inliers"):
+            out["noref_" + k] = v
+    # full-frame Harris goldens (BASELINE configs[0]/[1] shape): K = 200 (test_harris.py) and K = 1000 (main.py default)
+    from vo.features.harris import HarrisCornerDetector
+    from vo.primitives import Frame
+    g = kitti_gray(0)
+    for Kk in (200, 1000):
+        det = HarrisCornerDetector(num_keypoints=Kk)
+        out[f"harris_full_kp{Kk}"] = det.extractKeypoints(Frame(g.copy())).features.keypoints.reshape(-1, 2).astype(np.int32)
+    # Shi-Tomasi corners of every frame (klt.py:24-26, 99-100): cv2's own output, the detector of the KLT mode
+    for i in range(6):
+        out[f"gftt_{i}"] = cv2.goodFeaturesToTrack(kitti_gray(i), maxCorners=500, qualityLevel=0.01, minDistance=8,
+                                                   blockSize=7).reshape(-1, 2)
+    np.savez_compressed(os.path.join(OUT, "loop.npz"), **out)
+    print("loop.npz", {k: np.shape(v) for k, v in out.items() if not k.startswith(("cv_", "noref_"))})
+
+
 def to_pixels(K, M, X):
     x = K @ (M[:, :3] @ X + M[:, 3:])
     return x[:2] / x[2:]
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["harris", "klt", "p3p", "triangulation", "bookkeeping"]
+    which = sys.argv[1:] or ["harris", "klt", "p3p", "triangulation", "bookkeeping", "loop"]
     for w in which:
         globals()["make_" + w]()

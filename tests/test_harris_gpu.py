@@ -170,3 +170,22 @@ def test_nms_random_soak(ctx):
         assert np.array_equal(kp[0], oracle.harris_nms(m, K, r)), (it, kind, H, W, r, K)
         n += 1
     assert n == 100
+
+
+def test_full_kitti_frame_vs_reference(ctx, golden):
+    """The full frame the reference ships (1226x370, BASELINE configs[0]): the keypoints of the reference's own
+    HarrisCornerDetector, K = 200 (its tests/test_harris.py) and K = 1000 (main.py's default), in selection order."""
+    import os
+    import cv2
+    from conftest import GOLDEN
+    from vo import _ops
+    g = golden("loop")
+    img = cv2.imread(os.path.join(GOLDEN, "kitti05", "000000.png"), cv2.IMREAD_GRAYSCALE)
+    for K in (200, 1000):
+        kp, _, _ = _ops.harris_detect(img, K, ctx=ctx)
+        assert np.array_equal(kp, g[f"harris_full_kp{K}"]), K
+    # the drop-in class on the same frame
+    from vo.features import HarrisCornerDetector
+    from vo.primitives import Frame
+    fr = HarrisCornerDetector(num_keypoints=200).extractKeypoints(Frame(img.copy()))
+    assert np.array_equal(fr.features.keypoints.reshape(-1, 2).astype(np.int32), g["harris_full_kp200"])

@@ -111,3 +111,33 @@ def test_large_sweep_property(ctx):
     sel = rng.choice(Hn, 64, replace=False)
     m, v, c = oracle.p3p_ransac_score(L, uv, K, S[sel], 1.5)
     assert np.array_equal(r["counts"][sel], c) and np.array_equal(r["models"][sel], m)
+
+
+def test_full_size_sweep_3000x65536(ctx):
+    """BASELINE configs[2] at its upper end: 3000 correspondences x 65536 hypotheses in one call.  1024 hypotheses
+    are checked against the oracle bit for bit (models, validity, counts); the replay over all of them must pick
+    the first maximum, and its mask must have exactly that many inliers."""
+    from vo import _ops
+    rng = np.random.default_rng(17)
+    N, Hn = 3000, 65536
+    K = np.array([[707.0912, 0, 601.8873], [0, 707.0912, 183.1104], [0, 0, 1.0]])
+    L = rng.uniform(-12, 12, (N, 3))
+    L[:, 2] = rng.uniform(4, 60, N)
+    uv = (K @ L.T).T
+    uv = uv[:, :2] / uv[:, 2:] + rng.normal(0, 0.4, (N, 2))
+    out = rng.choice(N, int(0.4 * N), replace=False)
+    uv[out] += rng.uniform(-100, 100, (len(out), 2))
+    S = np.argsort(rng.random((Hn, 16)), axis=1)[:, :4].astype(np.int32)          # 4 distinct numbers ...
+    S = (S + rng.integers(0, N - 16, (Hn, 1))).astype(np.int32)                    # ... shifted to a random window
+    table = np.full(N + 1, 10 ** 7, np.int32)
+    r = _ops.p3p_ransac(L, uv, K, S, 1.25, table, 10 ** 7, want_all=True, ctx=ctx)
+    valid = r["valid"].astype(bool)
+    assert int(r["consumed"]) == Hn and bool(r["exhausted"]) and int(r["n"]) == int(valid.sum())
+    assert int(r["best"]) == int(np.argmax(np.where(valid, r["counts"], -1)))
+    assert int(r["best_count"]) == int(r["counts"][valid].max()) == int(r["inliers"].sum())
+    sel = np.sort(rng.choice(Hn, 1024, replace=False))
+    m, v, c = oracle.p3p_ransac_score(L, uv, K, S[sel], 1.25)
+    assert np.array_equal(r["valid"][sel], v) and np.array_equal(r["counts"][sel], c) and np.array_equal(r["models"][sel], m)
+    # the inclusive rule of the OpenCV mode never counts fewer
+    r2 = _ops.p3p_ransac(L, uv, K, S[:2048], 1.25, table, 10 ** 7, want_all=True, inclusive=True, ctx=ctx)
+    assert (r2["counts"] >= r["counts"][:2048]).all()

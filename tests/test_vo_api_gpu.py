@@ -147,3 +147,20 @@ def test_klt_tracker_vs_reference_run(ctx, golden):
     assert np.array_equal(kp1.astype(np.float32), g["tracker_kp1"])
     assert np.abs(kp2 - g["tracker_kp2"]).max() < 1e-2  # 1e-2 px
     assert (m.frame2.features.state == 1).all()
+
+
+def test_two_contexts_in_one_process():
+    """Per-device kernel attributes (dynamic shared memory opt-ins) are tracked per context: a second context -- on
+    another GPU when the box has one, else on the same -- must be able to run every large-shared-memory kernel."""
+    import torch
+    from conftest import synthetic_image
+    from vo import _native as nat, _ops
+    dev = 1 if torch.cuda.device_count() > 1 else 0
+    c2 = nat.Context(dev)
+    img = synthetic_image(128, 192, seed=3)
+    a = _ops.harris_detect(img, 60, desc_radius=9, ctx=c2)
+    b = _ops.harris_detect(img, 60, desc_radius=9, ctx=nat.default_context(0))
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    pairs = _ops.match_descriptors(a[2], b[2], ctx=c2)
+    assert len(pairs) > 30
+    c2.close()

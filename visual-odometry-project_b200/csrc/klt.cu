@@ -136,12 +136,13 @@ __device__ __forceinline__ void stage_patch(const uint8_t* __restrict__ img, int
 __global__ void __launch_bounds__(KLT_WARPS * 32)
 klt_track_kernel(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__ pyr_next, PyrLayout lay,
                  int win, int max_iters, double eps2, double min_eig, const float* __restrict__ prev_pts, int n_pts,
-                 float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
+                 float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err,
+                const int* __restrict__ n_valid) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pt = blockIdx.x * KLT_WARPS + warp;
     const int f = blockIdx.y;
-    if (pt >= n_pts) return;
+    if (pt >= n_pts || (n_valid && pt >= n_valid[f])) return;   // per-frame row count of a resident feature table
     const int w2 = win * win;
     const int pn = win + 3;                 // staged I neighbourhood
     const int dn = win + 1;                 // integer positions where derivatives / J are needed
@@ -365,7 +366,8 @@ template <int WIN>
 __global__ void __launch_bounds__(KLT_WARPS * 32, 4)
 klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__ pyr_next, PyrLayout lay,
                int max_iters, double eps2, double min_eig, const float* __restrict__ prev_pts, int n_pts,
-               float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
+               float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err,
+                const int* __restrict__ n_valid) {
     constexpr int W2 = WIN * WIN, PN = WIN + 3, DN = WIN + 1;
     constexpr int PPL = (W2 + 31) / 32;                        // window pixels per lane
     constexpr int PATCH_BYTES = (PN * PN + 15) & ~15;
@@ -374,7 +376,7 @@ klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pt = blockIdx.x * KLT_WARPS + warp;
     const int f = blockIdx.y;
-    if (pt >= n_pts) return;
+    if (pt >= n_pts || (n_valid && pt >= n_valid[f])) return;   // per-frame row count of a resident feature table
     uint8_t* patch = smem + warp * PER_WARP;                                  // I (PN^2), later J (DN^2)
     short* dpatch = reinterpret_cast<short*>(patch + PATCH_BYTES);             // [DN*DN][2]
 
@@ -610,7 +612,8 @@ template <int WIN>
 __global__ void __launch_bounds__(KLT_SWARPS * 32, 4)
 klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__ pyr_next, PyrLayout lay,
                 int max_iters, double eps2, double min_eig, const float* __restrict__ prev_pts, int n_pts,
-                float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err) {
+                float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err,
+                const int* __restrict__ n_valid) {
     constexpr int W2 = WIN * WIN, PN = WIN + 3, DN = WIN + 1;
     constexpr int T = (W2 + 31) / 32;                      // window pixels per lane
     constexpr int PATCH_BYTES = (PN * PN + 15) & ~15;
@@ -622,7 +625,7 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pt = blockIdx.x * KLT_SWARPS + warp;
     const int f = blockIdx.y;
-    if (pt >= n_pts) return;
+    if (pt >= n_pts || (n_valid && pt >= n_valid[f])) return;   // per-frame row count of a resident feature table
     uint8_t* patch = smem + warp * PER_WARP;                                  // I (PN^2), later J (DN^2)
     short* dpatch = reinterpret_cast<short*>(patch + PATCH_BYTES);             // [DN*DN][2]
     int* At = reinterpret_cast<int*>(patch + PATCH_BYTES);                     // [AN*AN] (fast setup, same storage)
@@ -931,7 +934,7 @@ int vo_launch_klt_pyramid(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H
 int vo_launch_klt_track(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d_pyr_next, int n_frames, int H, int W,
                         int max_level, int win, int max_iters, double epsilon, double min_eig,
                         const float* d_prev_pts, int n_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const int* d_n_valid) {
     PyrLayout L;
     VO_REQUIRE(H >= 1 && W >= 1 && win >= 3 && win <= 31 && n_frames >= 1 && n_pts >= 0, "klt track: bad arguments");
     VO_REQUIRE(klt_layout(H, W, max_level, win, &L) == 0, "klt: max_level must be in [0, %d)", KLT_MAX_LEVELS);
@@ -954,20 +957,20 @@ int vo_launch_klt_track(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d
     if (win == 17 && roomy && !ctx->env_klt_generic) {
         dim3 gs(vo_div_up(n_pts, KLT_SWARPS), n_frames);
         klt_track_packed<17><<<gs, KLT_SWARPS * 32, 0, stream>>>(d_pyr_prev, d_pyr_next, L, max_iters, epsilon * epsilon, min_eig,
-                                                                  d_prev_pts, n_pts, d_next_pts, d_status, d_err);
+                                                                  d_prev_pts, n_pts, d_next_pts, d_status, d_err, d_n_valid);
         ctx->launches++;
         VO_CHECK_LAUNCH();
         return VO_OK;
     }
     if (win == 21 && roomy && !ctx->env_klt_generic) {
         klt_track_fast<21><<<g, KLT_WARPS * 32, 0, stream>>>(d_pyr_prev, d_pyr_next, L, max_iters, epsilon * epsilon, min_eig,
-                                                              d_prev_pts, n_pts, d_next_pts, d_status, d_err);
+                                                              d_prev_pts, n_pts, d_next_pts, d_status, d_err, d_n_valid);
         ctx->launches++;
         VO_CHECK_LAUNCH();
         return VO_OK;
     }
     klt_track_kernel<<<g, KLT_WARPS * 32, smem, stream>>>(d_pyr_prev, d_pyr_next, L, win, max_iters, epsilon * epsilon,
-                                                          min_eig, d_prev_pts, n_pts, d_next_pts, d_status, d_err);
+                                                          min_eig, d_prev_pts, n_pts, d_next_pts, d_status, d_err, d_n_valid);
     ctx->launches++;
     VO_CHECK_LAUNCH();
     return VO_OK;

@@ -79,6 +79,20 @@ def lib():
             "vo_frontend_submit_host": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp,
                                               vp, vp, vp, vp, vp, vp, vp, vp]),
             "vo_frontend_wait_host": (i32, [vp]),
+            "vo_pipeline_create": (i32, [vp, vp, C.POINTER(vp)]),
+            "vo_pipeline_destroy": (None, [vp]),
+            "vo_pipeline_prime_dev": (i32, [vp, vp, sz, sz, i32, vp]),
+            "vo_pipeline_prime_host": (i32, [vp, vp, i32]),
+            "vo_pipeline_step_dev": (i32, [vp, vp, sz, sz, vp]),
+            "vo_pipeline_summary_dev": (vp, [vp]),
+            "vo_pipeline_prefetch_host": (i32, [vp, vp]),
+            "vo_pipeline_submit_host": (i32, [vp, vp, vp]),
+            "vo_pipeline_wait_host": (i32, [vp]),
+            "vo_pipeline_step_host": (i32, [vp, vp, vp]),
+            "vo_pipeline_read_table_host": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+            "vo_pipeline_write_table_host": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+            "vo_pipeline_read_detections_host": (i32, [vp, i32, vp, vp]),
+            "vo_test_pcg64_choice4_host": (i32, [vp, vp, i32, i32, vp]),
         })
         for name, (rt, at) in _optional.items():
             if hasattr(L, name):  # all are present in a complete build; tests/test_abi.py checks that
