@@ -1,6 +1,6 @@
 // Device functions of the P3P minimal solver and the reprojection test, shared by p3p.cu (batched scoring) and
 // pipeline.cu (the per-sequence RANSAC of the resident pipeline).  See p3p.cu for the algorithm notes; float64 with
-// + - * / sqrt only and --fmad=false, in the same order as oracle/p3p.c.
+// + - * / sqrt only and --fmad=false, in the same order as the CPU checker used by the tests.
 #pragma once
 #include "common.cuh"
 

@@ -24,7 +24,7 @@
 //                         winner's inlier mask and a damped Gauss-Newton refinement on SE(3) (block reductions)
 //   pipe_update_kernel    pose inverse, reset_outliers, bearing-angle candidates, per-row DLT (Jacobi SVD in registers),
 //                         cheirality check, per-sequence summary
-// float64 for geometry (--fmad=false, same operation order as oracle/loop.py), float32 keypoints as cv2 returns them.
+// float64 for geometry (--fmad=false, same operation order as the CPU restatement the tests check it against), float32 keypoints as cv2 returns them.
 #include "../../include/vo_b200.h"
 
 #include <initializer_list>
@@ -435,7 +435,7 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
     int gn_iters = 0;
     if (P.refine) {
         // Damped Gauss-Newton on SE(3) over the inliers' 2N reprojection residuals (same minimum as p3p.py:188-213's
-        // least_squares over per-point distances; oracle/loop.py::refine_gn is the restatement this follows).
+        // least_squares over per-point distances; the tests hold a numpy restatement of exactly these steps).
         double lam = 0.0, cost = 0.0;
         bool have_system = false;
         double Hs[21], gs[6];
