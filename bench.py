@@ -1,18 +1,22 @@
 #!/usr/bin/env python
-"""VO front-end benchmark: frames/s of the full step (Harris + KLT + P3P-RANSAC + triangulation) on
-synthetic KITTI-shaped 1241x376 grayscale sequences, plus the Harris response kernel's HBM roofline.
+"""VO front-end benchmark: frames/s of the full, CHAINED step (Harris + KLT + P3P-RANSAC + triangulation with the
+reference's per-frame data flow, src/main.py:248-287) on synthetic KITTI-shaped 1241x376 grayscale sequences, plus the
+Harris response kernel's HBM roofline.
 
-    python bench.py --gpus 1 --steps 20 --warmup 3            # this repo's CUDA path
-    python bench.py --impl reference --steps 3 --warmup 1     # the reference algorithm on host cores
+    python bench.py --gpus 1 --steps 60 --warmup 5           # this repo's CUDA path (vo_pipeline_*)
+    python bench.py --impl reference --steps 3 --warmup 1    # the reference algorithm on the box's host cores
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --workload p3p_sweep | stress            # the other BASELINE configs (extra lines, same contract)
 
-One "step" advances S independent sequences (S per GPU, `config.sequences_per_gpu`) by one frame.
-`value` is measured with every input resident in HBM (CUDA events on the launching stream, max
-over ranks); `e2e` goes through the host-buffer C ABI (vo_frontend_step_host): frames and all
-other inputs start in pinned host memory and results are read back every step.
-Sequences are sharded across ranks with no data-path collective (weak scaling).
+One "step" advances S independent sequences (S per GPU, `config.sequences_per_gpu`) by one frame: the detector runs on
+the new frame, the sequence's feature table (resident in HBM) is tracked into it, the pose comes from P3P-RANSAC on the
+rows that carry landmarks, outliers restart their tracks, tracks with enough parallax are triangulated.  `value` is
+measured with the frames already in HBM (CUDA events on the launching stream, max over ranks); `e2e` goes through the
+host-buffer C ABI: every step uploads its frames from pinned host memory (nothing else) and downloads the poses and
+counters.  Sequences are sharded across ranks with no data-path collective (weak scaling).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import subprocess
@@ -29,10 +33,15 @@ sys.path.insert(0, ROOT)
 H, W = 376, 1241
 K_INTR = np.array([[707.0912, 0, 601.8873], [0, 707.0912, 183.1104], [0, 0, 1.0]])
 METRIC = "VO frames/s @1241x376 (Harris+KLT+P3P-RANSAC+triang)"
+DEPTH = 20.0                  # the static scene is a textured plane at this depth
+FLOW = (3, 1)                 # camera translation per frame, in pixels of image motion (x, y)
+KP, CAPACITY = 1000, 2048     # Harris keypoints per detection (harris.py:16-34), table rows per sequence
+P3P_CONF, P3P_MAX_ITER, P3P_THR = 0.9999, 10000, 1.25          # src/main.py:194-201
+N_MOVERS = 22                 # independently moving patches per sequence: their features are the RANSAC outliers
 
 
 # ------------------------------------------------------------------------------------------------
-# synthetic workload (seeded; the same generator feeds the CUDA arm, the e2e arm and the CPU arm)
+# synthetic world (seeded; the same generator feeds the CUDA arm, the e2e arm and the CPU arm)
 # ------------------------------------------------------------------------------------------------
 def make_texture(seed, th=1024, tw=3072):
     import cv2
@@ -49,76 +58,94 @@ def make_texture(seed, th=1024, tw=3072):
 
 
 def frame_from_texture(tex, s, t):
-    """Frame t of sequence s: a crop that moves 3 px right / 1 px down per frame."""
+    """Frame t of sequence s without movers: a crop that moves FLOW px per frame (used by the stage-level tools)."""
     th, tw = tex.shape
-    ox = (37 * s + 3 * t) % (tw - W)
-    oy = (11 * s + t) % (th - H)
+    ox = (37 * s + FLOW[0] * t) % (tw - W)
+    oy = (11 * s + FLOW[1] * t) % (th - H)
     return tex[oy:oy + H, ox:ox + W]
 
 
-def make_geometry(seed, S, N, T, Hn):
-    """3D-2D correspondences (30% outliers), sample-index sets and triangulation tracks per sequence."""
-    rng = np.random.default_rng(seed)
-    L = rng.uniform(-12, 12, (S, N, 3))
-    L[..., 2] = rng.uniform(5, 50, (S, N))
-    kp = np.empty((S, N, 2))
+class World:
+    """S sequences of a camera translating in front of a textured plane (depth DEPTH, FLOW pixels of image motion per
+    frame) with N_MOVERS independently moving patches each.  Frame `t` of every sequence is a pure function of t, so a
+    pool of P time steps can be walked back and forth (0, 1, .., P-1, P-2, .., 0, 1, ..) as an endless, geometrically
+    consistent sequence."""
+
+    def __init__(self, seed, S, P):
+        self.S, self.P = S, P
+        self.tex = make_texture(seed)
+        self.tex2 = make_texture(seed + 7919, 512, 1024)
+        rng = np.random.default_rng(seed + 1)
+        th, tw = self.tex.shape
+        self.ox = (37 * np.arange(S)) % (tw - W - FLOW[0] * P)
+        self.oy = (11 * np.arange(S)) % (th - H - FLOW[1] * P)
+        m = N_MOVERS
+        self.mw, self.mh = rng.integers(40, 100, (S, m)), rng.integers(30, 70, (S, m))
+        self.mx, self.my = rng.uniform(0, W - 100, (S, m)), rng.uniform(0, H - 70, (S, m))
+        v = rng.uniform(2.0, 5.0, (S, m)) * rng.choice([-1, 1], (S, m))
+        self.mvx = v - FLOW[0] * (v < 0)                      # at least 2 px/frame away from the background flow (-FLOW)
+        self.mvy = rng.integers(-3, 4, (S, m)).astype(float)
+        self.msx, self.msy = rng.integers(0, 1024 - 100, (S, m)), rng.integers(0, 512 - 70, (S, m))
+
+    def frame(self, s, t):
+        oy, ox = self.oy[s] + FLOW[1] * t, self.ox[s] + FLOW[0] * t
+        f = self.tex[oy:oy + H, ox:ox + W].copy()
+        for j in range(N_MOVERS):
+            x, y = int(round(self.mx[s, j] + self.mvx[s, j] * t)), int(round(self.my[s, j] + self.mvy[s, j] * t))
+            w, h = int(self.mw[s, j]), int(self.mh[s, j])
+            x0, y0, x1, y1 = max(x, 0), max(y, 0), min(x + w, W), min(y + h, H)
+            if x1 > x0 and y1 > y0:
+                sx, sy = int(self.msx[s, j]) + (x0 - x), int(self.msy[s, j]) + (y0 - y)
+                f[y0:y1, x0:x1] = self.tex2[sy:sy + (y1 - y0), sx:sx + (x1 - x0)]
+        return f
+
+    def pool(self):
+        out = np.empty((self.P, self.S, H, W), np.uint8)
+        for t in range(self.P):
+            for s in range(self.S):
+                out[t, s] = self.frame(s, t)
+        return out
+
+    def time_index(self, i):
+        """pool index of step i of the endless back-and-forth walk"""
+        if self.P == 1:
+            return 0
+        k = i % (2 * (self.P - 1))
+        return k if k < self.P else 2 * (self.P - 1) - k
+
+    @staticmethod
+    def landmarks_of(kp_xy):
+        """World points (camera-0 frame) of frame-0 pixels on the static plane."""
+        kp = np.asarray(kp_xy, dtype=np.float64).reshape(-1, 2)
+        return np.stack([(kp[:, 0] - K_INTR[0, 2]) * DEPTH / K_INTR[0, 0], (kp[:, 1] - K_INTR[1, 2]) * DEPTH / K_INTR[1, 1],
+                         np.full(len(kp), DEPTH)], 1)
+
+    @staticmethod
+    def true_position(t):
+        return np.array([FLOW[0] * t * DEPTH / K_INTR[0, 0], FLOW[1] * t * DEPTH / K_INTR[1, 1], 0.0])
+
+
+def pipeline_kwargs():
+    return dict(capacity=CAPACITY, det_max_corners=KP, p3p_threshold=P3P_THR, p3p_opencv=False, confidence=P3P_CONF,
+                max_iterations=P3P_MAX_ITER, refine=True, tri_opencv=True)
+
+
+def start_tables(pl, S):
+    """Hand-over after the (host-side, one-off) bootstrap: every corner of frame 0 gets the landmark of the static plane
+    under it (corners on moving patches get a wrong one: they are the first outliers)."""
     for s in range(S):
-        ang = rng.normal(0, 0.05, 3)
-        Rx = np.array([[1, 0, 0], [0, np.cos(ang[0]), -np.sin(ang[0])], [0, np.sin(ang[0]), np.cos(ang[0])]])
-        Ry = np.array([[np.cos(ang[1]), 0, np.sin(ang[1])], [0, 1, 0], [-np.sin(ang[1]), 0, np.cos(ang[1])]])
-        R = Rx @ Ry
-        t = rng.normal(0, 0.3, 3)
-        Xc = L[s] @ R.T + t
-        uv = Xc @ K_INTR.T
-        kp[s] = uv[:, :2] / uv[:, 2:] + rng.normal(0, 0.3, (N, 2))
-        out = rng.choice(N, int(0.3 * N), replace=False)
-        kp[s, out] += rng.uniform(-80, 80, (len(out), 2))
-    samples = np.empty((S, Hn, 4), np.int32)
-    for s in range(S):
-        samples[s] = np.argsort(rng.random((Hn, N)), axis=1)[:, :4]   # 4 distinct indices per set
-    X = rng.uniform(-10, 10, (S, T, 3))
-    X[..., 2] = rng.uniform(6, 60, (S, T))
-    proj2 = np.empty((S, 3, 4))
-    proj1 = np.empty((S, T, 3, 4))
-    p1 = np.empty((S, T, 2))
-    p2 = np.empty((S, T, 2))
-    Xh = np.concatenate([X, np.ones((S, T, 1))], -1)
-    for s in range(S):
-        proj2[s] = K_INTR @ np.hstack([np.eye(3), np.array([[-0.8], [0.0], [0.1]])])
-        base = np.hstack([np.eye(3), np.zeros((3, 1))])
-        M = np.repeat(base[None], T, 0)
-        M[:, :, 3] += rng.normal(0, 0.1, (T, 3))
-        proj1[s] = K_INTR @ M
-        a = np.einsum("tij,tj->ti", proj1[s], Xh[s])
-        b = Xh[s] @ proj2[s].T
-        p1[s] = a[:, :2] / a[:, 2:] + rng.normal(0, 0.3, (T, 2))
-        p2[s] = b[:, :2] / b[:, 2:] + rng.normal(0, 0.3, (T, 2))
-    return dict(landmarks=L, kp2d=kp, samples=samples, tri_p1=p1, tri_p2=p2, tri_proj1=proj1.reshape(S, T, 12),
-                tri_proj2=proj2.reshape(S, 12))
-
-
-def iters_table(N, conf, max_iter):
-    """n_iterations(best_n_inliers) exactly as ransac.py:58-67,115-120 evaluates it (numpy scalars)."""
-    out = np.empty(N + 1, dtype=np.int32)
-    for c in range(N + 1):
-        ratio = min(max(1 - np.int64(c) / N, 0.01), 0.99)
-        out[c] = int(min(max_iter, int(np.ceil(np.log(1 - conf) / np.log(1 - (1 - ratio) ** 4)))))
-    return out
-
-
-P3P_CONF, P3P_MAX_ITER, P3P_THR = 0.9999, 10000, 1.25          # src/main.py:194-201
-
-
-def initial_iters():
-    return int(min(P3P_MAX_ITER, int(np.ceil(np.log(1 - P3P_CONF) / np.log(1 - (1 - 0.9) ** 4)))))
+        t = pl.read_table(s)
+        n = t["n"]
+        pl.write_table(s, t["kp"], World.landmarks_of(t["kp"]), np.full(n, 2), t["kp"], np.stack([np.eye(4)] * n),
+                       curr_pose=np.eye(4), num_features=KP)
 
 
 # ------------------------------------------------------------------------------------------------
 # clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Polls NVML every few ms from a thread while the timed region runs (nvidia-smi -lms is too coarse for
-    a region of tens of ms); falls back to one nvidia-smi query."""
+    """Polls NVML every few ms from a thread while the timed region runs (nvidia-smi -lms is too coarse for a region of
+    a fraction of a second); falls back to one nvidia-smi query."""
 
     def __init__(self, gpu_index):
         self.idx, self.sm, self.reasons, self.max_mhz, self._stop, self.th = gpu_index, [], set(), None, False, None
@@ -168,55 +195,112 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm on host cores (oracle port; cv2 for the call the reference itself
-# makes into OpenCV).  Only this function and cpu_baseline touch oracle/.
+# CPU arm: the reference algorithm on host cores (loop oracle = restated main.py loop; cv2 for the call the reference
+# itself makes into OpenCV, scipy for its refinement).  Only these functions touch oracle/.
 # ------------------------------------------------------------------------------------------------
-def cpu_frame(args):
+def _cv_klt(prev, nxt, pts, win, max_level, max_iters, epsilon):
     import cv2
+    n, s, e = cv2.calcOpticalFlowPyrLK(prev, nxt, np.ascontiguousarray(pts).reshape(-1, 1, 2), None, winSize=(win, win),
+                                       maxLevel=max_level, criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, max_iters, epsilon))
+    return n.reshape(-1, 2), s.ravel(), e.ravel()
+
+
+def cpu_make_sequence(world, s):
     import oracle
-    prev, cur, geo, s, Hn, table, init = args
-    kp, _ = oracle.harris_keypoints(cur, 1000, 9, 0.09, 5)                       # harris.py:86-158
-    cv2.calcOpticalFlowPyrLK(prev, cur, kp.astype(np.float32).reshape(-1, 1, 2), None, winSize=(17, 17),
-                             maxLevel=2, criteria=(cv2.TERM_CRITERIA_EPS | cv2.TERM_CRITERIA_COUNT, 10, 0.03))
-    models, valid, counts = oracle.p3p_ransac_score(geo["landmarks"][s], geo["kp2d"][s], K_INTR, geo["samples"][s][:Hn], P3P_THR)
-    oracle.ransac_scan(valid, counts, table, init)
-    oracle.triangulate(geo["tri_p1"][s], geo["tri_p2"][s], geo["tri_proj1"][s].reshape(-1, 3, 4),
-                       geo["tri_proj2"][s].reshape(3, 4), mode=1)
-    return 1
+    from oracle.loop import LoopOracle
+    det = lambda im: oracle.harris_keypoints(im, KP, 9, 0.09, 5)[0].astype(np.float32)      # harris.py:86-158
+    lo = LoopOracle(K_INTR, detector=det, refine="scipy", klt=_cv_klt, inlier_threshold=P3P_THR, confidence=P3P_CONF,
+                    max_iterations=P3P_MAX_ITER, eager_detector=True)
+    f0 = world.frame(s, 0)
+    lo.init_detect(f0)
+    lo.set_table(lo.kp, World.landmarks_of(lo.kp), np.full(len(lo.kp), 2), lo.kp, lo.pose, curr_pose=np.eye(4), num_features=KP)
+    lo._cached_det = det(f0)
+    return lo
 
 
-def cpu_pipeline_fps(n_frames, steps, warmup, Hn, threads):
-    """frames/s of the CPU arm: `n_frames` frames per step spread over `threads` host threads."""
-    from concurrent.futures import ThreadPoolExecutor
+def _cpu_worker(conn, seed, n_seq, P, mine):
+    """One host process of the CPU arm: owns the sequences `mine` and advances them on command."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+    except Exception:
+        pass
     import oracle
     oracle.lib()
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    tex = make_texture(1234)
-    geo = make_geometry(99, n_frames, 1000, 1000, Hn)
-    table, init = iters_table(1000, P3P_CONF, P3P_MAX_ITER), initial_iters()
-    jobs = [(np.ascontiguousarray(frame_from_texture(tex, s, 0)), np.ascontiguousarray(frame_from_texture(tex, s, 1)),
-             geo, s, Hn, table, init) for s in range(n_frames)]
-    times = []
-    with ThreadPoolExecutor(max_workers=threads) as ex:
-        for it in range(warmup + steps):
-            t0 = time.perf_counter()
-            list(ex.map(cpu_frame, jobs))
-            if it >= warmup:
-                times.append(time.perf_counter() - t0)
+    world = World(seed, n_seq, P)
+    seqs = {s: cpu_make_sequence(world, s) for s in mine}
+    frames = {(s, t): world.frame(s, t) for s in mine for t in range(P)}
+    conn.send("ready")
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            break
+        a, b = msg
+        infos = [seqs[s].step(frames[(s, a)], frames[(s, b)]) for s in mine]
+        conn.send([(i["n_tracked"], i["p3p_N"], i["n_candidates"]) for i in infos])
+    conn.close()
+
+
+def cpu_pipeline_fps(n_seq, steps, warmup, procs, seed=1234):
+    """frames/s of the CPU arm: `n_seq` sequences advance one frame per step on `procs` host processes (the reference
+    is single-threaded Python; independent sequences in independent processes is how it would be scaled on a host)."""
+    import multiprocessing as mp
+    import oracle
+    oracle.lib()                                   # build the C port once, before the workers need it
+    mpc = mp.get_context("spawn")                  # the parent may hold a CUDA context: never fork it
+    P = min(8, warmup + steps + 1)
+    world = World(seed, 1, P)
+    workers = []
+    for w in range(procs):
+        mine = list(range(w, n_seq, procs))
+        if not mine:
+            continue
+        pc, cc = mpc.Pipe()
+        pr = mpc.Process(target=_cpu_worker, args=(cc, seed, n_seq, P, mine), daemon=True)
+        pr.start()
+        workers.append((pr, pc))
+    for _, pc in workers:
+        assert pc.recv() == "ready"
+    times, stats = [], []
+    for it in range(warmup + steps):
+        a, b = world.time_index(it), world.time_index(it + 1)
+        t0 = time.perf_counter()
+        for _, pc in workers:
+            pc.send((a, b))
+        res = [r for _, pc in workers for r in pc.recv()]
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+            stats.append(np.mean(np.array(res, dtype=np.float64), axis=0))
+    for pr, pc in workers:
+        pc.send(None)
+    for pr, pc in workers:
+        pr.join(timeout=10)
     ms = 1e3 * float(np.mean(times))
-    return n_frames / (ms / 1e3), ms
+    return n_seq / (ms / 1e3), ms, np.mean(stats, axis=0).tolist()
 
 
 # ------------------------------------------------------------------------------------------------
 def bind_near_gpu(local_rank):
-    """Pin this process to the CPUs NVML names as closest to its GPU, so that the pinned staging buffers are allocated on
-    that socket and uploads do not cross the inter-socket link.  Best effort: returns a short description."""
+    """Pin this process -- and with it the pinned staging buffers it allocates next -- to the NUMA node of its GPU, so
+    that uploads do not cross the inter-socket link.  CPU affinity first (NVML's ideal set when it is a proper subset of
+    what we may use); independently of that the MEMORY policy is set to the GPU's node with set_mempolicy(MPOL_PREFERRED),
+    which works even when the cpuset does not contain that node's CPUs.  Best effort: returns a short description."""
+    notes = []
+    node = None
     try:
         import pynvml as nv
         nv.nvmlInit()
         vis = os.environ.get("CUDA_VISIBLE_DEVICES")
         phys = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].strip().isdigit() else local_rank
         h = nv.nvmlDeviceGetHandleByIndex(phys)
+        try:
+            bus = nv.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            path = f"/sys/bus/pci/devices/{bus.lower()[-12:]}/numa_node"
+            node = int(open(path).read().strip())
+        except Exception:
+            node = None
         n_words = (os.cpu_count() + 63) // 64
         mask = nv.nvmlDeviceGetCpuAffinity(h, n_words)
         cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
@@ -224,24 +308,54 @@ def bind_near_gpu(local_rank):
         use = cpus & allowed
         if use and use != allowed:
             os.sched_setaffinity(0, use)
-            return f"bound to {len(use)} cpus near gpu {phys}"
-        return f"no binding ({len(cpus)} ideal cpus, {len(allowed)} allowed)"
+            notes.append(f"cpus: bound to {len(use)} near gpu {phys}")
+        else:
+            notes.append(f"cpus: no binding ({len(cpus)} ideal, {len(allowed)} allowed)")
     except Exception as ex:   # NVML or the affinity call not available: run unbound
-        return f"no binding ({type(ex).__name__})"
+        notes.append(f"cpus: no binding ({type(ex).__name__})")
+    try:
+        if node is not None and node >= 0:
+            libc = C.CDLL(None, use_errno=True)
+            MPOL_PREFERRED = 1
+            maskbits = (C.c_ulong * 16)()
+            maskbits[node // 64] = 1 << (node % 64)
+            rc = libc.syscall(238, MPOL_PREFERRED, maskbits, C.c_ulong(16 * 64 + 1))       # __NR_set_mempolicy (x86_64)
+            notes.append(f"memory: preferred numa node {node}" if rc == 0 else f"memory: set_mempolicy failed (errno {C.get_errno()})")
+        else:
+            notes.append("memory: gpu numa node unknown")
+    except Exception as ex:
+        notes.append(f"memory: no policy ({type(ex).__name__})")
+    return "; ".join(notes)
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def workload_text():
+    return ("synthetic KITTI-shaped 1241x376 grayscale sequences (camera translating over a textured plane, "
+            f"{N_MOVERS} independently moving patches per sequence), chained per-frame flow of src/main.py:248-287: "
+            f"Harris detection of {KP} keypoints on every frame, pyramidal KLT (win 17, 3 levels) of the sequence's "
+            f"feature table (up to {CAPACITY} rows), P3P-RANSAC (numpy PCG64 stream, adaptive stop, conf {P3P_CONF}) on the "
+            "triangulated rows + pose refinement, bearing-angle candidates, DLT triangulation, cheirality check")
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="vo", choices=["vo", "p3p_sweep", "stress"])
     ap.add_argument("--seqs", type=int, default=148, help="independent sequences per GPU")
-    ap.add_argument("--hyp", type=int, default=512, help="P3P hypotheses per frame")
-    ap.add_argument("--pool", type=int, default=6, help="distinct frame sets cycled through (inputs > L2)")
+    ap.add_argument("--pool", type=int, default=8, help="distinct time steps per sequence, walked back and forth (inputs > L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps")
     ap.add_argument("--no-single-sequence", action="store_true", help="skip the S = 1 leg (keeps an ncu launch list to one batch size)")
+    ap.add_argument("--no-extras", action="store_true", help="only the contract line's own measurements")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -252,19 +366,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n_frames = cores
-        fps, ms = cpu_pipeline_fps(n_frames, args.steps, args.warmup, args.hyp, cores)
+        n_seq = cores
+        fps, ms, st = cpu_pipeline_fps(n_seq, args.steps, args.warmup, cores)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic KITTI-shaped 1241x376, 1000 Harris keypoints, 1000 KLT points, "
-                                   f"{args.hyp} P3P hypotheses x 1000 correspondences, 1000 triangulated points",
-                       "frames_per_step": n_frames},
+            "config": {"workload": workload_text(), "frames_per_step": n_seq,
+                       "mean_rows_tracked": st[0], "mean_p3p_population": st[1], "mean_candidates": st[2]},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"{n_frames} frames per step on {cores} host threads: oracle C port of "
-                                       "harris.py / ransac.py+p3p.py, cv2.calcOpticalFlowPyrLK (the reference's own "
-                                       "call), numpy SVD triangulation"},
+                             "sample": f"{n_seq} sequences advance one frame per step on {cores} host processes: oracle C port of "
+                                       "harris.py, cv2.calcOpticalFlowPyrLK (the reference's own call), oracle C port of "
+                                       "cv2.solvePnP(P3P) + ransac.py's loop with the numpy rng, scipy least_squares refinement "
+                                       "(p3p.py:188-213), numpy bookkeeping of matches.py / state.py, numpy SVD triangulation"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -272,7 +386,7 @@ def main():
     import torch
     import torch.distributed as dist
     from vo import _native as nat
-    from vo.frontend import Frontend
+    from vo.pipeline import DETECTOR_HARRIS, SUMMARY_DOUBLES, Pipeline
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
@@ -282,36 +396,35 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = nat.Context(local_rank)
-    S, Hn, P, N, T, KP = args.seqs, args.hyp, args.pool, 1000, 1000, 1000
+    L = nat.lib()
+    if args.workload != "vo":
+        import bench_extra
+        line = bench_extra.run(args, ctx, dev, rank, world, ClockSampler(local_rank), load_peaks())
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    S, P = args.seqs, max(2, args.pool)
 
     # ---- synthetic inputs -------------------------------------------------------------------
-    tex = make_texture(1234 + rank)
-    pitch = (W + 15) & ~15
-    pool_h = np.zeros((P, S, H, W), np.uint8)
-    for t in range(P):
-        for s in range(S):
-            pool_h[t, s] = frame_from_texture(tex, s, t)
+    wd = World(1234 + rank, S, P)
+    pool_h = wd.pool()
     pool_pinned = torch.from_numpy(pool_h).pin_memory()
+    pitch = (W + 15) & ~15
     pool_d = torch.zeros((P, S, H, pitch), dtype=torch.uint8, device=dev)
     pool_d[..., :W] = pool_pinned.to(dev)
-    geo = make_geometry(99 + rank, S, N, T, Hn)
-    table_h = iters_table(N, P3P_CONF, P3P_MAX_ITER)
-    init = initial_iters()
-    K9 = np.ascontiguousarray(K_INTR.reshape(9))
-    hostbuf = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in geo.items()}
-    hostbuf["table"] = torch.from_numpy(table_h).pin_memory()
-    devbuf = {k: v.to(dev) for k, v in hostbuf.items()}
-    fe = Frontend(S, H, W, num_keypoints=KP, n_corr=N, n_hyp=Hn, p3p_threshold=P3P_THR, n_tri=T, tri_mode=1, ctx=ctx)
     tstream = torch.cuda.Stream(device=dev)          # explicit stream: kernels and timing events share it
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
 
-    def step_dev(i):
-        fr = pool_d[i % P]
-        fe.step_dev(fr.data_ptr(), pitch, H * pitch, devbuf["landmarks"].data_ptr(), devbuf["kp2d"].data_ptr(), K9,
-                    devbuf["samples"].data_ptr(), devbuf["table"].data_ptr(), init, devbuf["tri_p1"].data_ptr(),
-                    devbuf["tri_p2"].data_ptr(), devbuf["tri_proj1"].data_ptr(), devbuf["tri_proj2"].data_ptr(), stream)
+    def new_pipeline(n_seq):
+        pl = Pipeline(n_seq, H, W, K_INTR, detector=DETECTOR_HARRIS, ctx=ctx, **pipeline_kwargs())
+        pl.prime_dev(pool_d[0].data_ptr(), pitch, H * pitch, init_tables=True, stream=stream)
+        torch.cuda.synchronize()
+        start_tables(pl, n_seq)
+        return pl
 
     def barrier():
         torch.cuda.synchronize()
@@ -327,8 +440,14 @@ def main():
         return float(t.item())
 
     # ---- device-resident arm (`value`) -----------------------------------------------------
-    for i in range(warmup):
-        step_dev(i)
+    pl = new_pipeline(S)
+
+    def step_dev(p, i, n_seq=S):
+        fr = pool_d[wd.time_index(i)]
+        p.step_dev(fr.data_ptr(), pitch, H * pitch, stream=stream)
+
+    for i in range(1, warmup + 1):
+        step_dev(pl, i)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -337,7 +456,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(tstream)
     for i in range(args.steps):
-        step_dev(warmup + i)
+        step_dev(pl, warmup + 1 + i)
     e1.record(tstream)
     barrier()
     launches = ctx.launch_count() - l0
@@ -346,19 +465,23 @@ def main():
     ms_step = ms_total / args.steps
     value = world * S * args.steps / (ms_total / 1e3)
 
-    # sanity: the step produced something (poses finite, keypoints non-trivial)
-    o = fe.outputs()
-    pose = np.empty((S, 12))
-    kp_chk = np.empty((S, KP, 2), np.int32)
-    import ctypes as C
-    ctx.copy_to_host(pose, o.d_pose)
-    ctx.copy_to_host(kp_chk, o.d_kp_xy)
-    if not (np.isfinite(pose).all() and kp_chk.any()):
-        raise SystemExit("bench.py: the timed step produced no valid output")
+    # sanity + workload statistics from the last step's summary: poses finite and on the true trajectory
+    summ_raw = np.empty((S, SUMMARY_DOUBLES))
+    ctx.copy_to_host(summ_raw, pl.summary_dev())
+    summ = Pipeline.summary_dict(summ_raw)
+    t_true = World.true_position(wd.time_index(warmup + args.steps))
+    pos_err = np.linalg.norm(summ["pose"][:, :, 3] - t_true, axis=1)
+    # monocular VO drifts (landmarks triangulated over two or three frames of 0.085 units of baseline each at depth 20);
+    # "valid" = finite, still on the trajectory (a frame of motion is 0.09 units) and most rows carrying landmarks
+    if not (np.isfinite(summ["pose"]).all() and np.median(pos_err) < 0.5 and (summ["n_tri"] > 100).mean() > 0.9):
+        raise SystemExit(f"bench.py: the timed steps did not produce valid poses (median position error {np.median(pos_err):.3g})")
+    stats = {k: float(np.mean(summ[k])) for k in ("n_tracked", "n_kept", "p3p_N", "n_inliers", "n_candidates", "n_tri", "draws", "gn_iters")}
+    stats["redetections_last_step"] = int((summ["flags"] & 1).sum())
+    stats["median_position_error"] = float(np.median(pos_err))
 
     # ---- Harris response kernel alone: live roofline ------------------------------------------
     resp_d = torch.empty((S, H, W), dtype=torch.float64, device=dev)
-    L = nat.lib()
+
     def harris_only(i):
         fr = pool_d[i % P]
         nat.check(L.vo_harris_response_dev(ctx.handle, fr.data_ptr(), S, H, W, pitch, H * pitch, 9,
@@ -374,11 +497,7 @@ def main():
     torch.cuda.synchronize()
     harris_ms = e0.elapsed_time(e1) / n_rf
     algo_bytes = S * H * W * (1 + 8)                 # uint8 pixel in, float64 score out
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = load_peaks()
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = algo_bytes / (harris_ms / 1e3) / 1e9
     traffic = None
@@ -390,80 +509,72 @@ def main():
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": algo_bytes, "launch_ms": harris_ms,
-                "note": "9 B/pixel (uint8 in, float64 score out) x S frames per launch"}
+                "note": "9 B/pixel (uint8 in, float64 score out) x S frames per launch; traffic from the committed ncu capture "
+                        "(profiles/harris_traffic.json, refreshed by tools/refresh_roofline.sh)"}
+    del resp_d
 
     # ---- one sequence alone (latency-bound): device-resident steps of a single 1241x376 stream -----
     single = None
-    if rank == 0 and not args.no_single_sequence:
-        fe1 = Frontend(1, H, W, num_keypoints=KP, n_corr=N, n_hyp=Hn, p3p_threshold=P3P_THR, n_tri=T, tri_mode=1, ctx=ctx)
-        def step_one(i):
-            fr = pool_d[i % P][0:1]
-            fe1.step_dev(fr.data_ptr(), pitch, H * pitch, devbuf["landmarks"].data_ptr(), devbuf["kp2d"].data_ptr(), K9,
-                         devbuf["samples"].data_ptr(), devbuf["table"].data_ptr(), init, devbuf["tri_p1"].data_ptr(),
-                         devbuf["tri_p2"].data_ptr(), devbuf["tri_proj1"].data_ptr(), devbuf["tri_proj2"].data_ptr(), stream)
-        for i in range(5):
-            step_one(i)
+    if rank == 0 and not args.no_single_sequence and not args.no_extras:
+        pl1 = new_pipeline(1)
+        for i in range(1, 6):
+            step_dev(pl1, i)
         torch.cuda.synchronize()
-        n1 = 50
+        n1 = 100
         e0.record(tstream)
         for i in range(n1):
-            step_one(5 + i)
+            step_dev(pl1, 6 + i)
         e1.record(tstream)
         torch.cuda.synchronize()
         ms1 = e0.elapsed_time(e1) / n1
         single = {"frames_per_s": 1e3 / ms1, "ms_per_frame": ms1, "note": "S = 1: one sequence, back-to-back device-resident steps"}
-        fe1.close()
+        pl1.close()
 
     # ---- end-to-end arm through the host-buffer C ABI ------------------------------------------
-    fe2 = Frontend(S, H, W, num_keypoints=KP, n_corr=N, n_hyp=Hn, p3p_threshold=P3P_THR, n_tri=T, tri_mode=1, ctx=ctx)
-    outs = {"kp_xy": np.empty((S, KP, 2), np.int32), "tracked": np.empty((S, KP, 2), np.float32),
-            "status": np.empty((S, KP), np.uint8), "err": np.empty((S, KP), np.float32),
-            "best4": np.empty((S, 4), np.int32), "inliers": np.empty((S, N), np.uint8),
-            "pose": np.empty((S, 12), np.float64), "tri_out": np.empty((S * T, 3), np.float64)}
-    # two result sets: the download of step t lands in one while step t+1 is being submitted with the other
-    outs2 = [{k: torch.from_numpy(v.copy()).pin_memory().numpy() for k, v in outs.items()} for _ in range(2)]
-    hb = {k: v.numpy() for k, v in hostbuf.items()}
+    pl2 = new_pipeline(S)
     pool_np = pool_pinned.numpy()
-
-    def prefetch(i):
-        fe2.prefetch_host(pool_np[i % P], hb["landmarks"], hb["kp2d"], hb["samples"], hb["table"], hb["tri_p1"],
-                          hb["tri_p2"], hb["tri_proj1"], hb["tri_proj2"])
+    outs = [torch.zeros((S, SUMMARY_DOUBLES), dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
 
     def submit(i):
-        # documented call order (include/vo_b200.h): the upload of step i+1 is queued, then step i (whose inputs were
-        # uploaded during step i-1) is submitted together with the download of its results.  Every step moves
-        # h2d + d2h bytes; with two steps in flight the GPU always has the next step queued.
-        prefetch(i + 1)
-        fe2.submit_host(None, None, None, K9, None, None, init, None, None, None, None, outs2[i & 1])
+        # documented call order (include/vo_b200.h): the upload of step i+1 is queued, then step i (whose frames were
+        # uploaded during step i-1) is submitted together with the download of its summary.  Every step moves h2d + d2h
+        # bytes; with two steps in flight the GPU always has the next step queued.
+        pl2.prefetch(pool_np[wd.time_index(i + 1)])
+        pl2.submit(None, outs[i & 1])
 
     def run_pipelined(first, n):
         for i in range(n):
             submit(first + i)
             if i > 0:
-                fe2.wait_host()           # results of step first + i - 1 are on the host
+                pl2.wait()                # the summary of step first + i - 1 is on the host
         if n > 0:
-            fe2.wait_host()               # drain: results of the last step are on the host
+            pl2.wait()
 
     e2e_steps = args.e2e_steps or args.steps
-    prefetch(0)
-    run_pipelined(0, warmup)
+    pl2.prefetch(pool_np[wd.time_index(1)])
+    run_pipelined(1, warmup)
     barrier()
     t0 = time.perf_counter()
-    run_pipelined(warmup, e2e_steps)
+    run_pipelined(1 + warmup, e2e_steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * S * e2e_steps / e2e_s
-    h2d = S * H * W + S * N * 40 + S * Hn * 16 + (N + 1) * 4 + S * T * 128 + S * 96
-    d2h = S * KP * 8 + S * KP * 13 + S * 16 + S * N + S * 96 + S * T * 24
+    h2d = S * H * W
+    d2h = S * SUMMARY_DOUBLES * 8
+    last = Pipeline.summary_dict(outs[(warmup + e2e_steps) & 1])
+    if not np.isfinite(last["pose"]).all():
+        raise SystemExit("bench.py: the end-to-end arm returned non-finite poses")
+    pl2.close()
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            fps, ms = cpu_pipeline_fps(cores, 2, 1, Hn, cores)
+            fps, ms, st = cpu_pipeline_fps(cores, 2, 1, cores)
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                   "sample": f"{cores} frames per step x 2 steps on {cores} host threads (oracle C port + "
-                             "cv2.calcOpticalFlowPyrLK + numpy SVD), same per-frame workload"}
+                   "sample": f"{cores} sequences x 2 timed steps (1 warm-up) on {cores} host processes: the loop oracle (C port of harris.py "
+                             "and of the P3P solver, cv2.calcOpticalFlowPyrLK, ransac.py's loop, scipy least_squares, numpy "
+                             f"bookkeeping / SVD), same per-frame workload; rows tracked {st[0]:.0f}, P3P population {st[1]:.0f}"}
         except Exception as ex:  # the oracle is a checker; its absence must not break the product bench
             cpu = {"value": None, "unit": "frames/s", "cores": cores, "kind": "port", "sample": f"unavailable: {ex}"}
 
@@ -472,18 +583,19 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic KITTI-shaped 1241x376 grayscale sequences, 1000 Harris keypoints, "
-                                   f"1000 KLT points (win 17, 3 levels), {Hn} P3P hypotheses x 1000 correspondences, "
-                                   "1000 triangulated points per frame",
-                       "sequences_per_gpu": S, "frames_per_step": world * S,
-                       "l2_policy": f"inputs larger than L2: {P} frame sets of {S} frames cycled "
+            "config": {"workload": workload_text(), "sequences_per_gpu": S, "frames_per_step": world * S,
+                       "l2_policy": f"inputs larger than L2: {P} time steps of {S} frames walked back and forth "
                                     f"({P * S * H * pitch / 1e6:.0f} MB) + {S * H * W * 8 / 1e6:.0f} MB score maps per step",
-                       "parallelism": f"{world} x independent sequence shards, no collective", "host_binding": numa},
+                       "parallelism": f"{world} x independent sequence shards, no collective", "host_binding": numa,
+                       "per_frame_means_last_step": stats},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "vo_frontend_prefetch_host + vo_frontend_submit_host + vo_frontend_wait_host (pinned host buffers in, results out on the host, every step; two steps in flight: the upload of step t+1 and the download of step t-1 overlap the compute of step t)"},
+                    "steps": e2e_steps, "h2d_gbs_per_gpu": h2d * e2e_steps / e2e_s / 1e9,
+                    "api": "vo_pipeline_prefetch_host + vo_pipeline_submit_host + vo_pipeline_wait_host: only the frames go up "
+                           "(pinned host buffers), poses + counters come back, every step; two steps in flight"},
             "gpu_launches": int(launches) * world,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "single_sequence": single,
         }))
+    pl.close()
     if world > 1:
         dist.destroy_process_group()
 

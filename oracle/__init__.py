@@ -275,14 +275,18 @@ class RansacP3P:
         k = np.ceil(np.log(1 - self.confidence) / np.log(1 - (1 - self.outlier_ratio) ** self.s))
         return int(k)
 
-    def find_best_model(self, landmarks, keypoints):
+    def find_best_model(self, landmarks, keypoints, draw_cap=None):
         L = np.asarray(landmarks, dtype=np.float64).reshape(-1, 3)
         P = np.asarray(keypoints, dtype=np.float64).reshape(-1, 2)
         N = L.shape[0]
         best_n, best_inl, best_model, n = -1, None, None, 0
+        drawn = 0
         while n < self.n_iterations:
+            if draw_cap is not None and drawn >= draw_cap:      # not in the reference (it would spin); see loop.py
+                break
             idxs = self.rng.choice(np.arange(N), replace=False, size=self.s)
             self.draws += 1
+            drawn += 1
             model = p3p_solve4(L[idxs], P[idxs], self.K)
             if model is None:
                 continue

@@ -149,7 +149,7 @@ class LoopOracle:
 
     def __init__(self, K, detector, *, p3p_opencv=False, refine="scipy", tri_opencv=True, inlier_threshold=1.25,
                  outlier_ratio=0.9, confidence=0.9999, max_iterations=10000, bearing_threshold=0.0075,
-                 error_threshold=100.0, redetect_fraction=0.8, klt=None, klt_params=None):
+                 error_threshold=100.0, redetect_fraction=0.8, klt=None, klt_params=None, eager_detector=False):
         self.K = np.asarray(K)                               # dtype kept: the reference's KITTI K is float32 (loader.py:94-96)
         self.Kinv = np.linalg.inv(self.K)                    # camera.py:92 (float32 inverse when K is float32)
         self.K64 = np.asarray(K, dtype=np.float64)
@@ -165,6 +165,10 @@ class LoopOracle:
         self.ransac = oracle.RansacP3P(self.K64, thr, outlier_ratio, confidence, max_iterations, inclusive=p3p_opencv)
         self.klt = klt or oracle.klt_track
         self.klt_params = klt_params or dict(win=17, max_level=2, max_iters=10, epsilon=0.03)   # klt.py:29-33
+        # eager_detector: run the detector on every new frame and keep its corners for the next step's re-detection
+        # (what the CUDA pipeline does; the result of a step is the same, klt.py:207-230 detects on that very frame)
+        self.eager_detector = eager_detector
+        self._cached_det = None
         self.curr_pose = np.eye(4)
         self.prev_pose = None
         self.num_features = None
@@ -204,7 +208,8 @@ class LoopOracle:
         n = len(self.kp)
         info["redetect"] = bool(n < self.num_features * self.redetect_fraction)
         if info["redetect"]:
-            fresh = np.asarray(self.detector(prev_gray), dtype=np.float32).reshape(-1, 2)
+            fresh = self._cached_det if self._cached_det is not None else self.detector(prev_gray)
+            fresh = np.asarray(fresh, dtype=np.float32).reshape(-1, 2)
             self.num_features = fresh.shape[0]                              # klt.py:114 (find_corners side effect)
             m = len(fresh)
             self.kp = np.concatenate([self.kp, fresh])
@@ -233,22 +238,34 @@ class LoopOracle:
         # main.py:254-262: P3P on the triangulated rows
         N = n2
         info["p3p_N"] = N
-        model, inl = self.ransac.find_best_model(land[:N], kp[:N].astype(np.float64))
+        # the reference raises when fewer than 4 landmarks are left (Generator.choice) and loops forever when no sample
+        # yields a model; the CUDA pipeline reports "no pose" and keeps the last one -- restated here for those cases
+        model, inl = (None, np.zeros(N, bool))
+        if N >= 4:
+            model, inl = self.ransac.find_best_model(land[:N], kp[:N].astype(np.float64),
+                                                     draw_cap=10 * min(self.ransac.max_iterations, 1 << 24) + 4096)
         info["ransac_n_iterations"] = self.ransac.n_iterations
         info["ransac_draws"] = self.ransac.draws
-        R, t = model
-        info["p3p_R"], info["p3p_t"] = np.array(R), np.array(t).reshape(3)
-        if self.refine == "scipy":
-            R, t = refine_scipy(R, t, land[:N][inl], kp[:N][inl], self.K)
-        elif self.refine == "gn":
-            R, t = refine_gn(R, t, land[:N][inl], kp[:N][inl], self.K)
-        info["inliers"] = inl.copy()
-        outliers = np.zeros(len(kp), bool)
-        outliers[:N] = ~inl                                                                  # main.py:264-265
-        # state.py:19-23, 39-51
+        info["no_pose"] = model is None
         self.prev_pose = self.curr_pose
-        Tcw = np.concatenate([np.concatenate([np.asarray(R), np.asarray(t).reshape(3, 1)], 1), [[0, 0, 0, 1]]], 0)
-        self.curr_pose = np.linalg.inv(Tcw)
+        if model is None:
+            inl = np.zeros(N, bool)
+            info["inliers"] = inl
+            outliers = np.zeros(len(kp), bool)
+            info["p3p_R"], info["p3p_t"] = np.linalg.inv(self.curr_pose)[:3, :3], np.linalg.inv(self.curr_pose)[:3, 3]
+        else:
+            R, t = model
+            info["p3p_R"], info["p3p_t"] = np.array(R), np.array(t).reshape(3)
+            if self.refine == "scipy":
+                R, t = refine_scipy(R, t, land[:N][inl], kp[:N][inl], self.K)
+            elif self.refine == "gn":
+                R, t = refine_gn(R, t, land[:N][inl], kp[:N][inl], self.K)
+            info["inliers"] = inl.copy()
+            outliers = np.zeros(len(kp), bool)
+            outliers[:N] = ~inl                                                              # main.py:264-265
+            # state.py:19-23, 39-51
+            Tcw = np.concatenate([np.concatenate([np.asarray(R), np.asarray(t).reshape(3, 1)], 1), [[0, 0, 0, 1]]], 0)
+            self.curr_pose = np.linalg.inv(Tcw)
         pose[state == 0] = self.curr_pose                                                    # features.py:228 (no such rows here)
 
         def reset(mask):                                                                     # state.py:167-178
@@ -257,7 +274,7 @@ class LoopOracle:
             pose[mask] = self.curr_pose
         reset(outliers)
         # state.py:139-165 + 180-229
-        sel = state == 1
+        sel = (state == 1) & (model is not None)
         ends = np.concatenate([kp[sel].astype(np.float64), np.ones((int(sel.sum()), 1))], 1)
         starts = np.concatenate([track[sel], np.ones((int(sel.sum()), 1))], 1)
         d1 = np.einsum("nij,nj->ni", pose[sel][:, :3, :3], starts @ self.Kinv.T)
@@ -284,6 +301,7 @@ class LoopOracle:
             reset(behind)
             info["n_behind"] = int(behind.sum())
         self.kp, self.land, self.state, self.track, self.pose, self.cand = kp, land, state, track, pose, cand
+        self._cached_det = self.detector(new_gray) if self.eager_detector else None
         info["n"] = len(kp)
         info["n_tri"] = int((state == 2).sum())
         return info
