@@ -100,6 +100,19 @@ int vo_klt_track_host(vo_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next,
                       int max_level, int win, int max_iters, double epsilon, double min_eig_threshold,
                       const float* h_prev_pts, int n_pts, float* h_next_pts, uint8_t* h_status, float* h_err);
 
+/* The same with BGR frames (uint8 [n_frames][H][W][3], as cv2.imread returns them): the conversion klt.py:57-62 does
+ * with cv2.cvtColor(BGR2GRAY) runs on the device (OpenCV's 15-bit fixed point, bit-exact) straight into the pyramid.
+ * Both host entry points keep the pyramid of the last `next` batch and reuse it when the following call's `prev` has
+ * the same content (a tracker fed consecutive frame pairs uploads every frame once); vo_klt_cache_hits counts reuses. */
+int vo_klt_track_bgr_host(vo_ctx* ctx, const uint8_t* h_prev_bgr, const uint8_t* h_next_bgr, int n_frames, int H, int W,
+                          int max_level, int win, int max_iters, double epsilon, double min_eig_threshold,
+                          const float* h_prev_pts, int n_pts, float* h_next_pts, uint8_t* h_status, float* h_err);
+unsigned long long vo_klt_cache_hits(const vo_ctx* ctx);
+/* klt.py:57-62, 84-85  cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) for uint8 images, bit-exact.                          */
+int vo_bgr2gray_dev(vo_ctx* ctx, const uint8_t* d_bgr, int n_frames, int H, int W, size_t in_pitch, size_t in_frame_stride,
+                    uint8_t* d_gray, size_t out_pitch, size_t out_frame_stride, void* stream);
+int vo_bgr2gray_host(vo_ctx* ctx, const uint8_t* h_bgr, int n_frames, int H, int W, uint8_t* h_gray);
+
 /* ---- P3P + RANSAC: src/vo/pose_estimation/p3p.py:51-108, src/vo/algorithms/ransac.py:69-129 --- */
 /* For every hypothesis h (4 sample indices: 3 for P3P, the 4th disambiguates, as cv2.solvePnP with
  * SOLVEPNP_P3P does) solve the pose, count reprojection inliers (squared pixel error < threshold,
@@ -129,6 +142,17 @@ int vo_p3p_ransac_host(vo_ctx* ctx, const double* h_landmarks, const double* h_k
                        const int32_t* h_iters_for_count, int initial_iters, int start_n, int start_best,
                        int32_t* h_best4, int32_t* h_consumed, int32_t* h_iters_out, uint8_t* h_inliers,
                        double* h_best_model, int32_t* h_counts, uint8_t* h_valid, double* h_models);
+
+/* p3p.py:188-213  _nonlinear_refinement for n_frames independent problems: minimise the sum of squared reprojection
+ * distances of the correspondences with mask != 0 (NULL = all) over the 6-dof pose, starting from pose_in (R row-major |
+ * t, world -> camera).  The reference runs scipy.optimize.least_squares over the twist with a numeric Jacobian and stops
+ * on ftol = 1e-8; this is a damped Gauss-Newton on SE(3) with the analytic Jacobian run to a 1e-11 step: same cost, its
+ * minimum (never a higher cost than the reference's result; see DESIGN.md for the measured distance).  One CTA per
+ * problem, block-wide reductions; iters (optional) = steps tried.                                                    */
+int vo_refine_pose_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, const uint8_t* d_mask, int n_frames, int N,
+                       const double* K9, const double* d_pose_in, double* d_pose_out, int32_t* d_iters, void* stream);
+int vo_refine_pose_host(vo_ctx* ctx, const double* h_landmarks, const double* h_keypoints, const uint8_t* h_mask, int n_frames, int N,
+                        const double* K9, const double* h_pose_in, double* h_pose_out, int32_t* h_iters);
 
 /* ---- Triangulation: src/vo/landmarks/triangulation.py:352-389, 38-86 -------------------------- */
 /* Linear (DLT) triangulation, one point per thread, one-sided Jacobi SVD in registers.

@@ -118,3 +118,43 @@ def test_pyramid_levels_vs_oracle(ctx, shape):
             got = pyr[f, lo[l]:lo[l] + lh[l] * lp[l]].reshape(lh[l], lp[l])[:, :lw[l]]
             assert ref.shape == (lh[l], lw[l])
             assert np.array_equal(got, ref), (shape, f, l)
+
+
+def test_bgr2gray_bitexact_vs_cv2(ctx):
+    """klt.py:57-62 converts with cv2.cvtColor(BGR2GRAY); the device kernel must reproduce OpenCV's fixed point on
+    every colour (a 4096x4096 image holding all 2^24 of them) and on ragged widths."""
+    import cv2
+    from vo import _ops
+    b, g, r = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    img = np.ascontiguousarray(np.stack([b, g, r], -1).reshape(4096, 4096, 3))
+    assert np.array_equal(_ops.bgr2gray(img, ctx=ctx), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    rng = np.random.default_rng(0)
+    for shape in [(3, 37, 53, 3), (1, 5, 1, 3), (2, 64, 1241, 3)]:
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        want = np.stack([cv2.cvtColor(x, cv2.COLOR_BGR2GRAY) for x in a])
+        assert np.array_equal(_ops.bgr2gray(a, ctx=ctx), want)
+
+
+def test_bgr_input_and_pyramid_cache(ctx, golden):
+    """BGR frames through vo_klt_track_bgr_host equal the gray path, and a second call whose `prev` is the last call's
+    `next` reuses the resident pyramid (same results)."""
+    from vo import _native as nat, _ops
+    g = golden("klt")
+    c0, c1 = g["prev"], g["next"]
+    rng = np.random.default_rng(1)
+    b0 = np.stack([c0, c0, c0], -1)
+    b1 = np.stack([c1, c1, c1], -1)
+    b2 = np.roll(b1, 2, axis=1)
+    pts = g["pts"]
+    want = _ops.klt_track(c0, c1, pts, ctx=ctx)
+    got = _ops.klt_track(b0, b1, pts, ctx=ctx)
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b)
+    h0 = nat.lib().vo_klt_cache_hits(ctx.handle)
+    a2 = _ops.klt_track(b1, b2, got[0], ctx=ctx)          # prev == last next: cache hit
+    assert nat.lib().vo_klt_cache_hits(ctx.handle) == h0 + 1
+    _ops.klt_track(b0, b1, pts, ctx=ctx)                  # miss (prev differs)
+    assert nat.lib().vo_klt_cache_hits(ctx.handle) == h0 + 1
+    a3 = _ops.klt_track(np.ascontiguousarray(b1[..., 0]), np.ascontiguousarray(b2[..., 0]), got[0], ctx=ctx)   # gray, no cache
+    for a, b in zip(a2, a3):
+        assert np.array_equal(a, b)

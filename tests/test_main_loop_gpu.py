@@ -1,0 +1,139 @@
+"""GPU: the reference's src/main.py:185-287 (bootstrap + loop body, without the plotting) run through THIS repo's
+drop-in `vo` package on the six KITTI frames the reference ships, against the tables the reference's own classes
+produced for the same script (tests/golden/loop.npz, made by tests/golden/make_golden.py::make_loop).
+
+This is the "src/main.py drops in unchanged" claim of the north star as a test: the script below is main.py's code,
+line for line, importing `vo` from visual-odometry-project_b200/."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def run_main(p3p_opencv, refine=True, mode="klt"):
+    import cv2
+    from vo.features import Tracker
+    from vo.landmarks import LandmarksTriangulator
+    from vo.pose_estimation import P3PPoseEstimator
+    from vo.primitives import Features, Frame, State
+    from vo.sensors import Camera
+
+    g = np.load(os.path.join(GOLDEN, "loop.npz"))
+    K = g["K"]                                        # float32, as loader.py:86-96 reads calib.txt
+    camera = Camera(intrinsic_matrix=K)
+    frames = []
+    for i in range(6):
+        f = Frame(cv2.imread(os.path.join(GOLDEN, "kitti05", f"{i:06d}.png")), sensor=camera, intrinsics=K)
+        f.frame_id = i
+        frames.append(f)
+    np.random.seed(0)
+    # ---- main.py:185-201
+    triangulator = LandmarksTriangulator(camera1=camera, camera2=camera, use_ransac=True, use_opencv=True,
+                                         outlier_ratio=0.9, ransac_threshold=0.25, ransac_confidence=0.999)
+    pose_estimator = P3PPoseEstimator(use_opencv=p3p_opencv, intrinsic_matrix=camera.intrinsic_matrix, inlier_threshold=1.25,
+                                      outlier_ratio=0.9, confidence=0.9999, nonlinear_refinement=refine)
+    # ---- main.py:203-231 (bootstrap)
+    sequence = iter(frames)
+    init_frame = next(sequence)
+    state = State(init_frame)
+    next(sequence)  # skip frame 1
+    new_frame = next(sequence)
+    tracker = Tracker(init_frame, mode=mode)
+    matches = tracker.trackFeatures(state.curr_frame, new_frame)
+    state.update_from_matches(matches)
+    M, landmarks, inliers = triangulator.triangulate_matches(matches)
+    outliers = np.zeros(shape=(matches.frame2.features.length,), dtype=bool)
+    outliers[matches.frame2.features.match_inliers] = ~inliers
+    state.update_with_local_pose(M)
+    inliers_mask = np.zeros_like(matches.frame2.features.matched_candidate_inliers).astype(bool)
+    inliers_mask[matches.frame2.features.matched_candidate_inliers] = inliers
+    state.update_with_local_landmarks(landmarks[inliers], inliers_mask)
+    state.reset_outliers(outliers)
+    out = {"boot": _table(state)}
+    # ---- main.py:248-287 (loop body)
+    for new_frame in sequence:
+        matches = tracker.trackFeatures(state.curr_frame, new_frame)
+        (rmatrix, tvec), inliers = pose_estimator.estimate_pose(
+            Features(keypoints=matches.frame2.features.triangulated_inliers_keypoints,
+                     landmarks=matches.frame2.features.triangulated_inliers_landmarks))
+        outliers = np.zeros(shape=(matches.frame2.features.length,), dtype=bool)
+        outliers[matches.frame2.features.triangulate_inliers] = ~inliers
+        state.update_from_matches(matches)
+        state.update_with_world_pose(np.concatenate((rmatrix, tvec), axis=1))
+        state.reset_outliers(outliers)
+        state.compute_candidates()
+        assert np.sum(state.curr_frame.features.candidate_mask) <= np.sum(state.curr_frame.features.matched_candidate_inliers)
+        n_candidates = np.sum(state.curr_frame.features.candidate_mask)
+        if n_candidates > 0:
+            landmarks_world = triangulator.triangulate_candidates(state.curr_frame.features, current_pose=state.get_pose())
+            state.update_with_world_landmarks(landmarks_world, matches.frame2.features.candidate_mask)
+        t = _table(state)
+        t["inliers"] = np.asarray(inliers).copy()
+        out[new_frame.frame_id] = t
+    return g, out
+
+
+def _table(state):
+    f = state.curr_frame.features
+    return dict(kp=f.keypoints.reshape(-1, 2).copy(), land=f.landmarks.reshape(-1, 3).copy(), state=f.state.astype(int),
+                track=f.tracks.reshape(-1, 2).copy(), pose=f.poses.copy(), cand=f.candidate_mask.copy(),
+                curr_pose=state.get_pose().copy())
+
+
+def test_main_py_klt_mode_p3p_reference_ransac():
+    """use_opencv=False for P3P (the reproducible path: numpy rng 2023): the bootstrap table and every discrete result of
+    the first loop frame are the reference's; poses within the refinement tolerance (see test_pipeline_gpu.py)."""
+    from vo import _native as nat
+    hits0 = nat.lib().vo_klt_cache_hits(nat.default_context(0).handle)
+    g, out = run_main(False)
+    b = out["boot"]
+    assert np.array_equal(b["kp"], g["boot_kp"]) or np.abs(b["kp"] - g["boot_kp"]).max() < 1e-2       # tracker: 1e-2 px
+    assert np.array_equal(b["state"], g["boot_state"])
+    assert np.allclose(b["curr_pose"], g["boot_curr_pose"], atol=1e-6)
+    # two-view landmarks from a 1-unit baseline: a 1e-3 px difference of the tracker moves a point at depth 45 by 1e-5
+    assert np.array_equal(np.isnan(b["land"]), np.isnan(g["boot_land"]))
+    rel = np.abs(b["land"] - g["boot_land"]) / (1 + np.abs(g["boot_land"]))
+    assert np.nanmedian(rel) < 1e-5 and np.nanmax(rel) < 1e-2
+    f3 = out[3]
+    assert np.array_equal(f3["inliers"], g["f3_inliers"])
+    assert np.array_equal(f3["state"], g["f3_state"]) and np.array_equal(f3["cand"], g["f3_cand"])
+    for i in (3, 4, 5):
+        t = out[i]
+        assert len(t["kp"]) == len(g[f"f{i}_kp"])
+        ref = g[f"f{i}_curr_pose"]
+        tol_R, tol_t = (2e-4, 5e-3) if i == 3 else (6e-4, 1.5e-2)
+        assert np.abs(t["curr_pose"][:3, :3] - ref[:3, :3]).max() < tol_R and np.abs(t["curr_pose"][:3, 3] - ref[:3, 3]).max() < tol_t, i
+    # every frame was uploaded and pyramided once: frames 3, 4 and 5 found the previous call's pyramid
+    assert nat.lib().vo_klt_cache_hits(nat.default_context(0).handle) - hits0 >= 3
+
+
+def test_main_py_default_path_tolerance_pin():
+    """main.py's own configuration (use_opencv=True: the reference calls cv2.solvePnPRansac, whose sample stream is
+    OpenCV's).  Here the same model class and inlier rule run over the numpy sample stream, so the result is pinned by
+    tolerance: refined pose within 5e-3 / 2e-4 of the reference's on the first loop frame, inlier masks with a Jaccard
+    index >= 0.97 (two good minimal models of different samples disagree on the points near the 1.25 px threshold:
+    324 of 331 agree here), the same number of candidates within 10 %."""
+    g, out = run_main(True)
+    t = out[3]
+    ref = g["cv_f3_curr_pose"]
+    assert np.abs(t["curr_pose"][:3, :3] - ref[:3, :3]).max() < 2e-4 and np.abs(t["curr_pose"][:3, 3] - ref[:3, 3]).max() < 5e-3
+    a, b = t["inliers"], g["cv_f3_inliers"]
+    assert len(a) == len(b)
+    assert (a & b).sum() / (a | b).sum() >= 0.97
+    assert abs(int(t["cand"].sum()) - int(g["cv_f3_n_candidates"])) <= 0.1 * int(g["cv_f3_n_candidates"]) + 2
+    for i in (4, 5):
+        ref = g[f"cv_f{i}_curr_pose"]
+        assert np.abs(out[i]["curr_pose"][:3, :3] - ref[:3, :3]).max() < 6e-4 and np.abs(out[i]["curr_pose"][:3, 3] - ref[:3, 3]).max() < 1.5e-2
+
+
+def test_main_py_harris_mode_runs():
+    """TRACKER_MODE = "harris" (main.py:44): detector + descriptors + matcher every frame.  The per-stage results are
+    pinned elsewhere (test_harris_gpu.py); here the script must run through the package and keep a sane trajectory."""
+    g, out = run_main(False, mode="harris")
+    for i in (3, 4, 5):
+        p = out[i]["curr_pose"]
+        assert np.isfinite(p).all() and 0.2 * (i - 1) < p[2, 3] < 0.8 * (i - 1)      # about half a unit forward per frame

@@ -141,3 +141,31 @@ def test_full_size_sweep_3000x65536(ctx):
     # the inclusive rule of the OpenCV mode never counts fewer
     r2 = _ops.p3p_ransac(L, uv, K, S[:2048], 1.25, table, 10 ** 7, want_all=True, inclusive=True, ctx=ctx)
     assert (r2["counts"] >= r["counts"][:2048]).all()
+
+
+def test_refine_pose_matches_restatement_and_beats_reference_cost(ctx, golden):
+    """vo_refine_pose_host (p3p.py:188-213 on the device) against its numpy restatement (oracle.loop.refine_gn) and
+    against the reference's own refined pose on its frame-3 problem: same minimum (1e-9), never a higher cost than
+    where scipy stopped."""
+    from oracle.loop import _cost, refine_gn
+    from vo import _ops
+    g = golden("loop")
+    inl = g["f3_inliers"]
+    N = len(inl)
+    kp, land = g["f3_kp"][:N][inl], g["f3_land"][:N][inl]
+    ok = ~np.isnan(land).any(1)
+    kp, land = kp[ok].astype(np.float64), land[ok]
+    K = g["K"].astype(np.float64)
+    f = (K[0, 0], K[1, 1], K[0, 2], K[1, 2])
+    R0, t0 = g["noref_f3_R"], g["noref_f3_t"]
+    R, t, iters = _ops.refine_pose(land, kp, K, R0, t0, ctx=ctx)
+    Rg, tg = refine_gn(R0, t0, land, kp, K)
+    assert np.abs(R - Rg).max() < 1e-9 and np.abs(t - tg).max() < 1e-8 and 1 <= iters <= 30
+    assert _cost(R, t.ravel(), land, kp, *f) <= _cost(g["f3_R"], g["f3_t"], land, kp, *f)
+    assert np.abs(R - g["f3_R"]).max() < 2e-4 and np.abs(t.ravel() - g["f3_t"]).max() < 5e-3
+    # a mask restricts the problem: refining on the first half equals refining the first half alone
+    m = np.zeros(len(land), np.uint8)
+    m[: len(land) // 2] = 1
+    Ra, ta, _ = _ops.refine_pose(land, kp, K, R0, t0, mask=m, ctx=ctx)
+    Rb, tb, _ = _ops.refine_pose(land[: len(land) // 2], kp[: len(land) // 2], K, R0, t0, ctx=ctx)
+    assert np.abs(Ra - Rb).max() < 1e-10 and np.abs(ta - tb).max() < 1e-9

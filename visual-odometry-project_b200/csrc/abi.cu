@@ -268,10 +268,43 @@ int vo_klt_track_dev(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d_py
                                pick_stream(ctx, stream));
 }
 
-int vo_klt_track_host(vo_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next, int n_frames, int H, int W,
-                      int max_level, int win, int max_iters, double epsilon, double min_eig_threshold,
-                      const float* h_prev_pts, int n_pts, float* h_next_pts, uint8_t* h_status, float* h_err) {
+// 64-bit content hash of a host image batch (identifies "the same frame as last call's next")
+static unsigned long long host_hash(const uint8_t* p, size_t n) {
+    unsigned long long h0 = 0x9E3779B97F4A7C15ull, h1 = 0xC2B2AE3D27D4EB4Full, h2 = 0x165667B19E3779F9ull, h3 = 0x27D4EB2F165667C5ull;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        unsigned long long w[4];
+        memcpy(w, p + i, 32);
+        h0 = (h0 ^ w[0]) * 0x100000001B3ull; h1 = (h1 ^ w[1]) * 0x100000001B3ull;
+        h2 = (h2 ^ w[2]) * 0x100000001B3ull; h3 = (h3 ^ w[3]) * 0x100000001B3ull;
+        h0 ^= h0 >> 29; h1 ^= h1 >> 31; h2 ^= h2 >> 27; h3 ^= h3 >> 33;
+    }
+    for (; i < n; i++) h0 = (h0 ^ p[i]) * 0x100000001B3ull;
+    return (h0 ^ (h1 << 1) ^ (h2 << 2) ^ (h3 << 3)) + n;
+}
+
+// upload one image batch (1 or 3 channels, tightly packed) into the level-0 slots of pyramid `dst` and build the levels
+static int klt_stage_pyramid(vo_ctx* ctx, const uint8_t* h_img, int channels, int n_frames, int H, int W, int max_level, int win,
+                             size_t pitch0, size_t fb, uint8_t* dst, cudaStream_t s) {
+    int rc;
+    if (channels == 1) {
+        for (int f = 0; f < n_frames; f++)
+            VO_CUDA(cudaMemcpy2DAsync(dst + f * fb, pitch0, h_img + (size_t)f * H * W, W, W, H, cudaMemcpyHostToDevice, s));
+    } else {
+        const size_t bytes = (size_t)n_frames * H * W * 3;
+        if ((rc = vo_buf_reserve(&ctx->scratch[14], bytes + 16))) return rc;
+        VO_CUDA(cudaMemcpyAsync(ctx->scratch[14].p, h_img, bytes, cudaMemcpyHostToDevice, s));
+        if ((rc = vo_launch_bgr2gray(ctx, (const uint8_t*)ctx->scratch[14].p, n_frames, H, W, (size_t)W * 3, (size_t)H * W * 3, dst,
+                                     pitch0, fb, s))) return rc;
+    }
+    return vo_launch_klt_pyramid(ctx, dst, n_frames, H, W, pitch0, fb, max_level, win, dst, s);
+}
+
+static int klt_track_host_impl(vo_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next, int channels, int n_frames, int H, int W,
+                               int max_level, int win, int max_iters, double epsilon, double min_eig_threshold,
+                               const float* h_prev_pts, int n_pts, float* h_next_pts, uint8_t* h_status, float* h_err) {
     VO_REQUIRE(ctx && h_prev && h_next, "vo_klt_track_host: null argument");
+    VO_REQUIRE(channels == 1 || channels == 3, "vo_klt_track_host: 1 (gray) or 3 (BGR) channels");
     VO_REQUIRE(n_pts == 0 || (h_prev_pts && h_next_pts && h_status && h_err), "vo_klt_track_host: null argument");
     VO_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
@@ -281,28 +314,75 @@ int vo_klt_track_host(vo_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next,
     if (rc) return rc;
     if (n_pts == 0) return VO_OK;
     const size_t pts_b = (size_t)n_frames * n_pts * 2 * sizeof(float);
+    const size_t img_bytes = (size_t)n_frames * H * W * channels;
+    auto& kc = ctx->klt_cache;
+    const bool same_shape = kc.valid && kc.H == H && kc.W == W && kc.channels == channels && kc.n_frames == n_frames &&
+                            kc.max_level == max_level && kc.win == win && kc.bytes == img_bytes;
+    const unsigned long long hp = host_hash(h_prev, img_bytes), hn = host_hash(h_next, img_bytes);
+    const bool need_a = fb * n_frames > ctx->scratch[5].cap, need_b = fb * n_frames > ctx->scratch[6].cap;
     if ((rc = vo_buf_reserve(&ctx->scratch[5], fb * n_frames))) return rc;
     if ((rc = vo_buf_reserve(&ctx->scratch[6], fb * n_frames))) return rc;
     if ((rc = vo_buf_reserve(&ctx->scratch[7], 2 * pts_b + (size_t)n_frames * n_pts * 8 + 1024))) return rc;
-    uint8_t* pa = (uint8_t*)ctx->scratch[5].p;
-    uint8_t* pb = (uint8_t*)ctx->scratch[6].p;
+    const bool hit = same_shape && !need_a && !need_b && kc.hash == hp;
+    const int prev_buf = hit ? kc.which : 0;
+    uint8_t* pa = (uint8_t*)ctx->scratch[5 + prev_buf].p;
+    uint8_t* pb = (uint8_t*)ctx->scratch[5 + (1 - prev_buf)].p;
     float* d_prev = (float*)ctx->scratch[7].p;
     float* d_next = d_prev + (size_t)n_frames * n_pts * 2;
     float* d_err = d_next + (size_t)n_frames * n_pts * 2;
     uint8_t* d_st = (uint8_t*)(d_err + (size_t)n_frames * n_pts);
-    // frames go straight into the level-0 slots of the pyramids
-    for (int f = 0; f < n_frames; f++) {
-        VO_CUDA(cudaMemcpy2DAsync(pa + f * fb, lp[0], h_prev + (size_t)f * H * W, W, W, H, cudaMemcpyHostToDevice, s));
-        VO_CUDA(cudaMemcpy2DAsync(pb + f * fb, lp[0], h_next + (size_t)f * H * W, W, W, H, cudaMemcpyHostToDevice, s));
-    }
+    kc.valid = false;
+    if (hit) kc.hits++;
+    else if ((rc = klt_stage_pyramid(ctx, h_prev, channels, n_frames, H, W, max_level, win, lp[0], fb, pa, s))) return rc;
+    if ((rc = klt_stage_pyramid(ctx, h_next, channels, n_frames, H, W, max_level, win, lp[0], fb, pb, s))) return rc;
     VO_CUDA(cudaMemcpyAsync(d_prev, h_prev_pts, pts_b, cudaMemcpyHostToDevice, s));
-    if ((rc = vo_launch_klt_pyramid(ctx, pa, n_frames, H, W, lp[0], fb, max_level, win, pa, s))) return rc;
-    if ((rc = vo_launch_klt_pyramid(ctx, pb, n_frames, H, W, lp[0], fb, max_level, win, pb, s))) return rc;
     if ((rc = vo_launch_klt_track(ctx, pa, pb, n_frames, H, W, max_level, win, max_iters, epsilon, min_eig_threshold,
                                   d_prev, n_pts, d_next, d_st, d_err, s))) return rc;
     VO_CUDA(cudaMemcpyAsync(h_next_pts, d_next, pts_b, cudaMemcpyDeviceToHost, s));
     VO_CUDA(cudaMemcpyAsync(h_err, d_err, (size_t)n_frames * n_pts * sizeof(float), cudaMemcpyDeviceToHost, s));
     VO_CUDA(cudaMemcpyAsync(h_status, d_st, (size_t)n_frames * n_pts, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
+    kc.hash = hn; kc.bytes = img_bytes; kc.H = H; kc.W = W; kc.channels = channels; kc.n_frames = n_frames;
+    kc.max_level = max_level; kc.win = win; kc.which = 1 - prev_buf; kc.valid = true;
+    return VO_OK;
+}
+
+int vo_klt_track_host(vo_ctx* ctx, const uint8_t* h_prev, const uint8_t* h_next, int n_frames, int H, int W,
+                      int max_level, int win, int max_iters, double epsilon, double min_eig_threshold,
+                      const float* h_prev_pts, int n_pts, float* h_next_pts, uint8_t* h_status, float* h_err) {
+    return klt_track_host_impl(ctx, h_prev, h_next, 1, n_frames, H, W, max_level, win, max_iters, epsilon, min_eig_threshold,
+                               h_prev_pts, n_pts, h_next_pts, h_status, h_err);
+}
+
+int vo_klt_track_bgr_host(vo_ctx* ctx, const uint8_t* h_prev_bgr, const uint8_t* h_next_bgr, int n_frames, int H, int W,
+                          int max_level, int win, int max_iters, double epsilon, double min_eig_threshold,
+                          const float* h_prev_pts, int n_pts, float* h_next_pts, uint8_t* h_status, float* h_err) {
+    return klt_track_host_impl(ctx, h_prev_bgr, h_next_bgr, 3, n_frames, H, W, max_level, win, max_iters, epsilon, min_eig_threshold,
+                               h_prev_pts, n_pts, h_next_pts, h_status, h_err);
+}
+
+unsigned long long vo_klt_cache_hits(const vo_ctx* ctx) { return ctx ? ctx->klt_cache.hits : 0ull; }
+
+int vo_bgr2gray_dev(vo_ctx* ctx, const uint8_t* d_bgr, int n_frames, int H, int W, size_t in_pitch, size_t in_frame_stride,
+                    uint8_t* d_gray, size_t out_pitch, size_t out_frame_stride, void* stream) {
+    VO_REQUIRE(ctx && d_bgr && d_gray, "vo_bgr2gray_dev: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_launch_bgr2gray(ctx, d_bgr, n_frames, H, W, in_pitch, in_frame_stride, d_gray, out_pitch, out_frame_stride,
+                              pick_stream(ctx, stream));
+}
+
+int vo_bgr2gray_host(vo_ctx* ctx, const uint8_t* h_bgr, int n_frames, int H, int W, uint8_t* h_gray) {
+    VO_REQUIRE(ctx && h_bgr && h_gray && n_frames >= 1 && H >= 1 && W >= 1, "vo_bgr2gray_host: bad argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t pitch = ((size_t)W + 15) & ~(size_t)15, in_b = (size_t)n_frames * H * W * 3;
+    int rc;
+    if ((rc = vo_buf_reserve(&ctx->scratch[14], in_b + 16))) return rc;
+    if ((rc = vo_buf_reserve(&ctx->scratch[15], pitch * H * n_frames))) return rc;
+    VO_CUDA(cudaMemcpyAsync(ctx->scratch[14].p, h_bgr, in_b, cudaMemcpyHostToDevice, s));
+    if ((rc = vo_launch_bgr2gray(ctx, (const uint8_t*)ctx->scratch[14].p, n_frames, H, W, (size_t)W * 3, (size_t)H * W * 3,
+                                 (uint8_t*)ctx->scratch[15].p, pitch, pitch * H, s))) return rc;
+    VO_CUDA(cudaMemcpy2DAsync(h_gray, W, ctx->scratch[15].p, pitch, W, (size_t)H * n_frames, cudaMemcpyDeviceToHost, s));
     VO_CUDA(cudaStreamSynchronize(s));
     return VO_OK;
 }

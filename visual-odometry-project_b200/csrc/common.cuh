@@ -53,6 +53,10 @@ struct vo_ctx {
     bool env_klt_generic = false;     // VO_KLT_GENERIC=1: runtime-window tracker for every window size
     bool env_frontend_serial = false; // VO_FRONTEND_SERIAL=1: no fork/join across streams
     int nms_band = 0;                 // VO_NMS_BAND (0 = built-in default)
+    // vo_klt_track_*_host keeps the pyramid of the last `next` image: a tracker that is called with consecutive frame
+    // pairs (klt.py:233-239) uploads and pyramids every frame once, not twice.
+    struct { unsigned long long hash = 0; size_t bytes = 0; int H = 0, W = 0, channels = 0, n_frames = 0, max_level = 0, win = 0;
+             int which = 0; bool valid = false; unsigned long long hits = 0; } klt_cache;
 };
 
 // A context is bound to ONE device and its launchers carve working memory from ctx-owned scratch: calls that

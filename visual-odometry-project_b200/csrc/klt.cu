@@ -109,6 +109,37 @@ copy_level0_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch,
     }
 }
 
+// cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) for 8-bit images (klt.py:57-62, 84-85): OpenCV's 15-bit fixed point,
+// gray = (B * 3735 + G * 19235 + R * 9798 + 2^14) >> 15 (checked against cv2 on all 2^24 colours).  A thread converts
+// four pixels: 12 interleaved bytes in, one 32-bit word out (destination rows are 16-byte aligned).
+__global__ void __launch_bounds__(256)
+bgr2gray_kernel(const uint8_t* __restrict__ src, int H, int W, size_t spitch, size_t sframe, uint8_t* __restrict__ dst,
+                size_t dpitch, size_t dframe) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x >= W) return;
+    const uint8_t* s = src + (size_t)blockIdx.z * sframe + (size_t)y * spitch + (size_t)x * 3;
+    uint8_t* d = dst + (size_t)blockIdx.z * dframe + (size_t)y * dpitch + x;
+    const int n = min(4, W - x);
+    uint8_t px[12];
+    if (n == 4 && (reinterpret_cast<uintptr_t>(s) & 3) == 0) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(s);
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { px[k] = (w0 >> (8 * k)) & 255; px[4 + k] = (w1 >> (8 * k)) & 255; px[8 + k] = (w2 >> (8 * k)) & 255; }
+    } else {
+        for (int k = 0; k < 3 * n; k++) px[k] = s[k];
+    }
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t g = (px[3 * k] * 3735u + px[3 * k + 1] * 19235u + px[3 * k + 2] * 9798u + (1u << 14)) >> 15;
+        out |= (k < n ? g : 0u) << (8 * k);
+    }
+    if (n == 4) *reinterpret_cast<uint32_t*>(d) = out;
+    else for (int k = 0; k < n; k++) d[k] = (out >> (8 * k)) & 255;
+}
+
 struct PyrLayout {
     int n_levels;
     int h[KLT_MAX_LEVELS], w[KLT_MAX_LEVELS];
@@ -928,6 +959,17 @@ int vo_launch_klt_pyramid(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H
         ctx->launches++;
         VO_CHECK_LAUNCH();
     }
+    return VO_OK;
+}
+
+int vo_launch_bgr2gray(vo_ctx* ctx, const uint8_t* d_bgr, int n_frames, int H, int W, size_t in_pitch, size_t in_frame_stride,
+                       uint8_t* d_gray, size_t out_pitch, size_t out_frame_stride, cudaStream_t stream) {
+    VO_REQUIRE(n_frames >= 1 && H >= 1 && W >= 1 && in_pitch >= (size_t)3 * W && out_pitch >= (size_t)W, "bgr2gray: bad shape / pitch");
+    VO_REQUIRE(out_pitch % 4 == 0 && ((uintptr_t)d_gray % 4) == 0 && out_frame_stride % 4 == 0, "bgr2gray: destination rows must be 4-byte aligned");
+    dim3 g(vo_div_up(vo_div_up(W, 4), 256), H, n_frames);
+    bgr2gray_kernel<<<g, 256, 0, stream>>>(d_bgr, H, W, in_pitch, in_frame_stride, d_gray, out_pitch, out_frame_stride);
+    ctx->launches++;
+    VO_CHECK_LAUNCH();
     return VO_OK;
 }
 

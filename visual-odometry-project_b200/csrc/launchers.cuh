@@ -23,6 +23,8 @@ int vo_launch_klt_track(vo_ctx* ctx, const uint8_t* d_pyr_prev, const uint8_t* d
                         int max_level, int win, int max_iters, double epsilon, double min_eig,
                         const float* d_prev_pts, int n_pts, float* d_next_pts, uint8_t* d_status, float* d_err,
                         cudaStream_t stream, const int* d_n_valid = nullptr);
+int vo_launch_bgr2gray(vo_ctx* ctx, const uint8_t* d_bgr, int n_frames, int H, int W, size_t in_pitch, size_t in_frame_stride,
+                       uint8_t* d_gray, size_t out_pitch, size_t out_frame_stride, cudaStream_t stream);
 // p3p.cu
 int vo_launch_p3p_score(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames, int N,
                         const double* K9, const int* d_sample_idx, int n_hyp, double threshold, int inclusive, double* d_models,

@@ -308,6 +308,110 @@ __device__ bool solve6(double (*A)[7]) {
     return true;
 }
 
+// Damped Gauss-Newton on SE(3) over the flagged points' 2N reprojection residuals (same minimum as p3p.py:188-213's
+// least_squares over per-point distances; the tests hold a numpy restatement of exactly these steps).  Called by all
+// PO_THREADS threads of a CTA; s_pose holds the start (R row-major | t) and receives the result.  Returns the number of
+// steps tried.
+struct GnShared { double red[(PO_WARPS + 1) * 28]; double tr[12]; double delta[6]; int ok; };
+__device__ int gn_refine(const double* sX, const double* sY, const double* sZ, const double* sU, const double* sV,
+                         const uint8_t* sIn, int N, const Intr& K, double* s_pose, GnShared& G) {
+    const int tid = threadIdx.x;
+    double* s_red = G.red; double* s_try = G.tr; double* s_delta = G.delta;
+    int gn_iters = 0;
+    // Damped Gauss-Newton on SE(3) over the inliers' 2N reprojection residuals (same minimum as p3p.py:188-213's
+    // least_squares over per-point distances; the tests hold a numpy restatement of exactly these steps).
+    double lam = 0.0, cost = 0.0;
+    bool have_system = false;
+    double Hs[21], gs[6];
+    for (int it = 0; it < GN_MAX_ITERS; it++) {
+        if (!have_system) {
+            double acc[28];
+#pragma unroll
+            for (int k = 0; k < 28; k++) acc[k] = 0.0;
+            double m[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) m[i] = s_pose[i];
+            for (int i = tid; i < N; i += PO_THREADS) {
+                if (!sIn[i]) continue;
+                const double xc = m[0] * sX[i] + m[1] * sY[i] + m[2] * sZ[i] + m[9];
+                const double yc = m[3] * sX[i] + m[4] * sY[i] + m[5] * sZ[i] + m[10];
+                const double zc = m[6] * sX[i] + m[7] * sY[i] + m[8] * sZ[i] + m[11];
+                const double iz = 1.0 / zc, xn = xc * iz, yn = yc * iz;
+                const double ru = sU[i] - (K.fx * xn + K.cx), rv = sV[i] - (K.fy * yn + K.cy);
+                const double Ju[6] = {K.fx * iz, 0.0, -K.fx * xn * iz, -K.fx * xn * yn, K.fx * (1.0 + xn * xn), -K.fx * yn};
+                const double Jv[6] = {0.0, K.fy * iz, -K.fy * yn * iz, -K.fy * (1.0 + yn * yn), K.fy * xn * yn, K.fy * xn};
+                int q = 0;
+#pragma unroll
+                for (int a = 0; a < 6; a++)
+#pragma unroll
+                    for (int b = a; b < 6; b++) acc[q++] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
+#pragma unroll
+                for (int a = 0; a < 6; a++) acc[21 + a] += Ju[a] * ru + Jv[a] * rv;
+                acc[27] += ru * ru + rv * rv;
+            }
+            block_sum<28>(acc, s_red);
+            for (int k = 0; k < 21; k++) Hs[k] = s_red[PO_WARPS * 28 + k];
+            for (int k = 0; k < 6; k++) gs[k] = s_red[PO_WARPS * 28 + 21 + k];
+            cost = s_red[PO_WARPS * 28 + 27];
+            have_system = true;
+            __syncthreads();
+        }
+        if (tid == 0) {
+            double A[6][7];
+            int q = 0;
+            for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++) { A[a][b] = Hs[q]; A[b][a] = Hs[q]; q++; }
+            for (int a = 0; a < 6; a++) { A[a][a] += lam * A[a][a]; A[a][6] = gs[a]; }
+            bool ok = solve6(A);
+            for (int a = 0; a < 6; a++) ok = ok && isfinite(A[a][6]);
+            if (ok) {
+                double d[6], E[9];
+                for (int a = 0; a < 6; a++) { d[a] = A[a][6]; s_delta[a] = d[a]; }
+                so3_exp(d + 3, E);
+                for (int i = 0; i < 3; i++) {
+                    for (int j = 0; j < 3; j++)
+                        s_try[3 * i + j] = E[3 * i] * s_pose[j] + E[3 * i + 1] * s_pose[3 + j] + E[3 * i + 2] * s_pose[6 + j];
+                    s_try[9 + i] = E[3 * i] * s_pose[9] + E[3 * i + 1] * s_pose[10] + E[3 * i + 2] * s_pose[11] + d[i];
+                }
+            }
+            G.ok = ok ? 1 : 0;
+        }
+        __syncthreads();
+        if (!G.ok) break;
+        double c2[1] = {0.0};
+        {
+            double m[12];
+#pragma unroll
+            for (int i = 0; i < 12; i++) m[i] = s_try[i];
+            for (int i = tid; i < N; i += PO_THREADS) {
+                if (!sIn[i]) continue;
+                const double xc = m[0] * sX[i] + m[1] * sY[i] + m[2] * sZ[i] + m[9];
+                const double yc = m[3] * sX[i] + m[4] * sY[i] + m[5] * sZ[i] + m[10];
+                const double zc = m[6] * sX[i] + m[7] * sY[i] + m[8] * sZ[i] + m[11];
+                const double iz = 1.0 / zc;
+                const double ru = sU[i] - (K.fx * xc * iz + K.cx), rv = sV[i] - (K.fy * yc * iz + K.cy);
+                c2[0] += ru * ru + rv * rv;
+            }
+        }
+        block_sum<1>(c2, s_red);
+        const double cost2 = s_red[PO_WARPS];
+        double dmax = 0.0;
+        for (int a = 0; a < 6; a++) dmax = fmax(dmax, fabs(s_delta[a]));
+        __syncthreads();
+        gn_iters++;
+        if (cost2 <= cost) {
+            if (tid < 12) s_pose[tid] = s_try[tid];
+            lam = lam > 1e-9 ? lam * 0.1 : 0.0;
+            have_system = false;
+            __syncthreads();
+            if (dmax < 1e-11) break;
+        } else {
+            lam = (lam == 0.0) ? 1e-4 : lam * 10.0;
+            if (lam > 1e8) break;
+        }
+    }
+    return gn_iters;
+}
+
 __global__ void __launch_bounds__(PO_THREADS)
 pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inliers_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -317,8 +421,8 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
     uint8_t* sIn = reinterpret_cast<uint8_t*>(sV + C);                    // [C]
     __shared__ double s_models[PO_HYP][12];
     __shared__ double s_best[12];
-    __shared__ double s_red[(PO_WARPS + 1) * 28];
-    __shared__ double s_pose[12], s_try[12], s_delta[6];
+    __shared__ GnShared s_gn;
+    __shared__ double s_pose[12];
     __shared__ int s_idx[PO_HYP][4], s_valid[PO_HYP], s_cnt[PO_HYP];
     __shared__ PipeRng s_snap[PO_HYP + 1];
     __shared__ int s_ctl[8];      // 0 stop, 1 n, 2 best, 3 n_iter, 4 draws, 5 flags, 6 accept/continue
@@ -433,99 +537,7 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
     }
     __syncthreads();
     int gn_iters = 0;
-    if (P.refine) {
-        // Damped Gauss-Newton on SE(3) over the inliers' 2N reprojection residuals (same minimum as p3p.py:188-213's
-        // least_squares over per-point distances; the tests hold a numpy restatement of exactly these steps).
-        double lam = 0.0, cost = 0.0;
-        bool have_system = false;
-        double Hs[21], gs[6];
-        for (int it = 0; it < GN_MAX_ITERS; it++) {
-            if (!have_system) {
-                double acc[28];
-#pragma unroll
-                for (int k = 0; k < 28; k++) acc[k] = 0.0;
-                double m[12];
-#pragma unroll
-                for (int i = 0; i < 12; i++) m[i] = s_pose[i];
-                for (int i = tid; i < N; i += PO_THREADS) {
-                    if (!sIn[i]) continue;
-                    const double xc = m[0] * sX[i] + m[1] * sY[i] + m[2] * sZ[i] + m[9];
-                    const double yc = m[3] * sX[i] + m[4] * sY[i] + m[5] * sZ[i] + m[10];
-                    const double zc = m[6] * sX[i] + m[7] * sY[i] + m[8] * sZ[i] + m[11];
-                    const double iz = 1.0 / zc, xn = xc * iz, yn = yc * iz;
-                    const double ru = sU[i] - (K.fx * xn + K.cx), rv = sV[i] - (K.fy * yn + K.cy);
-                    const double Ju[6] = {K.fx * iz, 0.0, -K.fx * xn * iz, -K.fx * xn * yn, K.fx * (1.0 + xn * xn), -K.fx * yn};
-                    const double Jv[6] = {0.0, K.fy * iz, -K.fy * yn * iz, -K.fy * (1.0 + yn * yn), K.fy * xn * yn, K.fy * xn};
-                    int q = 0;
-#pragma unroll
-                    for (int a = 0; a < 6; a++)
-#pragma unroll
-                        for (int b = a; b < 6; b++) acc[q++] += Ju[a] * Ju[b] + Jv[a] * Jv[b];
-#pragma unroll
-                    for (int a = 0; a < 6; a++) acc[21 + a] += Ju[a] * ru + Jv[a] * rv;
-                    acc[27] += ru * ru + rv * rv;
-                }
-                block_sum<28>(acc, s_red);
-                for (int k = 0; k < 21; k++) Hs[k] = s_red[PO_WARPS * 28 + k];
-                for (int k = 0; k < 6; k++) gs[k] = s_red[PO_WARPS * 28 + 21 + k];
-                cost = s_red[PO_WARPS * 28 + 27];
-                have_system = true;
-                __syncthreads();
-            }
-            if (tid == 0) {
-                double A[6][7];
-                int q = 0;
-                for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++) { A[a][b] = Hs[q]; A[b][a] = Hs[q]; q++; }
-                for (int a = 0; a < 6; a++) { A[a][a] += lam * A[a][a]; A[a][6] = gs[a]; }
-                bool ok = solve6(A);
-                for (int a = 0; a < 6; a++) ok = ok && isfinite(A[a][6]);
-                if (ok) {
-                    double d[6], E[9];
-                    for (int a = 0; a < 6; a++) { d[a] = A[a][6]; s_delta[a] = d[a]; }
-                    so3_exp(d + 3, E);
-                    for (int i = 0; i < 3; i++) {
-                        for (int j = 0; j < 3; j++)
-                            s_try[3 * i + j] = E[3 * i] * s_pose[j] + E[3 * i + 1] * s_pose[3 + j] + E[3 * i + 2] * s_pose[6 + j];
-                        s_try[9 + i] = E[3 * i] * s_pose[9] + E[3 * i + 1] * s_pose[10] + E[3 * i + 2] * s_pose[11] + d[i];
-                    }
-                }
-                s_ctl[6] = ok ? 1 : 0;
-            }
-            __syncthreads();
-            if (!s_ctl[6]) break;
-            double c2[1] = {0.0};
-            {
-                double m[12];
-#pragma unroll
-                for (int i = 0; i < 12; i++) m[i] = s_try[i];
-                for (int i = tid; i < N; i += PO_THREADS) {
-                    if (!sIn[i]) continue;
-                    const double xc = m[0] * sX[i] + m[1] * sY[i] + m[2] * sZ[i] + m[9];
-                    const double yc = m[3] * sX[i] + m[4] * sY[i] + m[5] * sZ[i] + m[10];
-                    const double zc = m[6] * sX[i] + m[7] * sY[i] + m[8] * sZ[i] + m[11];
-                    const double iz = 1.0 / zc;
-                    const double ru = sU[i] - (K.fx * xc * iz + K.cx), rv = sV[i] - (K.fy * yc * iz + K.cy);
-                    c2[0] += ru * ru + rv * rv;
-                }
-            }
-            block_sum<1>(c2, s_red);
-            const double cost2 = s_red[PO_WARPS];
-            double dmax = 0.0;
-            for (int a = 0; a < 6; a++) dmax = fmax(dmax, fabs(s_delta[a]));
-            __syncthreads();
-            gn_iters++;
-            if (cost2 <= cost) {
-                if (tid < 12) s_pose[tid] = s_try[tid];
-                lam = lam > 1e-9 ? lam * 0.1 : 0.0;
-                have_system = false;
-                __syncthreads();
-                if (dmax < 1e-11) break;
-            } else {
-                lam = (lam == 0.0) ? 1e-4 : lam * 10.0;
-                if (lam > 1e8) break;
-            }
-        }
-    }
+    if (P.refine) gn_iters = gn_refine(sX, sY, sZ, sU, sV, sIn, N, K, s_pose, s_gn);
     __syncthreads();
     if (tid < 12) {
         Q.w2c_prev[(size_t)s * 12 + tid] = Q.w2c[(size_t)s * 12 + tid];
@@ -533,6 +545,31 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
     __syncthreads();
     if (tid < 12) Q.w2c[(size_t)s * 12 + tid] = s_pose[tid];
     if (tid == 0) { cnt[4] = best; cnt[7] |= s_ctl[5]; cnt[11] = gn_iters; }
+}
+
+// ---- the refinement alone (p3p.py:188-213 for the drop-in P3PPoseEstimator): one CTA per problem ------------------
+__global__ void __launch_bounds__(PO_THREADS)
+refine_pose_kernel(const double* __restrict__ landmarks, const double* __restrict__ keypoints, const uint8_t* __restrict__ mask,
+                   int N, Intr K, const double* __restrict__ pose_in, double* __restrict__ pose_out, int* __restrict__ iters_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sX = reinterpret_cast<double*>(smem_raw);
+    double* sY = sX + N; double* sZ = sY + N; double* sU = sZ + N; double* sV = sU + N;
+    uint8_t* sIn = reinterpret_cast<uint8_t*>(sV + N);
+    __shared__ GnShared s_gn;
+    __shared__ double s_pose[12];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const double* L = landmarks + (size_t)f * N * 3;
+    const double* P2 = keypoints + (size_t)f * N * 2;
+    for (int i = tid; i < N; i += PO_THREADS) {
+        sX[i] = L[3 * i]; sY[i] = L[3 * i + 1]; sZ[i] = L[3 * i + 2]; sU[i] = P2[2 * i]; sV[i] = P2[2 * i + 1];
+        sIn[i] = mask ? mask[(size_t)f * N + i] : 1;
+    }
+    if (tid < 12) s_pose[tid] = pose_in[(size_t)f * 12 + tid];
+    __syncthreads();
+    const int it = gn_refine(sX, sY, sZ, sU, sV, sIn, N, K, s_pose, s_gn);
+    __syncthreads();
+    if (tid < 12) pose_out[(size_t)f * 12 + tid] = s_pose[tid];
+    if (tid == 0 && iters_out) iters_out[f] = it;
 }
 
 // ---- update: state.py + triangulation.py:38-86 ----------------------------------------------------
@@ -1124,6 +1161,50 @@ int vo_pipeline_read_detections_host(vo_pipeline* pl, int seq, int32_t* h_xy, in
     VO_CUDA(cudaDeviceSynchronize());
     VO_CUDA(cudaMemcpy(n, pl->det_n[pl->cur] + seq, 4, cudaMemcpyDeviceToHost));
     VO_CUDA(cudaMemcpy(h_xy, pl->det_xy[pl->cur] + (size_t)seq * pl->det_cap * 2, (size_t)pl->det_cap * 8, cudaMemcpyDeviceToHost));
+    return VO_OK;
+}
+
+// p3p.py:188-213 for n_frames independent problems: minimise the reprojection error of the masked correspondences over
+// the pose, starting from pose_in (R row-major | t, world -> camera).
+int vo_refine_pose_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, const uint8_t* d_mask, int n_frames, int N,
+                       const double* K9, const double* d_pose_in, double* d_pose_out, int32_t* d_iters, void* stream) {
+    VO_REQUIRE(ctx && d_landmarks && d_keypoints && K9 && d_pose_in && d_pose_out, "vo_refine_pose_dev: null argument");
+    VO_REQUIRE(n_frames >= 1 && N >= 1, "vo_refine_pose_dev: bad sizes");
+    const size_t smem = (size_t)N * 41 + 64;
+    VO_REQUIRE(smem <= 200 * 1024, "vo_refine_pose_dev: at most %d correspondences per problem", (int)((200 * 1024 - 64) / 41));
+    VO_CUDA(cudaSetDevice(ctx->device));
+    if (vo_ctx_once(ctx, VO_ATTR_PIPE))
+        VO_CUDA(cudaFuncSetAttribute(refine_pose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    refine_pose_kernel<<<n_frames, PO_THREADS, smem, s>>>(d_landmarks, d_keypoints, d_mask, N, Intr{K9[0], K9[4], K9[2], K9[5]}, d_pose_in,
+                                                          d_pose_out, d_iters);
+    ctx->launches++;
+    VO_CHECK_LAUNCH();
+    return VO_OK;
+}
+
+int vo_refine_pose_host(vo_ctx* ctx, const double* h_landmarks, const double* h_keypoints, const uint8_t* h_mask, int n_frames, int N,
+                        const double* K9, const double* h_pose_in, double* h_pose_out, int32_t* h_iters) {
+    VO_REQUIRE(ctx && h_landmarks && h_keypoints && K9 && h_pose_in && h_pose_out, "vo_refine_pose_host: null argument");
+    VO_REQUIRE(n_frames >= 1 && N >= 1, "vo_refine_pose_host: bad sizes");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t F = n_frames;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_l = carve(F * N * 24), o_k = carve(F * N * 16), o_m = carve(F * N), o_pi = carve(F * 96), o_po = carve(F * 96), o_it = carve(F * 4);
+    int rc = vo_buf_reserve(&ctx->scratch[13], off);
+    if (rc) return rc;
+    unsigned char* b = (unsigned char*)ctx->scratch[13].p;
+    VO_CUDA(cudaMemcpyAsync(b + o_l, h_landmarks, F * N * 24, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(b + o_k, h_keypoints, F * N * 16, cudaMemcpyHostToDevice, s));
+    if (h_mask) VO_CUDA(cudaMemcpyAsync(b + o_m, h_mask, F * N, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(b + o_pi, h_pose_in, F * 96, cudaMemcpyHostToDevice, s));
+    if ((rc = vo_refine_pose_dev(ctx, (double*)(b + o_l), (double*)(b + o_k), h_mask ? b + o_m : nullptr, n_frames, N, K9, (double*)(b + o_pi),
+                                 (double*)(b + o_po), (int32_t*)(b + o_it), s))) return rc;
+    VO_CUDA(cudaMemcpyAsync(h_pose_out, b + o_po, F * 96, cudaMemcpyDeviceToHost, s));
+    if (h_iters) VO_CUDA(cudaMemcpyAsync(h_iters, b + o_it, F * 4, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
     return VO_OK;
 }
 

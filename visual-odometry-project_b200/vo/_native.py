@@ -93,6 +93,12 @@ def lib():
             "vo_pipeline_write_table_host": (i32, [vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
             "vo_pipeline_read_detections_host": (i32, [vp, i32, vp, vp]),
             "vo_test_pcg64_choice4_host": (i32, [vp, vp, i32, i32, vp]),
+            "vo_klt_track_bgr_host": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, dbl, dbl, vp, i32, vp, vp, vp]),
+            "vo_klt_cache_hits": (u64, [vp]),
+            "vo_bgr2gray_dev": (i32, [vp, vp, i32, i32, i32, sz, sz, vp, sz, sz, vp]),
+            "vo_bgr2gray_host": (i32, [vp, vp, i32, i32, i32, vp]),
+            "vo_refine_pose_dev": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
+            "vo_refine_pose_host": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]),
         })
         for name, (rt, at) in _optional.items():
             if hasattr(L, name):  # all are present in a complete build; tests/test_abi.py checks that

@@ -51,7 +51,8 @@ def harris_detect(img, num_keypoints=1000, patch_size=9, kappa=0.09, nms_radius=
 # KLT  (reference: src/vo/features/klt.py:233-239 -> cv2.calcOpticalFlowPyrLK)
 # ------------------------------------------------------------------------------------------------
 def klt_track(prev, nxt, pts, win=17, max_level=2, max_iters=10, epsilon=0.03, min_eig=1e-4, ctx=None):
-    """Pyramidal LK for one frame pair (H, W) or a batch (F, H, W); pts (N, 2) or (F, N, 2) float32.
+    """Pyramidal LK for one frame pair (H, W) / (H, W, 3) BGR or a batch (F, H, W) / (F, H, W, 3); pts (N, 2) or
+    (F, N, 2) float32.  BGR input is converted on the device (cv2.cvtColor's arithmetic, klt.py:57-62).
 
     Returns (next_pts float32, status uint8, err float32) shaped like cv2's outputs (without the
     middle singleton axis)."""
@@ -60,22 +61,38 @@ def klt_track(prev, nxt, pts, win=17, max_level=2, max_iters=10, epsilon=0.03, m
     b = np.ascontiguousarray(nxt, dtype=np.uint8)
     if a.shape != b.shape:
         raise ValueError("klt_track: prev and next images must have the same shape")
-    single = a.ndim == 2
+    bgr = a.shape[-1] == 3 and a.ndim in (3, 4) and not (a.ndim == 3 and np.asarray(pts).ndim == 3)
+    single = a.ndim == (3 if bgr else 2)
     if single:
         a, b = a[None], b[None]
-    F, H, W = a.shape
+    F, H, W = a.shape[:3]
     p = np.ascontiguousarray(np.asarray(pts, dtype=np.float32).reshape(F, -1, 2))
     n = p.shape[1]
     out = np.zeros((F, n, 2), dtype=np.float32)
     status = np.zeros((F, n), dtype=np.uint8)
     err = np.zeros((F, n), dtype=np.float32)
-    rc = nat.lib().vo_klt_track_host(ctx.handle, nat.ptr(a), nat.ptr(b), F, H, W, int(max_level), int(win),
-                                     int(max_iters), C.c_double(epsilon), C.c_double(min_eig), nat.ptr(p), n,
-                                     nat.ptr(out), nat.ptr(status), nat.ptr(err))
+    fn = nat.lib().vo_klt_track_bgr_host if bgr else nat.lib().vo_klt_track_host
+    rc = fn(ctx.handle, nat.ptr(a), nat.ptr(b), F, H, W, int(max_level), int(win), int(max_iters), C.c_double(epsilon),
+            C.c_double(min_eig), nat.ptr(p), n, nat.ptr(out), nat.ptr(status), nat.ptr(err))
     nat.check(rc, "vo_klt_track_host")
     if single:
         return out[0], status[0], err[0]
     return out, status, err
+
+
+def bgr2gray(img, ctx=None):
+    """cv2.cvtColor(img, cv2.COLOR_BGR2GRAY) for uint8 (H, W, 3) or (F, H, W, 3), on the device, bit-exact."""
+    ctx = _ctx(ctx)
+    a = np.ascontiguousarray(img, dtype=np.uint8)
+    single = a.ndim == 3
+    if single:
+        a = a[None]
+    if a.ndim != 4 or a.shape[-1] != 3:
+        raise ValueError("bgr2gray: image must be (H, W, 3) or (F, H, W, 3) uint8")
+    F, H, W = a.shape[:3]
+    out = np.empty((F, H, W), np.uint8)
+    nat.check(nat.lib().vo_bgr2gray_host(ctx.handle, nat.ptr(a), F, H, W, nat.ptr(out)), "vo_bgr2gray_host")
+    return out[0] if single else out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -124,6 +141,26 @@ def p3p_ransac(landmarks, keypoints, K, sample_idx, threshold, iters_for_count, 
     if single:
         res = {k: (v[0] if v is not None else None) for k, v in res.items()}
     return res
+
+
+def refine_pose(landmarks, keypoints, K, R, t, mask=None, ctx=None):
+    """_nonlinear_refinement (p3p.py:188-213) on the GPU: (R 3x3, t 3x1) minimising the reprojection error of the
+    (masked) correspondences, started at (R, t).  Also returns the number of Gauss-Newton steps."""
+    ctx = _ctx(ctx)
+    L = np.ascontiguousarray(np.asarray(landmarks, dtype=np.float64).reshape(-1, 3))
+    P = np.ascontiguousarray(np.asarray(keypoints, dtype=np.float64).reshape(-1, 2))
+    N = L.shape[0]
+    if P.shape[0] != N:
+        raise ValueError("refine_pose: landmarks and keypoints differ in length")
+    K9 = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    pin = np.ascontiguousarray(np.concatenate([np.asarray(R, dtype=np.float64).reshape(9), np.asarray(t, dtype=np.float64).reshape(3)]))
+    pout = np.empty(12)
+    it = np.zeros(1, np.int32)
+    m = None if mask is None else np.ascontiguousarray(np.asarray(mask).astype(np.uint8).reshape(N))
+    rc = nat.lib().vo_refine_pose_host(ctx.handle, nat.ptr(L), nat.ptr(P), nat.ptr(m) if m is not None else None, 1, N, nat.ptr(K9),
+                                       nat.ptr(pin), nat.ptr(pout), nat.ptr(it))
+    nat.check(rc, "vo_refine_pose_host")
+    return pout[:9].reshape(3, 3).copy(), pout[9:].reshape(3, 1).copy(), int(it[0])
 
 
 # ------------------------------------------------------------------------------------------------

@@ -47,8 +47,8 @@ class KLTTracker:
         return self.to_gray(self._frame.image)
 
     def to_gray(self, img) -> np.ndarray:
-        import cv2
-        return cv2.cvtColor(img, cv2.COLOR_BGR2GRAY)
+        """klt.py:84-85 (cv2.cvtColor BGR2GRAY) on the device, bit-exact."""
+        return _ops.bgr2gray(img)
 
     def _get_udis(self, length: int) -> np.ndarray:
         return np.random.randint(0, np.iinfo(np.int32).max, size=length, dtype=np.int32)
@@ -113,7 +113,10 @@ class KLTTracker:
         win = self._lk_params["winSize"][0]
         _, max_count, eps = self._lk_params["criteria"]
         prev_pts = np.asarray(self._old_frame.features.keypoints, dtype=np.float32).reshape(-1, 2)
-        next_pts, status, error = _ops.klt_track(self.old_img_gray, self.img_gray, prev_pts, win=win,
+        # BGR frames go to the device as they are (the grayscale conversion of klt.py:57-62 is fused into the upload),
+        # and the pyramid of a frame is built once: the previous call's `next` is this call's `prev`
+        old_img, new_img = self._old_frame.image, self._frame.image
+        next_pts, status, error = _ops.klt_track(old_img, new_img, prev_pts, win=win,
                                                  max_level=self._lk_params["maxLevel"], max_iters=max_count, epsilon=eps)
         next_pts = next_pts.reshape((-1, 2, 1))
         keep = np.logical_and(status.astype(bool), error < self._error_threshold)       # klt.py:244-249
