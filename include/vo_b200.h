@@ -80,6 +80,18 @@ int vo_match_descriptors_dev(vo_ctx* ctx, const uint8_t* d_desc1, const uint8_t*
 int vo_match_descriptors_host(vo_ctx* ctx, const uint8_t* h_desc1, const uint8_t* h_desc2, int n_frames, int Q, int T,
                               int D, double ratio, int32_t* h_pairs, int32_t* h_n_pairs);
 
+/* ---- Shi-Tomasi corners: src/vo/features/klt.py:24-26, 87-115 (cv2.goodFeaturesToTrack) -------------------------- */
+/* cv2.goodFeaturesToTrack(img, maxCorners, qualityLevel, minDistance, blockSize=block_size) with the default 3x3 Sobel
+ * aperture and no mask (the reference passes an all-255 mask).  OpenCV's float arithmetic is reproduced operation by
+ * operation (see csrc/gftt.cu), so the corner list -- float32 [n_frames][max_corners][2] = (x, y) in OpenCV's order, the
+ * first n[f] rows valid -- is cv2's.  d_eig receives cv2.cornerMinEigenVal's map, float32 [n_frames][H][W].
+ * stats (optional) uint32 [n_frames][4] = {candidates, corners before the maxCorners cut, selection rounds, overflow}. */
+int vo_gftt_dev(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch, size_t frame_stride, int max_corners,
+                double quality_level, double min_distance, int block_size, float* d_eig, float* d_xy, int32_t* d_n, uint32_t* d_stats,
+                void* stream);
+int vo_gftt_host(vo_ctx* ctx, const uint8_t* h_img, int n_frames, int H, int W, int max_corners, double quality_level,
+                 double min_distance, int block_size, float* h_eig, float* h_xy, int32_t* h_n, uint32_t* h_stats);
+
 /* ---- KLT: src/vo/features/klt.py:233-239 (cv2.calcOpticalFlowPyrLK) ------------------------- */
 /* Gaussian 5x5 pyramid (cv2.pyrDown, BORDER_REFLECT_101) of a batch of frames, frame-major: level l
  * of frame f lives at d_pyr + f * frame_bytes + level_offset[l] with row pitch level_pitch[l]
@@ -244,6 +256,7 @@ int vo_frontend_wait_host(vo_frontend* fe);
 typedef struct vo_pipeline vo_pipeline;
 #define VO_DETECTOR_NONE 0     /* the host appends corners itself (vo_pipeline_write_table_host)                 */
 #define VO_DETECTOR_HARRIS 1   /* HarrisCornerDetector.extractKeypoints (harris.py:86-158) on every new frame    */
+#define VO_DETECTOR_GFTT 2     /* cv2.goodFeaturesToTrack (klt.py:24-26, 87-115), the reference's KLT-mode detector */
 #define VO_PIPE_NCOUNTS 12
 #define VO_PIPE_SUMMARY_DOUBLES 18   /* per sequence: 12 doubles pose + VO_PIPE_NCOUNTS int32 counters            */
 /* counters: 0 rows after the step, 1 rows tracked, 2 rows kept by the status/error filter, 3 P3P population,
@@ -259,6 +272,7 @@ typedef struct {
     double redetect_fraction;                        /* klt.py:211 (0.8)                                           */
     int detector, det_max_corners;                   /* VO_DETECTOR_*; corners per detection                       */
     int patch_size; double kappa; int nms_radius;    /* harris.py:16-34                                            */
+    double gftt_quality, gftt_min_distance; int gftt_block_size;   /* klt.py:24-26                                 */
     double K[9], Kinv[9];                            /* intrinsics and their inverse AS THE HOST COMPUTES IT
                                                         (camera.py:92: np.linalg.inv in K's own dtype)             */
     double p3p_threshold; int p3p_inclusive;         /* p3p.py:20 / ransac.py:105; inclusive = cv2's `<=` rule     */
@@ -300,7 +314,8 @@ int vo_pipeline_read_table_host(vo_pipeline* pl, int seq, int* n_rows, float* h_
 int vo_pipeline_write_table_host(vo_pipeline* pl, int seq, int n_rows, const float* h_kp, const double* h_land, const uint8_t* h_state,
                                  const float* h_track, const double* h_pose, const double* h_c2w, int num_features, int n_iterations,
                                  const uint64_t* h_rng);
-int vo_pipeline_read_detections_host(vo_pipeline* pl, int seq, int32_t* h_xy, int* n);
+/* corners of the current frame as the detector left them: int32 (Harris) or float32 (Shi-Tomasi) [det_max_corners][2] */
+int vo_pipeline_read_detections_host(vo_pipeline* pl, int seq, void* h_xy, int* n);
 /* Test hook: n_draws samples of numpy's Generator(PCG64).choice(arange(N), size=4, replace=False) (ransac.py:92-94)
  * from the given generator state; the state is advanced in place.                                                 */
 int vo_test_pcg64_choice4_host(vo_ctx* ctx, uint64_t* state6, int N, int n_draws, int32_t* h_out);

@@ -94,6 +94,39 @@ def match_descriptors(desc1, desc2, ratio=0.85):
 
 
 # ----------------------------------------------------------------------------
+# Shi-Tomasi corners  (reference: src/vo/features/klt.py:24-26, 87-115 -> cv2.goodFeaturesToTrack)
+# ----------------------------------------------------------------------------
+def min_eigen_val(img: np.ndarray, block: int = 7) -> np.ndarray:
+    """cv2.cornerMinEigenVal(img, block, ksize=3) -> float32 (H, W)."""
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    H, W = img.shape
+    out = np.empty((H, W), dtype=np.float32)
+    rc = lib().oracle_min_eigen_val(_p(img, C.c_uint8), H, W, W, int(block), _p(out, C.c_float))
+    if rc != 0:
+        raise ValueError(f"oracle_min_eigen_val rc={rc}")
+    return out
+
+
+def gftt_select(eig: np.ndarray, max_corners=500, quality=0.01, min_distance=8.0, return_candidates=False):
+    """Thresholding, 3x3 local maxima, ordering and the minimum-distance greedy pass of cv2.goodFeaturesToTrack on a
+    given eigenvalue map -> float32 (n, 2) corners as (x, y)."""
+    e = np.ascontiguousarray(eig, dtype=np.float32)
+    H, W = e.shape
+    xy = np.empty((H * W // 2 + 64, 2), dtype=np.float32)
+    nc = C.c_int(0)
+    n = lib().oracle_gftt_select(_p(e, C.c_float), H, W, int(max_corners), C.c_double(quality), C.c_double(min_distance),
+                                 _p(xy, C.c_float), C.byref(nc))
+    if n < 0:
+        raise ValueError(f"oracle_gftt_select rc={n}")
+    return (xy[:n].copy(), nc.value) if return_candidates else xy[:n].copy()
+
+
+def good_features_to_track(img, max_corners=500, quality=0.01, min_distance=8.0, block=7):
+    """cv2.goodFeaturesToTrack(img, maxCorners, qualityLevel, minDistance, blockSize=block) -> float32 (n, 2)."""
+    return gftt_select(min_eigen_val(img, block), max_corners, quality, min_distance)
+
+
+# ----------------------------------------------------------------------------
 # P3P + RANSAC  (reference: src/vo/pose_estimation/p3p.py, src/vo/algorithms/ransac.py)
 # ----------------------------------------------------------------------------
 def p3p_solve4(X4, uv4, K, return_all=False):

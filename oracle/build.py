@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT_DIR = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT_DIR, "libvo_oracle.so")
-SOURCES = ["harris.c", "klt.c", "p3p.c", "triangulation.c"]
+SOURCES = ["harris.c", "klt.c", "p3p.c", "triangulation.c", "gftt.c"]
 
 
 def needs_build() -> bool:

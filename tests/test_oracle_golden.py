@@ -267,3 +267,26 @@ def test_p3p_solver_sweep_vs_cv2():
     assert both > 15000
     assert mism == 0, (mism, both)
     assert only_cv <= both // 500, (only_cv, only_or, both)
+
+
+# ---------------------------------------------------------------------------- Shi-Tomasi corners (klt.py:24-26, 87-115)
+def test_gftt_oracle_bitexact_vs_cv2(golden):
+    """cv2.goodFeaturesToTrack is a third-party dependency of the reference (not vendored); the restatement in
+    oracle/gftt.c must reproduce cv2.cornerMinEigenVal bit for bit and cv2.goodFeaturesToTrack's corner list exactly, on
+    the reference's KITTI frames and on ragged / tiny / dense synthetic frames."""
+    import cv2
+    from conftest import synthetic_image
+    g = golden("loop")
+    imgs = _kitti_frames() + [synthetic_image(120, 200, 1), synthetic_image(376, 1241, 2), synthetic_image(64, 31, 3),
+                              synthetic_image(50, 97, 4), synthetic_image(200, 1215, 6)]
+    for k, im in enumerate(imgs):
+        e = oracle.min_eigen_val(im, 7)
+        assert np.array_equal(e, cv2.cornerMinEigenVal(im, 7, ksize=3)), k
+        want = cv2.goodFeaturesToTrack(im, maxCorners=500, qualityLevel=0.01, minDistance=8, blockSize=7).reshape(-1, 2)
+        assert np.array_equal(oracle.gftt_select(e), want), k
+        if k < 6:
+            assert np.array_equal(want, g[f"gftt_{k}"])        # the fixture made with the reference's parameters
+    for block, md, q in [(3, 12, 0.01), (5, 1, 0.05), (7, 3, 0.001)]:
+        im = imgs[6]
+        want = cv2.goodFeaturesToTrack(im, maxCorners=300, qualityLevel=q, minDistance=md, blockSize=block).reshape(-1, 2)
+        assert np.array_equal(oracle.good_features_to_track(im, 300, q, md, block), want)

@@ -161,3 +161,38 @@ def test_pipeline_harris_detector_and_batching(ctx):
             assert got["num_features"] == los[s].num_features, (t, s)
             assert np.array_equal(pl.read_detections(s), oracle.harris_keypoints(frames[t][s], KP, 9, 0.09, 5)[0]), (t, s)
     pl.close()
+
+
+def test_pipeline_gftt_detector_reference_klt_mode(golden):
+    """The reference's KLT mode end to end on the device: Shi-Tomasi corners seed the table (KLTTracker.__init__,
+    klt.py:40-50) and refill it when fewer than 80 % survive (klt.py:207-230, forced here by telling the sequence it
+    once had 650 features)."""
+    import oracle
+    from oracle.loop import LoopOracle
+    from vo.pipeline import DETECTOR_GFTT, Pipeline
+    g = golden("loop")
+    frames = kitti_frames()
+    H, W = frames[0].shape
+    pl = Pipeline(1, H, W, g["K"], capacity=1024, detector=DETECTOR_GFTT, det_max_corners=500, refine=True)
+    pl.prime(frames[2][None], init_tables=True)
+    t = pl.read_table(0)
+    assert np.array_equal(t["kp"], g["gftt_2"]) and t["num_features"] == 500 and (t["state"] == 0).all()
+    lo = LoopOracle(g["K"], detector=lambda im: oracle.good_features_to_track(im), refine="gn")
+    for obj in (lo, pl):
+        args = (g["boot_kp"], g["boot_land"], g["boot_state"], g["boot_track"], g["boot_pose"])
+        if obj is lo:
+            lo.set_table(*args, g["boot_cand"], curr_pose=g["boot_curr_pose"], num_features=650)
+        else:
+            pl.write_table(0, *args, curr_pose=g["boot_curr_pose"], num_features=650)
+    for i in (3, 4, 5):
+        info = lo.step(frames[i - 1], frames[i])
+        summ = pl.step(frames[i][None])
+        got, want = pl.read_table(0), lo.table()
+        assert bool(summ["flags"][0] & 1) == info["redetect"] == (i == 3), i
+        assert got["n"] == len(want["kp"]) and got["num_features"] == lo.num_features == 500, i
+        assert np.array_equal(got["kp"], want["kp"]) and np.array_equal(got["state"], want["state"]), i
+        assert np.array_equal(got["cand"], want["cand"]) and np.array_equal(got["inliers"], info["inliers"]), i
+        assert np.allclose(got["curr_pose"], want["curr_pose"], atol=1e-9), i
+        assert np.array_equal(pl.read_detections(0), g[f"gftt_{i}"]), i
+    assert got["n"] > 800                                    # 486 tracked + 500 appended, minus the losses
+    pl.close()

@@ -240,6 +240,45 @@ int vo_match_descriptors_host(vo_ctx* ctx, const uint8_t* h_desc1, const uint8_t
 }
 
 // ------------------------------------------------------------------------------------------
+// Shi-Tomasi corners (cv2.goodFeaturesToTrack)
+// ------------------------------------------------------------------------------------------
+int vo_gftt_dev(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch, size_t frame_stride, int max_corners,
+                double quality_level, double min_distance, int block_size, float* d_eig, float* d_xy, int32_t* d_n, uint32_t* d_stats,
+                void* stream) {
+    VO_REQUIRE(ctx && d_img && d_eig && d_xy && d_n, "vo_gftt_dev: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_launch_gftt(ctx, d_img, n_frames, H, W, pitch, frame_stride, max_corners, quality_level, min_distance, block_size, d_eig,
+                          d_xy, d_n, d_stats, pick_stream(ctx, stream));
+}
+
+int vo_gftt_host(vo_ctx* ctx, const uint8_t* h_img, int n_frames, int H, int W, int max_corners, double quality_level,
+                 double min_distance, int block_size, float* h_eig, float* h_xy, int32_t* h_n, uint32_t* h_stats) {
+    VO_REQUIRE(ctx && h_img && h_xy && h_n, "vo_gftt_host: null argument");
+    VO_REQUIRE(n_frames >= 1 && H >= 3 && W >= 3 && max_corners >= 1, "vo_gftt_host: bad shape");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t pitch = ((size_t)W + 15) & ~(size_t)15, fstride = pitch * H, npx = (size_t)H * W, F = n_frames;
+    int rc;
+    if ((rc = vo_buf_reserve(&ctx->scratch[1], fstride * F))) return rc;
+    if ((rc = vo_buf_reserve(&ctx->scratch[2], npx * F * sizeof(float)))) return rc;
+    if ((rc = vo_buf_reserve(&ctx->scratch[3], F * max_corners * 8 + F * 4 + F * 16 + 1024))) return rc;
+    uint8_t* d_img = (uint8_t*)ctx->scratch[1].p;
+    float* d_eig = (float*)ctx->scratch[2].p;
+    float* d_xy = (float*)ctx->scratch[3].p;
+    int32_t* d_n = (int32_t*)((unsigned char*)ctx->scratch[3].p + ((F * max_corners * 8 + 255) & ~(size_t)255));
+    uint32_t* d_st = (uint32_t*)(d_n + ((F + 63) & ~(size_t)63));
+    VO_CUDA(cudaMemcpy2DAsync(d_img, pitch, h_img, W, W, (size_t)H * F, cudaMemcpyHostToDevice, s));
+    if ((rc = vo_launch_gftt(ctx, d_img, n_frames, H, W, pitch, fstride, max_corners, quality_level, min_distance, block_size, d_eig, d_xy,
+                             d_n, d_st, s))) return rc;
+    VO_CUDA(cudaMemcpyAsync(h_xy, d_xy, F * max_corners * 8, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_n, d_n, F * 4, cudaMemcpyDeviceToHost, s));
+    if (h_eig) VO_CUDA(cudaMemcpyAsync(h_eig, d_eig, npx * F * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (h_stats) VO_CUDA(cudaMemcpyAsync(h_stats, d_st, F * 16, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
+    return VO_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // KLT
 // ------------------------------------------------------------------------------------------
 int vo_klt_pyramid_layout(int H, int W, int max_level, int win, int* n_levels, int* level_h, int* level_w,

@@ -43,3 +43,10 @@ int vo_launch_kp_to_points(vo_ctx* ctx, const int* d_kp_xy, size_t n, float* d_p
 // match.cu
 int vo_launch_match(vo_ctx* ctx, const uint8_t* d_q, const uint8_t* d_t, int n_frames, int Q, int T, int D, double ratio,
                     int* d_pairs, int* d_n_pairs, cudaStream_t stream);
+// gftt.cu
+int vo_gftt_reserve(vo_ctx* ctx, int n_frames, int H, int W, double min_distance);
+int vo_launch_gftt_eig(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch, size_t frame_stride,
+                       int block_size, float* d_eig, int* d_frame_max, cudaStream_t stream);
+int vo_launch_gftt(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch, size_t frame_stride,
+                   int max_corners, double quality, double min_distance, int block_size, float* d_eig, float* d_xy, int* d_n,
+                   unsigned int* d_stats_or_null, cudaStream_t stream);

@@ -784,6 +784,9 @@ static int pipe_run_detector(vo_pipeline* pl, const uint8_t* pyr_level0, int set
         pipe_fill_int_kernel<<<vo_div_up(p.n_seq, 256), 256, 0, s>>>(pl->det_n[set], p.det_max_corners, p.n_seq);
         ctx->launches++;
         VO_CHECK_LAUNCH();
+    } else if (p.detector == VO_DETECTOR_GFTT) {
+        return vo_launch_gftt(ctx, pyr_level0, p.n_seq, p.H, p.W, pl->pitch0, pl->frame_bytes, p.det_max_corners, p.gftt_quality,
+                              p.gftt_min_distance, p.gftt_block_size, (float*)pl->resp, (float*)pl->det_xy[set], pl->det_n[set], nullptr, s);
     }
     return VO_OK;
 }
@@ -796,7 +799,8 @@ int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* prm, vo_pipeline**
     const vo_pipeline_params& p = *prm;
     VO_REQUIRE(p.n_seq >= 1 && p.H > 0 && p.W > 0, "vo_pipeline_create: bad sizes");
     VO_REQUIRE(p.capacity >= 32 && p.capacity <= 8192 && p.capacity % 32 == 0, "vo_pipeline_create: capacity must be a multiple of 32 in [32, 8192]");
-    VO_REQUIRE(p.detector == VO_DETECTOR_NONE || p.detector == VO_DETECTOR_HARRIS, "vo_pipeline_create: unknown detector %d", p.detector);
+    VO_REQUIRE(p.detector == VO_DETECTOR_NONE || p.detector == VO_DETECTOR_HARRIS || p.detector == VO_DETECTOR_GFTT,
+               "vo_pipeline_create: unknown detector %d", p.detector);
     VO_REQUIRE(p.detector == VO_DETECTOR_NONE || (p.det_max_corners >= 1 && p.det_max_corners <= p.capacity),
                "vo_pipeline_create: det_max_corners must be in [1, capacity]");
     VO_REQUIRE(p.K[0] != 0.0 && p.K[4] != 0.0, "vo_pipeline_create: singular intrinsic matrix");
@@ -832,7 +836,7 @@ int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* prm, vo_pipeline**
         const size_t o_cw = carve(S * 96), o_cp = carve(S * 96), o_wc = carve(S * 96), o_wp = carve(S * 96), o_pm = carve(S * 96);
         const size_t o_rng = carve(S * sizeof(PipeRng)), o_cnt = carve(S * VO_PIPE_NCOUNTS * 4);
         const size_t o_nx = carve(S * C * 8), o_st = carve(S * C), o_er = carve(S * C * 4), o_in = carve(S * C);
-        const size_t o_resp = carve(p.detector == VO_DETECTOR_HARRIS ? S * npx * 8 : 0);
+        const size_t o_resp = carve(p.detector == VO_DETECTOR_HARRIS ? S * npx * 8 : (p.detector == VO_DETECTOR_GFTT ? S * npx * 4 : 0));
         const size_t o_dx0 = carve(S * DC * 8), o_dx1 = carve(S * DC * 8), o_dn0 = carve(S * 4), o_dn1 = carve(S * 4);
         const size_t o_su0 = carve(S * VO_PIPE_SUMMARY_DOUBLES * 8), o_su1 = carve(S * VO_PIPE_SUMMARY_DOUBLES * 8);
         const size_t o_sg0 = carve(S * npx + 256), o_sg1 = carve(S * npx + 256);
@@ -851,7 +855,7 @@ int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* prm, vo_pipeline**
         q.c2w = (double*)(b + o_cw); q.c2w_prev = (double*)(b + o_cp); q.w2c = (double*)(b + o_wc); q.w2c_prev = (double*)(b + o_wp);
         q.p3p_model = (double*)(b + o_pm); q.rng = (PipeRng*)(b + o_rng); q.counts = (int*)(b + o_cnt);
         pl->nxt = (float2*)(b + o_nx); pl->status = b + o_st; pl->err = (float*)(b + o_er); pl->inliers = b + o_in;
-        pl->resp = p.detector == VO_DETECTOR_HARRIS ? (double*)(b + o_resp) : nullptr;
+        pl->resp = p.detector != VO_DETECTOR_NONE ? (double*)(b + o_resp) : nullptr;
         pl->det_xy[0] = (int*)(b + o_dx0); pl->det_xy[1] = (int*)(b + o_dx1); pl->det_n[0] = (int*)(b + o_dn0); pl->det_n[1] = (int*)(b + o_dn1);
         pl->summary[0] = (double*)(b + o_su0); pl->summary[1] = (double*)(b + o_su1);
         pl->stage[0] = b + o_sg0; pl->stage[1] = b + o_sg1;
@@ -888,6 +892,10 @@ int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* prm, vo_pipeline**
             const int rc2 = vo_harris_nms_reserve(ctx, p.n_seq, p.H, p.W, p.nms_radius, p.det_max_corners);
             if (rc2) return rc2;
         }
+        if (p.detector == VO_DETECTOR_GFTT) {
+            const int rc2 = vo_gftt_reserve(ctx, p.n_seq, p.H, p.W, p.gftt_min_distance);
+            if (rc2) return rc2;
+        }
         return VO_OK;
     };
     rc = finish();
@@ -919,7 +927,9 @@ static int pipe_prime(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, si
     if ((rc = pipe_run_detector(pl, pl->pyr[pl->cur], pl->cur, s))) return rc;
     if (init_tables) {
         VO_REQUIRE(p.detector != VO_DETECTOR_NONE, "vo_pipeline_prime: init_tables needs a detector");
-        pipe_init_from_det_kernel<<<p.n_seq, 256, 0, s>>>(pl->tab[pl->cur], pl->seq, pl->dp, pl->det_xy[pl->cur], nullptr, pl->det_n[pl->cur], pl->det_cap);
+        const bool fl = p.detector == VO_DETECTOR_GFTT;      // Shi-Tomasi corners are float32, Harris keypoints int32
+        pipe_init_from_det_kernel<<<p.n_seq, 256, 0, s>>>(pl->tab[pl->cur], pl->seq, pl->dp, fl ? nullptr : pl->det_xy[pl->cur],
+                                                          fl ? (const float*)pl->det_xy[pl->cur] : nullptr, pl->det_n[pl->cur], pl->det_cap);
         ctx->launches++;
         VO_CHECK_LAUNCH();
     }
@@ -962,7 +972,9 @@ static int pipe_step(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, siz
     if (fork) VO_CUDA(cudaStreamWaitEvent(sd, pl->ev_level0, 0));
     if (fork) { if ((rc = pipe_run_detector(pl, pl->pyr[nx], nx, sd))) return rc; VO_CUDA(cudaEventRecord(pl->ev_det, sd)); }
     if (p.detector != VO_DETECTOR_NONE) {
-        pipe_append_kernel<<<p.n_seq, 256, 0, s>>>(pl->tab[cur], pl->seq, pl->dp, pl->det_xy[cur], nullptr, pl->det_n[cur], pl->det_cap);
+        const bool fl = p.detector == VO_DETECTOR_GFTT;
+        pipe_append_kernel<<<p.n_seq, 256, 0, s>>>(pl->tab[cur], pl->seq, pl->dp, fl ? nullptr : pl->det_xy[cur],
+                                                   fl ? (const float*)pl->det_xy[cur] : nullptr, pl->det_n[cur], pl->det_cap);
         ctx->launches++;
         VO_CHECK_LAUNCH();
     } else {
@@ -1153,8 +1165,9 @@ int vo_pipeline_write_table_host(vo_pipeline* pl, int seq, int n_rows, const flo
     return VO_OK;
 }
 
-// the detector's corners of the current frame (what the next step would append): int32 [det_max_corners][2], count
-int vo_pipeline_read_detections_host(vo_pipeline* pl, int seq, int32_t* h_xy, int* n) {
+// the detector's corners of the current frame (what the next step would append): [det_max_corners][2] (int32 for the
+// Harris detector, float32 for Shi-Tomasi), count
+int vo_pipeline_read_detections_host(vo_pipeline* pl, int seq, void* h_xy, int* n) {
     VO_REQUIRE(pl && seq >= 0 && seq < pl->p.n_seq && h_xy && n, "vo_pipeline_read_detections_host: bad argument");
     VO_REQUIRE(pl->p.detector != VO_DETECTOR_NONE, "vo_pipeline_read_detections_host: no detector configured");
     VO_CUDA(cudaSetDevice(pl->ctx->device));

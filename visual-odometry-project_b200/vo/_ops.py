@@ -48,6 +48,40 @@ def harris_detect(img, num_keypoints=1000, patch_size=9, kappa=0.09, nms_radius=
 
 
 # ------------------------------------------------------------------------------------------------
+# Shi-Tomasi corners  (reference: src/vo/features/klt.py:24-26, 87-115 -> cv2.goodFeaturesToTrack)
+# ------------------------------------------------------------------------------------------------
+def good_features_to_track(img, max_corners=500, quality_level=0.01, min_distance=8, block_size=7, want_eig=False,
+                           want_stats=False, ctx=None):
+    """cv2.goodFeaturesToTrack for one gray frame (H, W) or a batch (F, H, W) on the GPU.
+
+    Returns float32 corners (n, 2) = (x, y) in OpenCV's order (a list of such arrays for a batch), plus the
+    eigenvalue map float32 (cv2.cornerMinEigenVal) and / or the per-frame statistics when asked for."""
+    ctx = _ctx(ctx)
+    a = np.ascontiguousarray(img, dtype=np.uint8)
+    single = a.ndim == 2
+    if single:
+        a = a[None]
+    if a.ndim != 3:
+        raise ValueError("good_features_to_track: image must be (H, W) or (F, H, W) uint8 grayscale")
+    F, H, W = a.shape
+    xy = np.zeros((F, max_corners, 2), np.float32)
+    n = np.zeros(F, np.int32)
+    eig = np.empty((F, H, W), np.float32) if want_eig else None
+    st = np.zeros((F, 4), np.uint32)
+    rc = nat.lib().vo_gftt_host(ctx.handle, nat.ptr(a), F, H, W, int(max_corners), C.c_double(quality_level),
+                                C.c_double(min_distance), int(block_size), nat.ptr(eig) if want_eig else None, nat.ptr(xy),
+                                nat.ptr(n), nat.ptr(st))
+    nat.check(rc, "vo_gftt_host")
+    corners = [xy[f, : n[f]].copy() for f in range(F)]
+    out = [corners[0] if single else corners]
+    if want_eig:
+        out.append(eig[0] if single else eig)
+    if want_stats:
+        out.append(st[0] if single else st)
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+# ------------------------------------------------------------------------------------------------
 # KLT  (reference: src/vo/features/klt.py:233-239 -> cv2.calcOpticalFlowPyrLK)
 # ------------------------------------------------------------------------------------------------
 def klt_track(prev, nxt, pts, win=17, max_level=2, max_iters=10, epsilon=0.03, min_eig=1e-4, ctx=None):

@@ -59,12 +59,17 @@ class KLTTracker:
         return np.concatenate((array, self._get_udis(target_length - array.shape[0])))
 
     def find_corners(self, frame: Frame, mask=None, use_goodFeaturesToTrack=True) -> np.ndarray:
-        """Shi-Tomasi corners (klt.py:87-115); host OpenCV, as in the reference."""
+        """Shi-Tomasi corners (klt.py:87-115): vo_gftt_host on the GPU (a mask with holes, which the reference never
+        builds, falls back to the host call)."""
         import cv2
         img = frame.image
         if img.ndim == 3:
             img = self.to_gray(img)
-        if use_goodFeaturesToTrack:
+        if use_goodFeaturesToTrack and (mask is None or bool(np.all(mask))):
+            # the reference's own call (mask all 255, klt.py:214-226) on the GPU: cv2's arithmetic, cv2's corner list
+            fp = self._feature_params
+            points = _ops.good_features_to_track(img, fp["maxCorners"], fp["qualityLevel"], fp["minDistance"], fp["blockSize"])
+        elif use_goodFeaturesToTrack:
             points = cv2.goodFeaturesToTrack(img, mask=mask, **self._feature_params)
         else:
             dst = cv2.dilate(cv2.cornerHarris(img, 2, 3, 0.04), None)

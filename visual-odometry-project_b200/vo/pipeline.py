@@ -10,7 +10,7 @@ from . import _native as nat
 
 NCOUNTS = 12
 SUMMARY_DOUBLES = 18
-DETECTOR_NONE, DETECTOR_HARRIS = 0, 1
+DETECTOR_NONE, DETECTOR_HARRIS, DETECTOR_GFTT = 0, 1, 2
 COUNT_NAMES = ("n_rows", "n_tracked", "n_kept", "p3p_N", "n_inliers", "n_candidates", "n_tri", "flags", "n_iterations",
                "draws", "n_behind", "gn_iters")
 
@@ -22,6 +22,7 @@ class PipelineParams(C.Structure):
                 ("klt_epsilon", C.c_double), ("klt_min_eig", C.c_double), ("klt_error_threshold", C.c_float),
                 ("redetect_fraction", C.c_double), ("detector", C.c_int), ("det_max_corners", C.c_int),
                 ("patch_size", C.c_int), ("kappa", C.c_double), ("nms_radius", C.c_int),
+                ("gftt_quality", C.c_double), ("gftt_min_distance", C.c_double), ("gftt_block_size", C.c_int),
                 ("K", C.c_double * 9), ("Kinv", C.c_double * 9),
                 ("p3p_threshold", C.c_double), ("p3p_inclusive", C.c_int),
                 ("ransac_confidence", C.c_double), ("ransac_outlier_ratio", C.c_double), ("ransac_log1mconf", C.c_double),
@@ -52,7 +53,7 @@ def rng_from_state6(state6) -> np.random.Generator:
 
 class Pipeline:
     def __init__(self, n_seq, H, W, K, *, capacity=2048, detector=DETECTOR_HARRIS, det_max_corners=1000, patch_size=9,
-                 kappa=0.09, nms_radius=5, klt_win=17, klt_max_level=2, klt_max_iters=10, klt_epsilon=0.03,
+                 kappa=0.09, nms_radius=5, gftt_quality=0.01, gftt_min_distance=8.0, gftt_block_size=7, klt_win=17, klt_max_level=2, klt_max_iters=10, klt_epsilon=0.03,
                  klt_min_eig=1e-4, klt_error_threshold=100.0, redetect_fraction=0.8, p3p_threshold=1.25,
                  p3p_opencv=False, confidence=0.9999, outlier_ratio=0.9, max_iterations=10000, refine=True,
                  bearing_threshold=0.0075, tri_opencv=True, rng_seed=2023, ctx=None):
@@ -66,6 +67,7 @@ class Pipeline:
         p.redetect_fraction = float(redetect_fraction)
         p.detector, p.det_max_corners = int(detector), int(det_max_corners)
         p.patch_size, p.kappa, p.nms_radius = int(patch_size), float(kappa), int(nms_radius)
+        p.gftt_quality, p.gftt_min_distance, p.gftt_block_size = float(gftt_quality), float(gftt_min_distance), int(gftt_block_size)
         for i, v in enumerate(np.asarray(K, dtype=np.float64).reshape(9)):
             p.K[i] = float(v)
         for i, v in enumerate(np.asarray(Kinv, dtype=np.float64).reshape(9)):
@@ -182,7 +184,7 @@ class Pipeline:
                   "vo_pipeline_write_table_host")
 
     def read_detections(self, seq):
-        xy = np.empty((self.params.det_max_corners, 2), np.int32)
+        xy = np.empty((self.params.det_max_corners, 2), np.float32 if self.params.detector == DETECTOR_GFTT else np.int32)
         n = C.c_int()
         nat.check(nat.lib().vo_pipeline_read_detections_host(self._h, int(seq), nat.ptr(xy), C.byref(n)), "vo_pipeline_read_detections_host")
         return xy[: n.value].copy()
