@@ -448,6 +448,7 @@ def main():
 
     for i in range(1, warmup + 1):
         step_dev(pl, i)
+    pl.sync_dev(stream)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -457,6 +458,7 @@ def main():
     e0.record(tstream)
     for i in range(args.steps):
         step_dev(pl, warmup + 1 + i)
+    pl.sync_dev(stream)                      # the last step's pose / update / detector kernels (internal streams) count
     e1.record(tstream)
     barrier()
     launches = ctx.launch_count() - l0
@@ -524,6 +526,7 @@ def main():
         e0.record(tstream)
         for i in range(n1):
             step_dev(pl1, 6 + i)
+        pl1.sync_dev(stream)
         e1.record(tstream)
         torch.cuda.synchronize()
         ms1 = e0.elapsed_time(e1) / n1

@@ -293,6 +293,10 @@ int vo_pipeline_prime_host(vo_pipeline* pl, const uint8_t* h_frames, int init_ta
  * of the last step_dev is at vo_pipeline_summary_dev().                                                          */
 int vo_pipeline_step_dev(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, size_t frame_stride, void* stream);
 const double* vo_pipeline_summary_dev(vo_pipeline* pl);
+/* A step's detector and its pose / state-update kernels run on internal streams and may still be in flight when
+ * step_dev returns control to `stream` (they run under the NEXT step's tracker).  vo_pipeline_sync_dev makes `stream`
+ * wait for them: call it before timing events, before reading the summary, before destroying the frames' memory.   */
+int vo_pipeline_sync_dev(vo_pipeline* pl, void* stream);
 /* Host-buffer steps, pipelined like vo_frontend_*: prefetch uploads the NEXT step's frames (tightly packed) under the
  * current step, submit enqueues the step and the download of its summary, wait blocks for the oldest submitted step. */
 int vo_pipeline_prefetch_host(vo_pipeline* pl, const uint8_t* h_frames);

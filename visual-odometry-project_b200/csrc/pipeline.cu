@@ -105,7 +105,9 @@ struct PipeTable {          // every array is [n_seq][capacity] rows
 };
 
 struct PipeSeq {            // per-sequence scalars
-    int* n_rows;            // rows in the current table
+    int* n_rows;            // rows in the current table (regroup writes it, the next step's append may grow it)
+    int* n_keep;            // rows after the last regroup: what pose / update of that step work on (they may still be
+                            // running when the next step's append grows n_rows)
     int* n_tri;             // leading rows that were triangulated before this frame (the P3P population)
     int* num_features;      // klt.py:49 / 114  _num_features
     int* n_iterations;      // RANSAC.n_iterations, carried between frames (ransac.py:56,120)
@@ -233,6 +235,7 @@ pipe_regroup_kernel(PipeTable A, PipeTable B, PipeSeq Q, PipeParams P, const flo
         const int ap = Q.appended[s];
         cnt[7] = (ap != 0 ? 1 : 0) | (ap < 0 ? 4 : 0);
         Q.n_rows[s] = c2 + c1 + c0;
+        Q.n_keep[s] = c2 + c1 + c0;
         Q.n_tri[s] = c2;
     }
 }
@@ -579,7 +582,7 @@ pipe_update_kernel(PipeTable T, PipeSeq Q, PipeParams P, const uint8_t* __restri
     __shared__ double s_c2w[12], s_w2c[12], s_w2c_prev[12], s_proj2[12];
     __shared__ int s_ncand, s_nbehind, s_ntri;
     const int s = blockIdx.x, tid = threadIdx.x;
-    const int C = P.C, n = Q.n_rows[s], N = Q.n_tri[s];
+    const int C = P.C, n = Q.n_keep[s], N = Q.n_tri[s];
     const size_t base = (size_t)s * C;
     int* cnt = Q.counts + (size_t)s * VO_PIPE_NCOUNTS;
     const bool pose_ok = !(cnt[7] & 2);
@@ -725,7 +728,7 @@ pipe_init_from_det_kernel(PipeTable T, PipeSeq Q, PipeParams P, const int* __res
         double* p = T.pose + r * 12;
         for (int k = 0; k < 12; k++) p[k] = (k == 0 || k == 5 || k == 10) ? 1.0 : 0.0;
     }
-    if (threadIdx.x == 0) { Q.n_rows[s] = m; Q.n_tri[s] = 0; Q.num_features[s] = det_n[s]; Q.appended[s] = 0; }
+    if (threadIdx.x == 0) { Q.n_rows[s] = m; Q.n_keep[s] = m; Q.n_tri[s] = 0; Q.num_features[s] = det_n[s]; Q.appended[s] = 0; }
 }
 
 // test hook: n_draws samples of Generator.choice(arange(N), size=4, replace=False) from a given PCG64 state
@@ -765,9 +768,13 @@ struct vo_pipeline {
     double* summary[2] = {nullptr, nullptr};
     // host entry point: staging for tightly packed frames (two sets), streams, events
     uint8_t* stage[2] = {nullptr, nullptr};
-    cudaStream_t copy_stream = nullptr, down_stream = nullptr, side = nullptr;
+    // a step is spread over three streams: the caller's (pyramid, append, tracker, regroup), `side` (detector on the new
+    // frame) and `pose_stream` (RANSAC + refinement, state update).  The latency-bound per-sequence kernels of step t
+    // (one CTA per sequence) run under the tracker of step t + 1: nothing the tracker reads (keypoints, row counts) is
+    // written after the regroup.
+    cudaStream_t copy_stream = nullptr, down_stream = nullptr, side = nullptr, pose_stream = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_res[2] = {nullptr, nullptr};
-    cudaEvent_t ev_level0 = nullptr, ev_det = nullptr, ev_fork = nullptr;
+    cudaEvent_t ev_level0 = nullptr, ev_det = nullptr, ev_fork = nullptr, ev_rg = nullptr, ev_upd = nullptr;
     int stage_next = 0, prefetched = 0, in_flight = 0, sub_next = 0;
     size_t pose_smem = 0;
 };
@@ -832,6 +839,7 @@ int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* prm, vo_pipeline**
             o_t[t][0] = carve(S * C * 8); o_t[t][1] = carve(S * C * 8); o_t[t][2] = carve(S * C);
             o_t[t][3] = carve(S * C * 24); o_t[t][4] = carve(S * C * 96); o_t[t][5] = carve(S * C);
         }
+        const size_t o_nk = carve(S * 4);
         const size_t o_nr = carve(S * 4), o_nt = carve(S * 4), o_nf = carve(S * 4), o_ni = carve(S * 4), o_ap = carve(S * 4);
         const size_t o_cw = carve(S * 96), o_cp = carve(S * 96), o_wc = carve(S * 96), o_wp = carve(S * 96), o_pm = carve(S * 96);
         const size_t o_rng = carve(S * sizeof(PipeRng)), o_cnt = carve(S * VO_PIPE_NCOUNTS * 4);
@@ -850,6 +858,7 @@ int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* prm, vo_pipeline**
             pl->tab[t].land = (double*)(b + o_t[t][3]); pl->tab[t].pose = (double*)(b + o_t[t][4]); pl->tab[t].cand = b + o_t[t][5];
         }
         PipeSeq& q = pl->seq;
+        q.n_keep = (int*)(b + o_nk);
         q.n_rows = (int*)(b + o_nr); q.n_tri = (int*)(b + o_nt); q.num_features = (int*)(b + o_nf); q.n_iterations = (int*)(b + o_ni);
         q.appended = (int*)(b + o_ap);
         q.c2w = (double*)(b + o_cw); q.c2w_prev = (double*)(b + o_cp); q.w2c = (double*)(b + o_wc); q.w2c_prev = (double*)(b + o_wp);
@@ -877,7 +886,10 @@ int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* prm, vo_pipeline**
             int lo_p = 0, hi_p = 0;
             VO_CUDA(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
             VO_CUDA(cudaStreamCreateWithPriority(&pl->side, cudaStreamNonBlocking, hi_p));
+            VO_CUDA(cudaStreamCreateWithPriority(&pl->pose_stream, cudaStreamNonBlocking, hi_p));
         }
+        VO_CUDA(cudaEventCreateWithFlags(&pl->ev_rg, cudaEventDisableTiming));
+        VO_CUDA(cudaEventCreateWithFlags(&pl->ev_upd, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) {
             VO_CUDA(cudaEventCreateWithFlags(&pl->ev_up[i], cudaEventDisableTiming));
             VO_CUDA(cudaEventCreateWithFlags(&pl->ev_done[i], cudaEventDisableTiming));
@@ -908,9 +920,9 @@ void vo_pipeline_destroy(vo_pipeline* pl) {
     if (!pl) return;
     cudaSetDevice(pl->ctx->device);
     cudaStreamSynchronize(pl->ctx->stream);
-    for (cudaStream_t s : {pl->copy_stream, pl->down_stream, pl->side}) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+    for (cudaStream_t s : {pl->copy_stream, pl->down_stream, pl->side, pl->pose_stream}) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
     for (int i = 0; i < 2; i++) for (cudaEvent_t ev : {pl->ev_up[i], pl->ev_done[i], pl->ev_res[i]}) if (ev) cudaEventDestroy(ev);
-    for (cudaEvent_t ev : {pl->ev_level0, pl->ev_det, pl->ev_fork}) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : {pl->ev_level0, pl->ev_det, pl->ev_fork, pl->ev_rg, pl->ev_upd}) if (ev) cudaEventDestroy(ev);
     if (pl->base) cudaFree(pl->base);
     (void)cudaGetLastError();
     delete pl;
@@ -956,21 +968,30 @@ int vo_pipeline_prime_host(vo_pipeline* pl, const uint8_t* h_frames, int init_ta
     return VO_OK;
 }
 
-// one step on stream s: frames (device) -> tables advanced, summary written to set `slot`
-static int pipe_step(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, size_t frame_stride, int slot, cudaStream_t s) {
+// one step: frames (device) -> tables advanced, summary written to set `slot`.  Work is enqueued on s and on the two
+// internal streams; ev_upd fires when the step's results (tables, summary) are complete.  `staging_free` (optional) is
+// recorded as soon as d_frames has been consumed (after the pyramid's level-0 copy).
+static int pipe_step(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, size_t frame_stride, int slot, cudaStream_t s,
+                     cudaEvent_t staging_free = nullptr, cudaEvent_t slot_free = nullptr) {
     const vo_pipeline_params& p = pl->p;
     vo_ctx* ctx = pl->ctx;
     VO_REQUIRE(pl->primed, "vo_pipeline step: call vo_pipeline_prime_* first (there is no previous frame yet)");
     const int cur = pl->cur, nx = 1 - cur;
     int rc;
+    const bool fork = !ctx->env_frontend_serial;
+    cudaStream_t sd = fork ? pl->side : s, sp = fork ? pl->pose_stream : s;
+    // the detector of the previous step has left its corners (what this step's append may take)
+    if (fork && p.detector != VO_DETECTOR_NONE) VO_CUDA(cudaStreamWaitEvent(s, pl->ev_det, 0));
     // new frame -> pyramid; the detector runs on it on the side stream (its corners are what the NEXT step appends
     // when a sequence runs low: klt.py:207-230 detects on the old frame, which is this step's new frame)
     if ((rc = vo_launch_klt_pyramid(ctx, d_frames, p.n_seq, p.H, p.W, pitch, frame_stride, p.klt_max_level, p.klt_win,
                                     pl->pyr[nx], s, pl->ev_level0))) return rc;
-    const bool fork = p.detector != VO_DETECTOR_NONE && !ctx->env_frontend_serial;
-    cudaStream_t sd = fork ? pl->side : s;
-    if (fork) VO_CUDA(cudaStreamWaitEvent(sd, pl->ev_level0, 0));
-    if (fork) { if ((rc = pipe_run_detector(pl, pl->pyr[nx], nx, sd))) return rc; VO_CUDA(cudaEventRecord(pl->ev_det, sd)); }
+    if (staging_free) VO_CUDA(cudaEventRecord(staging_free, s));
+    if (p.detector != VO_DETECTOR_NONE && fork) {
+        VO_CUDA(cudaStreamWaitEvent(sd, pl->ev_level0, 0));
+        if ((rc = pipe_run_detector(pl, pl->pyr[nx], nx, sd))) return rc;
+        VO_CUDA(cudaEventRecord(pl->ev_det, sd));
+    }
     if (p.detector != VO_DETECTOR_NONE) {
         const bool fl = p.detector == VO_DETECTOR_GFTT;
         pipe_append_kernel<<<p.n_seq, 256, 0, s>>>(pl->tab[cur], pl->seq, pl->dp, fl ? nullptr : pl->det_xy[cur],
@@ -983,20 +1004,44 @@ static int pipe_step(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, siz
     if ((rc = vo_launch_klt_track(ctx, pl->pyr[cur], pl->pyr[nx], p.n_seq, p.H, p.W, p.klt_max_level, p.klt_win, p.klt_max_iters,
                                   p.klt_epsilon, p.klt_min_eig, (const float*)pl->tab[cur].kp, p.capacity, (float*)pl->nxt, pl->status,
                                   pl->err, s, pl->seq.n_rows))) return rc;
+    // the regroup reads the states the previous step's update wrote
+    if (fork) VO_CUDA(cudaStreamWaitEvent(s, pl->ev_upd, 0));
     pipe_regroup_kernel<<<p.n_seq, RG_THREADS, 0, s>>>(pl->tab[cur], pl->tab[nx], pl->seq, pl->dp, pl->nxt, pl->status, pl->err);
     ctx->launches++;
     VO_CHECK_LAUNCH();
-    pipe_pose_kernel<<<p.n_seq, PO_THREADS, pl->pose_smem, s>>>(pl->tab[nx], pl->seq, pl->dp, pl->inliers);
+    if (fork) {
+        VO_CUDA(cudaEventRecord(pl->ev_rg, s));
+        VO_CUDA(cudaStreamWaitEvent(sp, pl->ev_rg, 0));
+        if (slot_free) VO_CUDA(cudaStreamWaitEvent(sp, slot_free, 0));
+    } else if (slot_free) {
+        VO_CUDA(cudaStreamWaitEvent(s, slot_free, 0));
+    }
+    pipe_pose_kernel<<<p.n_seq, PO_THREADS, pl->pose_smem, sp>>>(pl->tab[nx], pl->seq, pl->dp, pl->inliers);
     ctx->launches++;
     VO_CHECK_LAUNCH();
-    pipe_update_kernel<<<p.n_seq, UP_THREADS, 0, s>>>(pl->tab[nx], pl->seq, pl->dp, pl->inliers, pl->summary[slot]);
+    pipe_update_kernel<<<p.n_seq, UP_THREADS, 0, sp>>>(pl->tab[nx], pl->seq, pl->dp, pl->inliers, pl->summary[slot]);
     ctx->launches++;
     VO_CHECK_LAUNCH();
+    VO_CUDA(cudaEventRecord(pl->ev_upd, sp));
     if (!fork && p.detector != VO_DETECTOR_NONE) { if ((rc = pipe_run_detector(pl, pl->pyr[nx], nx, s))) return rc; }
-    if (fork) VO_CUDA(cudaStreamWaitEvent(s, pl->ev_det, 0));
     pl->cur = nx;
     pl->steps++;
     return VO_OK;
+}
+
+// make `stream` wait for everything the steps enqueued so far left running on the internal streams
+static int pipe_join(vo_pipeline* pl, cudaStream_t s) {
+    if (!pl->ctx->env_frontend_serial && pl->steps > 0) {
+        VO_CUDA(cudaStreamWaitEvent(s, pl->ev_upd, 0));
+        if (pl->p.detector != VO_DETECTOR_NONE) VO_CUDA(cudaStreamWaitEvent(s, pl->ev_det, 0));
+    }
+    return VO_OK;
+}
+
+int vo_pipeline_sync_dev(vo_pipeline* pl, void* stream) {
+    VO_REQUIRE(pl, "vo_pipeline_sync_dev: null argument");
+    VO_CUDA(cudaSetDevice(pl->ctx->device));
+    return pipe_join(pl, stream ? (cudaStream_t)stream : pl->ctx->stream);
 }
 
 int vo_pipeline_step_dev(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, size_t frame_stride, void* stream) {
@@ -1043,13 +1088,13 @@ int vo_pipeline_submit_host(vo_pipeline* pl, const uint8_t* h_frames, double* h_
         pl->stage_next = 1 - set;
     }
     const int slot = pl->sub_next;
-    VO_CUDA(cudaStreamWaitEvent(s, pl->ev_res[slot], 0));       // summary set `slot` has left the device
     VO_CUDA(cudaStreamWaitEvent(s, pl->ev_up[set], 0));
     const size_t npx = (size_t)pl->p.H * pl->p.W;
-    int rc = pipe_step(pl, pl->stage[set], (size_t)pl->p.W, npx, slot, s);
+    // ev_done[set]: the staged frames have been consumed; ev_res[slot]: summary set `slot` has left the device
+    int rc = pipe_step(pl, pl->stage[set], (size_t)pl->p.W, npx, slot, s, pl->ev_done[set], pl->ev_res[slot]);
     if (rc) return rc;
-    VO_CUDA(cudaEventRecord(pl->ev_done[set], s));
-    VO_CUDA(cudaStreamWaitEvent(pl->down_stream, pl->ev_done[set], 0));
+    VO_CUDA(cudaStreamWaitEvent(pl->down_stream, pl->ev_upd, 0));
+    if (pl->ctx->env_frontend_serial) VO_CUDA(cudaStreamWaitEvent(pl->down_stream, pl->ev_done[set], 0));
     VO_CUDA(cudaMemcpyAsync(h_summary, pl->summary[slot], (size_t)pl->p.n_seq * VO_PIPE_SUMMARY_DOUBLES * 8, cudaMemcpyDeviceToHost,
                             pl->down_stream));
     VO_CUDA(cudaEventRecord(pl->ev_res[slot], pl->down_stream));
@@ -1138,6 +1183,7 @@ int vo_pipeline_write_table_host(vo_pipeline* pl, int seq, int n_rows, const flo
     }
     if (n_rows >= 0) {                                       // n_rows < 0: scalars only, the rows stay
         VO_CUDA(cudaMemcpy(pl->seq.n_rows + seq, &n_rows, 4, cudaMemcpyHostToDevice));
+        VO_CUDA(cudaMemcpy(pl->seq.n_keep + seq, &n_rows, 4, cudaMemcpyHostToDevice));
         int n_tri = 0;
         for (int i = 0; i < n_rows; i++) n_tri += h_state[i] == 2;
         VO_CUDA(cudaMemcpy(pl->seq.n_tri + seq, &n_tri, 4, cudaMemcpyHostToDevice));

@@ -85,6 +85,7 @@ def lib():
             "vo_pipeline_prime_host": (i32, [vp, vp, i32]),
             "vo_pipeline_step_dev": (i32, [vp, vp, sz, sz, vp]),
             "vo_pipeline_summary_dev": (vp, [vp]),
+            "vo_pipeline_sync_dev": (i32, [vp, vp]),
             "vo_pipeline_prefetch_host": (i32, [vp, vp]),
             "vo_pipeline_submit_host": (i32, [vp, vp, vp]),
             "vo_pipeline_wait_host": (i32, [vp]),

@@ -136,6 +136,10 @@ class Pipeline:
     def step_dev(self, d_frames, pitch, frame_stride, stream=0):
         nat.check(nat.lib().vo_pipeline_step_dev(self._h, d_frames, pitch, frame_stride, stream or None), "vo_pipeline_step_dev")
 
+    def sync_dev(self, stream=0):
+        """Make `stream` wait for the detector / pose / update kernels the last steps left running on internal streams."""
+        nat.check(nat.lib().vo_pipeline_sync_dev(self._h, stream or None), "vo_pipeline_sync_dev")
+
     def summary_dev(self) -> int:
         return int(nat.lib().vo_pipeline_summary_dev(self._h) or 0)
 
