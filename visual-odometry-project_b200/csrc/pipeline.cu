@@ -77,6 +77,37 @@ __device__ __forceinline__ unsigned int bounded32(PipeRng& r, unsigned int rng) 
     }
     return (unsigned int)(m >> 32);
 }
+// The same from pre-drawn 32-bit words (one per bounded draw): false when a draw would have been rejected (probability
+// ~N / 2^32 per draw) -- the caller then falls back to the sequential sampler.
+__device__ __forceinline__ bool bounded32_from(unsigned int word, unsigned int rng, unsigned int& out) {
+    const unsigned int rng_excl = rng + 1u;
+    const unsigned long long m = (unsigned long long)word * rng_excl;
+    const unsigned int leftover = (unsigned int)(m & 0xffffffffull);
+    out = (unsigned int)(m >> 32);
+    if (leftover < rng_excl) {
+        const unsigned int threshold = (0xffffffffu - rng) % rng_excl;
+        if (leftover < threshold) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ bool choice4_from(const unsigned int* w, int N, int* out) {      // needs N > 4 (7 words)
+    bool ok = true;
+    for (int k = 0; k < 4; k++) {
+        const int j = N - 4 + k;
+        unsigned int v;
+        ok &= bounded32_from(w[k], (unsigned int)j, v);
+        bool dup = false;
+        for (int q = 0; q < k; q++) dup |= (out[q] == (int)v);
+        out[k] = dup ? j : (int)v;
+    }
+    for (int i = 3; i >= 1; i--) {
+        unsigned int j;
+        ok &= bounded32_from(w[7 - i], (unsigned int)i, j);
+        const int tmp = out[i]; out[i] = out[j]; out[j] = tmp;
+    }
+    return ok;
+}
+
 // Floyd's algorithm + the final shuffle, as numpy/random/_generator.pyx does for replace=False, p=None, small sizes
 __device__ __forceinline__ void choice4(PipeRng& r, int N, int* out) {
     for (int k = 0; k < 4; k++) {
@@ -241,7 +272,9 @@ pipe_regroup_kernel(PipeTable A, PipeTable B, PipeSeq Q, PipeParams P, const flo
 }
 
 // ---- pose: RANSAC (ransac.py:69-129 + p3p.py:51-108) and refinement (p3p.py:188-213) ------------------
-constexpr int PO_WARPS = 16, PO_THREADS = PO_WARPS * 32, PO_HYP = 16;
+// 4 warps per sequence: the kernel is a chain of short dependent phases (one CTA per sequence, one per SM), so a small
+// CTA costs no time and leaves three quarters of the SM's registers to the tracker CTAs it runs under
+constexpr int PO_WARPS = 4, PO_THREADS = PO_WARPS * 32, PO_HYP = 16;
 constexpr int GN_MAX_ITERS = 30;
 
 __device__ __forceinline__ int ransac_iterations(int best, int N, double log1mconf, int max_iter) {
@@ -428,7 +461,8 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
     __shared__ double s_pose[12];
     __shared__ int s_idx[PO_HYP][4], s_valid[PO_HYP], s_cnt[PO_HYP];
     __shared__ PipeRng s_snap[PO_HYP + 1];
-    __shared__ int s_ctl[8];      // 0 stop, 1 n, 2 best, 3 n_iter, 4 draws, 5 flags, 6 accept/continue
+    __shared__ int s_ctl[8];      // 0 stop, 1 n, 2 best, 3 n_iter, 4 draws, 5 flags, 7 parallel sampler ok
+    __shared__ unsigned int s_words[PO_HYP * 7];
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = Q.n_tri[s];
     const size_t base = (size_t)s * C;
@@ -453,7 +487,25 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
     }
     const long long draw_cap = 10ll * P.max_iter + 4096;
     while (true) {
-        if (tid == 0) {                                   // the sequence's sample stream, 16 draws ahead
+        // the sequence's sample stream, 16 samples ahead: thread 0 draws the 16 x 7 words a sample needs when nothing is
+        // rejected (the only serial part: 56 steps of the 128-bit LCG), 16 threads turn them into index sets
+        if (tid == 0) {
+            PipeRng r = s_snap[0];
+            for (int k = 0; k < PO_HYP * 7; k++) {
+                if (k % 7 == 0) s_snap[k / 7] = r;
+                s_words[k] = pcg64_next32(r);
+            }
+            s_snap[PO_HYP] = r;
+            s_ctl[7] = (N > 4) ? 1 : 0;                   // N == 4: the first bounded draw of a sample consumes nothing
+        }
+        __syncthreads();
+        if (tid < PO_HYP && N > 4) {
+            int idx[4];
+            if (!choice4_from(s_words + tid * 7, N, idx)) s_ctl[7] = 0;
+            for (int k = 0; k < 4; k++) s_idx[tid][k] = idx[k];
+        }
+        __syncthreads();
+        if (tid == 0 && !s_ctl[7]) {                      // a rejected draw shifts everything after it: redo in sequence
             PipeRng r = s_snap[0];
             for (int j = 0; j < PO_HYP; j++) {
                 s_snap[j] = r;
@@ -475,12 +527,12 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
             for (int i = 0; i < 12; i++) s_models[tid][i] = bm[i];
         }
         __syncthreads();
-        {                                                 // error_fn + threshold (p3p.py:81-108, ransac.py:104-106)
+        for (int h = warp; h < PO_HYP; h += PO_WARPS) {    // error_fn + threshold (p3p.py:81-108, ransac.py:104-106)
             int c = 0;
-            if (s_valid[warp]) {
+            if (s_valid[h]) {
                 double m[12];
 #pragma unroll
-                for (int i = 0; i < 12; i++) m[i] = s_models[warp][i];
+                for (int i = 0; i < 12; i++) m[i] = s_models[h][i];
                 for (int b0 = 0; b0 < N; b0 += 64) {
                     const int i0 = b0 + lane, i1 = i0 + 32;
                     bool in0 = false, in1 = false;
@@ -489,7 +541,7 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
                     c += __popc(__ballot_sync(0xffffffffu, in0)) + __popc(__ballot_sync(0xffffffffu, in1));
                 }
             }
-            if (lane == 0) s_cnt[warp] = c;
+            if (lane == 0) s_cnt[h] = c;
         }
         __syncthreads();
         if (tid == 0) {                                   // ransac.py:90-121 over the 16 pre-scored samples
