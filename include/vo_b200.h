@@ -44,6 +44,9 @@ void* vo_ctx_stream(vo_ctx* ctx);
 /* synchronous device -> host copy of a resident result buffer (after a device-wide sync) */
 int vo_copy_to_host(vo_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 
+/* measured FP64 fused-multiply-add rate of the device in GFLOP/s (the ceiling the P3P kernels are compared with) */
+int vo_test_dfma_peak(vo_ctx* ctx, double* gflops);
+
 /* ---- Harris: src/vo/features/harris.py ---------------------------------------------------- */
 /* harris.py:102-137  float64 score map [n_frames][H][W], zero border of patch_size/2+1 pixels.  */
 int vo_harris_response_dev(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch,

@@ -46,6 +46,18 @@ int vo_pinned_reserve(VoBuf* b, size_t bytes) {
     return VO_OK;
 }
 
+// Measured FP64 ceiling for the roofline of the P3P kernels: 8 independent DFMA chains per thread, every SM full.
+__global__ void __launch_bounds__(256)
+dfma_peak_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+        a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 static inline cudaStream_t pick_stream(vo_ctx* ctx, void* stream) {
     return stream ? (cudaStream_t)stream : ctx->stream;
 }
@@ -114,6 +126,28 @@ int vo_copy_to_host(vo_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
     VO_CUDA(cudaSetDevice(ctx->device));
     VO_CUDA(cudaDeviceSynchronize());
     VO_CUDA(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return VO_OK;
+}
+
+// FP64 fused multiply-add rate of this GPU in GFLOP/s (2 flop per DFMA), measured with CUDA events.
+int vo_test_dfma_peak(vo_ctx* ctx, double* gflops) {
+    VO_REQUIRE(ctx && gflops, "vo_test_dfma_peak: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 4096;
+    int rc = vo_buf_reserve(&ctx->scratch[12], (size_t)blocks * threads * 8);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    VO_CUDA(cudaEventCreate(&e0)); VO_CUDA(cudaEventCreate(&e1));
+    dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->scratch[12].p, iters);       // warm-up
+    VO_CUDA(cudaEventRecord(e0, ctx->stream));
+    for (int r = 0; r < 5; r++) dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>((double*)ctx->scratch[12].p, iters);
+    VO_CUDA(cudaEventRecord(e1, ctx->stream));
+    VO_CUDA(cudaEventSynchronize(e1));
+    ctx->launches += 6;
+    float ms = 0.f;
+    VO_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *gflops = 5.0 * blocks * threads * (double)iters * 8.0 * 2.0 / (ms * 1e-3) / 1e9;
     return VO_OK;
 }
 

@@ -100,6 +100,7 @@ def lib():
             "vo_bgr2gray_host": (i32, [vp, vp, i32, i32, i32, vp]),
             "vo_gftt_dev": (i32, [vp, vp, i32, i32, i32, sz, sz, i32, dbl, dbl, i32, vp, vp, vp, vp, vp]),
             "vo_gftt_host": (i32, [vp, vp, i32, i32, i32, i32, dbl, dbl, i32, vp, vp, vp, vp]),
+            "vo_test_dfma_peak": (i32, [vp, vp]),
             "vo_refine_pose_dev": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
             "vo_refine_pose_host": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]),
         })
