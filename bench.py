@@ -127,7 +127,7 @@ class World:
 
 def pipeline_kwargs():
     return dict(capacity=CAPACITY, det_max_corners=KP, p3p_threshold=P3P_THR, p3p_opencv=False, confidence=P3P_CONF,
-                max_iterations=P3P_MAX_ITER, refine=True, tri_opencv=True)
+                max_iterations=P3P_MAX_ITER, refine=os.environ.get("VO_BENCH_NO_REFINE") != "1", tri_opencv=True)
 
 
 def start_tables(pl, S):
