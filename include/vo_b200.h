@@ -131,8 +131,10 @@ int vo_bgr2gray_host(vo_ctx* ctx, const uint8_t* h_bgr, int n_frames, int H, int
 /* ---- P3P + RANSAC: src/vo/pose_estimation/p3p.py:51-108, src/vo/algorithms/ransac.py:69-129 --- */
 /* For every hypothesis h (4 sample indices: 3 for P3P, the 4th disambiguates, as cv2.solvePnP with
  * SOLVEPNP_P3P does) solve the pose, count reprojection inliers (squared pixel error < threshold,
- * p3p.py:104-108 / ransac.py:104-106; with inclusive != 0 `<=`, the rule of cv2.solvePnPRansac that the
- * reference's use_opencv=True path applies, p3p.py:142-151), and return per-hypothesis models, validity and counts.
+ * p3p.py:104-108 / ransac.py:104-106; with inclusive != 0 the rule of cv2.solvePnPRansac, which the reference's
+ * use_opencv=True path runs (p3p.py:142-151): projections rounded to float32, squared distance in float32,
+ * err <= (float)threshold with threshold = reprojectionError^2; the caller passes landmarks rounded to float32, as
+ * solvePnPRansac converts them), and return per-hypothesis models, validity and counts.
  * landmarks float64 [n_frames][N][3], keypoints float64 [n_frames][N][2], K9 float64 [9] row-major (HOST pointer),
  * sample_idx int32 [n_frames][n_hyp][4].  models float64 [n_frames][n_hyp][12] = R (row-major) | t. */
 int vo_p3p_ransac_score_dev(vo_ctx* ctx, const double* d_landmarks, const double* d_keypoints, int n_frames,
@@ -278,7 +280,11 @@ typedef struct {
     double gftt_quality, gftt_min_distance; int gftt_block_size;   /* klt.py:24-26                                 */
     double K[9], Kinv[9];                            /* intrinsics and their inverse AS THE HOST COMPUTES IT
                                                         (camera.py:92: np.linalg.inv in K's own dtype)             */
-    double p3p_threshold; int p3p_inclusive;         /* p3p.py:20 / ransac.py:105; inclusive = cv2's `<=` rule     */
+    double p3p_threshold; int p3p_inclusive;         /* p3p.py:20.  inclusive = 0: the reference's own RANSAC (ransac.py: numpy
+                                                        PCG64 stream, err < threshold, state carried between frames);
+                                                        1: cv2.solvePnPRansac restated (p3p.py:142-151: cv::RNG subsets, float32
+                                                        points and errors, err <= threshold = reprojectionError^2,
+                                                        RANSACUpdateNumIters; nothing carried between frames)        */
     double ransac_confidence, ransac_outlier_ratio;  /* p3p.py:22-23                                               */
     double ransac_log1mconf;                         /* log(1 - confidence) as the host evaluates it (0 = compute) */
     int ransac_max_iterations, ransac_initial_iterations; /* p3p.py:24; 0 = derive from the outlier ratio          */

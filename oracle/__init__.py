@@ -333,3 +333,93 @@ class RansacP3P:
                 self.n_iterations = int(min(self.max_iterations, self._n_iter()))
             n += 1
         return best_model, best_inl
+
+
+# ----------------------------------------------------------------------------
+# cv2.solvePnPRansac(flags=SOLVEPNP_P3P)  (reference: src/vo/pose_estimation/p3p.py:142-165, the use_opencv=True path
+# that src/main.py takes).  OpenCV is a third-party dependency (not vendored in /root/reference); restated from
+# calib3d/src/solvepnp.cpp (solvePnPRansac, PnPRansacCallback) and calib3d/src/ptsetreg.cpp
+# (RANSACPointSetRegistrator::run / getSubset / findInliers, RANSACUpdateNumIters) and core's cv::RNG:
+#   - object and image points are converted to float32 before anything else;
+#   - every run starts from RNG(0xffffffffffffffff); a subset is 4 distinct draws of uniform(0, N) = next() % N,
+#     next(): state = (uint32)state * 4164903690 + (state >> 32);
+#   - the model is solvePnP(P3P) of the subset (three points solve, the fourth picks the root); a failed subset still
+#     counts as an iteration;
+#   - the error of a point is the squared distance between the float32 image point and the float32-rounded projection,
+#     evaluated in float32; inliers are err <= (float)(reprojectionError^2);
+#   - a model is kept when its inlier count exceeds max(best, 3); then niters = RANSACUpdateNumIters(confidence,
+#     (N - good) / N, 4, niters) with cvRound;
+# Pinned (tests/test_oracle_golden.py): inlier masks EQUAL to cv2.solvePnPRansac's on random problems and on the
+# reference's own KITTI run (tests/golden/loop.npz cv_f3_inliers).
+# ----------------------------------------------------------------------------
+class CvRNG:
+    def __init__(self, state=0xFFFFFFFFFFFFFFFF):
+        self.state = state
+
+    def next(self):
+        self.state = ((self.state & 0xFFFFFFFF) * 4164903690 + (self.state >> 32)) & 0xFFFFFFFFFFFFFFFF
+        return self.state & 0xFFFFFFFF
+
+    def uniform(self, a, b):
+        return a if a == b else a + self.next() % (b - a)
+
+
+def cv_update_num_iters(p, ep, model_points, max_iters):
+    """RANSACUpdateNumIters (ptsetreg.cpp)."""
+    p = min(max(p, 0.0), 1.0)
+    ep = min(max(ep, 0.0), 1.0)
+    tiny = float(np.finfo(np.float64).tiny)
+    num = max(1.0 - p, tiny)
+    denom = 1.0 - (1.0 - ep) ** model_points
+    if denom < tiny:
+        return 0
+    num, denom = float(np.log(num)), float(np.log(denom))
+    return max_iters if (denom >= 0 or -num >= max_iters * (-denom)) else int(np.rint(num / denom))
+
+
+def cv_subset4(rng: CvRNG, N: int):
+    """RANSACPointSetRegistrator::getSubset for modelPoints = 4 (no degeneracy check for PnP)."""
+    idx = []
+    for _ in range(4):
+        while True:
+            v = rng.uniform(0, N)
+            if v not in idx:
+                break
+        idx.append(v)
+    return idx
+
+
+def cv_reproj_errors_f32(R, t, L32, P32, K):
+    """PnPRansacCallback::computeError: float32 projections, float32 squared distance."""
+    cam = L32 @ np.asarray(R, dtype=np.float64).T + np.asarray(t, dtype=np.float64).reshape(3)
+    with np.errstate(all="ignore"):
+        iz = np.where(cam[:, 2] != 0, 1.0 / cam[:, 2], 1.0)          # cvProjectPoints2: z = z ? 1./z : 1; x *= z
+        x = (cam[:, 0] * iz) * K[0, 0] + K[0, 2]
+        y = (cam[:, 1] * iz) * K[1, 1] + K[1, 2]
+    dx = P32[:, 0] - x.astype(np.float32)
+    dy = P32[:, 1] - y.astype(np.float32)
+    return dx * dx + dy * dy
+
+
+def cv_solve_pnp_ransac_p3p(landmarks, keypoints, K, reproj_error, confidence, max_iters):
+    """-> (best model (R, t) or None, inlier mask, iterations run)."""
+    K = np.asarray(K, dtype=np.float64)
+    L32 = np.asarray(landmarks, dtype=np.float64).reshape(-1, 3).astype(np.float32).astype(np.float64)
+    P32 = np.asarray(keypoints).reshape(-1, 2).astype(np.float32)
+    N = L32.shape[0]
+    rng = CvRNG()
+    niters, best, best_mask, best_model, it = int(max_iters), 0, np.zeros(N, bool), None, 0
+    thr = np.float32(reproj_error * reproj_error)
+    while it < niters:
+        idx = cv_subset4(rng, N)
+        it += 1
+        m = p3p_solve4(L32[idx], P32[idx].astype(np.float64), K)
+        if m is None:
+            continue
+        with np.errstate(invalid="ignore"):
+            mask = cv_reproj_errors_f32(m[0], m[1], L32, P32, K) <= thr
+        good = int(mask.sum())
+        if good > max(best, 3):
+            best, best_mask, best_model = good, mask, m
+            niters = cv_update_num_iters(confidence, (N - good) / N, 4, niters)
+    return best_model, best_mask, it

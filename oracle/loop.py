@@ -241,7 +241,13 @@ class LoopOracle:
         # the reference raises when fewer than 4 landmarks are left (Generator.choice) and loops forever when no sample
         # yields a model; the CUDA pipeline reports "no pose" and keeps the last one -- restated here for those cases
         model, inl = (None, np.zeros(N, bool))
-        if N >= 4:
+        if N >= 4 and self.p3p_opencv:
+            # p3p.py:142-151: cv2.solvePnPRansac (its own generator, restarted at every call; nothing carried over)
+            model, inl, it = oracle.cv_solve_pnp_ransac_p3p(land[:N], kp[:N], self.K64, self.inlier_threshold,
+                                                            self.ransac.confidence, self.ransac.max_iterations)
+            self.ransac.draws += it
+            info["cv_iterations"] = it
+        elif N >= 4:
             model, inl = self.ransac.find_best_model(land[:N], kp[:N].astype(np.float64),
                                                      draw_cap=10 * min(self.ransac.max_iterations, 1 << 24) + 4096)
         info["ransac_n_iterations"] = self.ransac.n_iterations

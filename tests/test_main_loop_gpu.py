@@ -111,23 +111,24 @@ def test_main_py_klt_mode_p3p_reference_ransac():
     assert nat.lib().vo_klt_cache_hits(nat.default_context(0).handle) - hits0 >= 3
 
 
-def test_main_py_default_path_tolerance_pin():
-    """main.py's own configuration (use_opencv=True: the reference calls cv2.solvePnPRansac, whose sample stream is
-    OpenCV's).  Here the same model class and inlier rule run over the numpy sample stream, so the result is pinned by
-    tolerance: refined pose within 5e-3 / 2e-4 of the reference's on the first loop frame, inlier masks with a Jaccard
-    index >= 0.97 (two good minimal models of different samples disagree on the points near the 1.25 px threshold:
-    324 of 331 agree here), the same number of candidates within 10 %."""
+def test_main_py_default_path():
+    """main.py's own configuration (use_opencv=True: the reference calls cv2.solvePnPRansac).  OpenCV's RANSAC is
+    restated (fixed-seed cv::RNG subsets, float32 points and errors, RANSACUpdateNumIters), so the inlier mask of the first
+    loop frame is cv2's own, and with it the states and the candidates; the refined pose is the minimum of the cost the
+    reference hands to scipy (within the distance scipy stops short of it, see test_pipeline_gpu.py)."""
     g, out = run_main(True)
     t = out[3]
+    assert np.array_equal(t["inliers"], g["cv_f3_inliers"])
+    assert np.array_equal(t["state"], g["cv_f3_state"]) and int(t["cand"].sum()) == int(g["cv_f3_n_candidates"])
     ref = g["cv_f3_curr_pose"]
     assert np.abs(t["curr_pose"][:3, :3] - ref[:3, :3]).max() < 2e-4 and np.abs(t["curr_pose"][:3, 3] - ref[:3, 3]).max() < 5e-3
-    a, b = t["inliers"], g["cv_f3_inliers"]
-    assert len(a) == len(b)
-    assert (a & b).sum() / (a | b).sum() >= 0.97
-    assert abs(int(t["cand"].sum()) - int(g["cv_f3_n_candidates"])) <= 0.1 * int(g["cv_f3_n_candidates"]) + 2
     for i in (4, 5):
         ref = g[f"cv_f{i}_curr_pose"]
         assert np.abs(out[i]["curr_pose"][:3, :3] - ref[:3, :3]).max() < 6e-4 and np.abs(out[i]["curr_pose"][:3, 3] - ref[:3, 3]).max() < 1.5e-2
+        a, b = out[i]["inliers"], g[f"cv_f{i}_inliers"]
+        assert len(a) == len(b) or abs(len(a) - len(b)) <= 12          # the populations follow the (1e-3 different) poses
+        if len(a) == len(b):
+            assert (a & b).sum() / (a | b).sum() >= 0.9
 
 
 def test_main_py_harris_mode_runs():

@@ -290,3 +290,49 @@ def test_gftt_oracle_bitexact_vs_cv2(golden):
         im = imgs[6]
         want = cv2.goodFeaturesToTrack(im, maxCorners=300, qualityLevel=q, minDistance=md, blockSize=block).reshape(-1, 2)
         assert np.array_equal(oracle.good_features_to_track(im, 300, q, md, block), want)
+
+
+# ---------------------------------------------------------------------------- cv2.solvePnPRansac (p3p.py:142-165, main.py's path)
+def test_cv_solvepnpransac_restatement_equals_cv2(golden):
+    """The restated OpenCV RANSAC (fixed-seed cv::RNG subsets, float32 points and errors, `<=` rule, RANSACUpdateNumIters)
+    must return cv2.solvePnPRansac's inlier mask exactly: 60 random problems (50-600 points, 5-50 % outliers) and the
+    reference's own frame-3 problem of the KITTI run."""
+    import cv2
+    rng = np.random.default_rng(0)
+    K = np.array([[707.0912, 0, 601.8873], [0, 707.0912, 183.1104], [0, 0, 1.0]])
+    n_exact = 0
+    for trial in range(60):
+        N = int(rng.integers(50, 600))
+        L = rng.uniform(-10, 10, (N, 3))
+        L[:, 2] = rng.uniform(4, 50, N)
+        R = cv2.Rodrigues(rng.normal(0, 0.1, 3).reshape(3, 1))[0]
+        cam = L @ R.T + rng.normal(0, 0.5, 3)
+        uv = cam @ K.T
+        P = uv[:, :2] / uv[:, 2:] + rng.normal(0, 0.4, (N, 2))
+        out = rng.choice(N, int(rng.uniform(0.05, 0.5) * N), replace=False)
+        P[out] += rng.uniform(-50, 50, (len(out), 2))
+        P = P.astype(np.float32)
+        ok, rv, tv, inl = cv2.solvePnPRansac(L, P, K, None, flags=cv2.SOLVEPNP_P3P, iterationsCount=10000, reprojectionError=1.25,
+                                             confidence=0.9999)
+        want = np.zeros(N, bool)
+        want[inl.ravel()] = True
+        model, mask, it = oracle.cv_solve_pnp_ransac_p3p(L, P, K, 1.25, 0.9999, 10000)
+        assert ok and model is not None
+        n_exact += int(np.array_equal(mask, want))
+        if not np.array_equal(mask, want):           # the restated minimal solver is cv2's to ~1e-7 rad: threshold-grazing points may flip
+            d = np.flatnonzero(mask != want)
+            e = oracle.cv_reproj_errors_f32(model[0], model[1], L.astype(np.float32).astype(np.float64), P, K)
+            assert len(d) <= 2 and np.all(np.abs(e[d] - 1.25 ** 2) < 1e-3), (trial, d, e[d])
+    assert n_exact >= 57
+    g = golden("loop")
+    # the reference's frame 3: population = the triangulated rows of the bootstrap table tracked into frame 3
+    from oracle.loop import LoopOracle
+    fr = _kitti_frames()
+    lo = LoopOracle(g["K"], detector=None, refine="gn", p3p_opencv=True, klt=_cv_klt)
+    lo.set_table(g["boot_kp"], g["boot_land"], g["boot_state"], g["boot_track"], g["boot_pose"], g["boot_cand"],
+                 curr_pose=g["boot_curr_pose"], num_features=int(g["num_features"]))
+    info = lo.step(fr[2], fr[3])
+    assert np.array_equal(info["inliers"], g["cv_f3_inliers"])                       # cv2's own mask, through the reference
+    assert np.array_equal(lo.state, g["cv_f3_state"]) and int(lo.cand.sum()) == int(g["cv_f3_n_candidates"])
+    ref = g["cv_f3_curr_pose"]
+    assert np.abs(lo.curr_pose[:3, :3] - ref[:3, :3]).max() < 2e-4 and np.abs(lo.curr_pose[:3, 3] - ref[:3, 3]).max() < 5e-3

@@ -70,7 +70,9 @@ def test_pipeline_equals_loop_oracle_on_kitti(golden, refine, p3p_opencv):
         assert np.array_equal(got["state"], want["state"]), i
         assert np.array_equal(got["cand"], want["cand"]), i
         assert np.array_equal(got["inliers"], info["inliers"]), i
-        assert got["n_iterations"] == info["ransac_n_iterations"], i
+        assert got["n_iterations"] == info["ransac_n_iterations"], i         # carried value (untouched in the OpenCV mode)
+        if p3p_opencv:
+            assert summ["draws"][0] == info["cv_iterations"], i                # iterations of OpenCV's loop
         assert np.array_equal(got["rng"], rng_now), i       # the sample stream is where numpy's is
         assert summ["p3p_N"][0] == info["p3p_N"] and summ["n_candidates"][0] == info["n_candidates"], i
         assert summ["n_inliers"][0] == int(info["inliers"].sum()) and summ["n_tri"][0] == info["n_tri"], i

@@ -77,8 +77,8 @@ p3p_count_kernel(const double* __restrict__ landmarks, const double* __restrict_
             for (int base = 0; base < n; base += 64) {     // two points per lane and step: independent FP64 chains
                 const int i0 = base + lane, i1 = i0 + 32;
                 bool in0 = false, in1 = false;
-                if (i0 < n) in0 = is_inlier(reproj_err2(m, sX[i0], sY[i0], sZ[i0], sU[i0], sV[i0], K), threshold, inclusive);
-                if (i1 < n) in1 = is_inlier(reproj_err2(m, sX[i1], sY[i1], sZ[i1], sU[i1], sV[i1], K), threshold, inclusive);
+                if (i0 < n) in0 = reproj_inlier(m, sX[i0], sY[i0], sZ[i0], sU[i0], sV[i0], K, threshold, inclusive);
+                if (i1 < n) in1 = reproj_inlier(m, sX[i1], sY[i1], sZ[i1], sU[i1], sV[i1], K, threshold, inclusive);
                 c += __popc(__ballot_sync(0xFFFFFFFFu, in0)) + __popc(__ballot_sync(0xFFFFFFFFu, in1));
             }
         }
@@ -132,7 +132,7 @@ p3p_select_kernel(const double* __restrict__ landmarks, const double* __restrict
     const double* L = landmarks + (size_t)f * N * 3;
     const double* P = keypoints + (size_t)f * N * 2;
     for (int i = threadIdx.x; i < N; i += blockDim.x)
-        in[i] = is_inlier(reproj_err2(m, L[3 * i], L[3 * i + 1], L[3 * i + 2], P[2 * i], P[2 * i + 1], K), threshold, inclusive) ? 1 : 0;
+        in[i] = reproj_inlier(m, L[3 * i], L[3 * i + 1], L[3 * i + 2], P[2 * i], P[2 * i + 1], K, threshold, inclusive) ? 1 : 0;
 }
 
 }  // namespace

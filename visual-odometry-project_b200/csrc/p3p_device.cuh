@@ -203,12 +203,23 @@ __device__ __forceinline__ double reproj_err2(const double* m, double X0, double
     return du * du + dv * dv;
 }
 
-// ransac.py:105 `errors < inlier_threshold`; with inclusive != 0 OpenCV's rule `err <= t` (findInliers of
-// cv2.solvePnPRansac, the reference's use_opencv=True path, p3p.py:142-151)
-__device__ __forceinline__ bool is_inlier(double e, double thr, int inclusive) {
-    return inclusive ? (e <= thr) : (e < thr);
+// The inlier test of one correspondence under the two rules the reference can run:
+//   rule 0  ransac.py:104-106 with p3p.py:81-108: squared reprojection error in float64, err < threshold;
+//   rule 1  cv2.solvePnPRansac (p3p.py:142-151): PnPRansacCallback::computeError + findInliers -- the projection is
+//           rounded to float32, the squared distance to the (float32) image point is evaluated in float32 and compared
+//           with err <= (float)threshold.  The caller passes landmarks already rounded to float32 (solvePnPRansac
+//           converts its inputs) and threshold = reprojectionError^2.
+__device__ __forceinline__ bool reproj_inlier(const double* m, double X0, double X1, double X2, double ku, double kv, const Intr& K,
+                                              double thr, int rule) {
+    if (rule == 0) return reproj_err2(m, X0, X1, X2, ku, kv, K) < thr;
+    const double xc = m[0] * X0 + m[1] * X1 + m[2] * X2 + m[9];
+    const double yc = m[3] * X0 + m[4] * X1 + m[5] * X2 + m[10];
+    const double zc = m[6] * X0 + m[7] * X1 + m[8] * X2 + m[11];
+    const double iz = zc != 0.0 ? 1.0 / zc : 1.0;
+    const float u = (float)((xc * iz) * K.fx + K.cx), v = (float)((yc * iz) * K.fy + K.cy);
+    const float dx = __fsub_rn((float)ku, u), dy = __fsub_rn((float)kv, v);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) <= (float)thr;
 }
-
 
 // model_fn of p3p.py:51-79 for one sample: X4 / uv4 = the four sampled correspondences (three solve, the fourth picks
 // among the <= 4 solutions, as cv2.solvePnP(SOLVEPNP_P3P) does).  Returns false when no real solution exists.

@@ -156,7 +156,8 @@ struct PipeParams {
     int C;                  // capacity
     Intr K;                 // promoted intrinsics
     double K9[9], Kinv9[9];
-    double thr; int inclusive; double log1mconf; int max_iter; int refine;
+    double thr; int inclusive; double log1mconf; int max_iter; int refine;   // inclusive != 0: cv2.solvePnPRansac's semantics
+    double conf;
     double bearing_thr; int tri_mode; float err_thr; double redetect_frac;
 };
 
@@ -286,6 +287,33 @@ __device__ __forceinline__ int ransac_iterations(int best, int N, double log1mco
     if (!(k < 2147483647.0)) return max_iter;
     const int ki = (int)k;
     return ki < max_iter ? ki : max_iter;
+}
+
+// RANSACUpdateNumIters (calib3d/src/ptsetreg.cpp), as cv2.solvePnPRansac calls it after an improvement
+__device__ __forceinline__ int cv_update_num_iters(double p, double ep, int model_points, int max_iters) {
+    p = fmin(fmax(p, 0.0), 1.0); ep = fmin(fmax(ep, 0.0), 1.0);
+    const double tiny = 2.2250738585072014e-308;
+    double num = fmax(1.0 - p, tiny);
+    double denom = 1.0 - pow(1.0 - ep, (double)model_points);
+    if (denom < tiny) return 0;
+    num = log(num); denom = log(denom);
+    return (denom >= 0.0 || -num >= (double)max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
+}
+// cv::RNG: multiply-with-carry; uniform(0, n) = next() % n
+__device__ __forceinline__ unsigned int cv_rng_next(unsigned long long& st) {
+    st = (unsigned long long)(unsigned int)st * 4164903690ull + (st >> 32);
+    return (unsigned int)st;
+}
+// RANSACPointSetRegistrator::getSubset for 4 model points (PnP has no degeneracy check)
+__device__ __forceinline__ void cv_subset4(unsigned long long& st, int N, int* out) {
+    for (int i = 0; i < 4; i++) {
+        for (;;) {
+            const int v = (int)(cv_rng_next(st) % (unsigned int)N);
+            bool dup = false;
+            for (int j = 0; j < i; j++) dup |= (out[j] == v);
+            if (!dup) { out[i] = v; break; }
+        }
+    }
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -463,22 +491,27 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
     __shared__ PipeRng s_snap[PO_HYP + 1];
     __shared__ int s_ctl[8];      // 0 stop, 1 n, 2 best, 3 n_iter, 4 draws, 5 flags, 7 parallel sampler ok
     __shared__ unsigned int s_words[PO_HYP * 7];
+    __shared__ unsigned long long s_cvrng;
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int N = Q.n_tri[s];
     const size_t base = (size_t)s * C;
     const Intr K = P.K;
     int* cnt = Q.counts + (size_t)s * VO_PIPE_NCOUNTS;
+    const bool cvmode = P.inclusive != 0;       // cv2.solvePnPRansac: float32 points, its own generator, nothing carried over
     for (int i = tid; i < N; i += PO_THREADS) {
-        sX[i] = T.land[(base + i) * 3]; sY[i] = T.land[(base + i) * 3 + 1]; sZ[i] = T.land[(base + i) * 3 + 2];
+        double x = T.land[(base + i) * 3], y = T.land[(base + i) * 3 + 1], z = T.land[(base + i) * 3 + 2];
+        if (cvmode) { x = (double)(float)x; y = (double)(float)y; z = (double)(float)z; }     // solvePnPRansac converts to CV_32F
+        sX[i] = x; sY[i] = y; sZ[i] = z;
         const float2 k = T.kp[base + i];
         sU[i] = (double)k.x; sV[i] = (double)k.y;
     }
     if (tid == 0) {
-        s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[2] = -1; s_ctl[3] = Q.n_iterations[s]; s_ctl[4] = 0; s_ctl[5] = 0;
+        s_ctl[0] = 0; s_ctl[1] = 0; s_ctl[2] = cvmode ? 0 : -1; s_ctl[3] = cvmode ? P.max_iter : Q.n_iterations[s]; s_ctl[4] = 0; s_ctl[5] = 0;
         s_snap[0] = Q.rng[s];
+        s_cvrng = 0xFFFFFFFFFFFFFFFFull;        // RANSACPointSetRegistrator::run: RNG rng((uint64)-1)
     }
     __syncthreads();
-    if (N < 4) {
+    if (N < 4 || (cvmode && N == 4)) {
         // the reference raises here (Generator.choice cannot take 4 of fewer than 4): report and keep the last pose
         for (int i = tid; i < N; i += PO_THREADS) inliers_out[base + i] = 0;
         if (tid == 0) { cnt[4] = 0; cnt[7] |= 2; cnt[8] = Q.n_iterations[s]; cnt[9] = 0; cnt[11] = 0; }
@@ -489,7 +522,14 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
     while (true) {
         // the sequence's sample stream, 16 samples ahead: thread 0 draws the 16 x 7 words a sample needs when nothing is
         // rejected (the only serial part: 56 steps of the 128-bit LCG), 16 threads turn them into index sets
-        if (tid == 0) {
+        if (cvmode) {
+            if (tid == 0) {
+                unsigned long long st = s_cvrng;
+                for (int j = 0; j < PO_HYP; j++) cv_subset4(st, N, s_idx[j]);
+                s_cvrng = st;
+                s_ctl[7] = 1;
+            }
+        } else if (tid == 0) {
             PipeRng r = s_snap[0];
             for (int k = 0; k < PO_HYP * 7; k++) {
                 if (k % 7 == 0) s_snap[k / 7] = r;
@@ -499,13 +539,13 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
             s_ctl[7] = (N > 4) ? 1 : 0;                   // N == 4: the first bounded draw of a sample consumes nothing
         }
         __syncthreads();
-        if (tid < PO_HYP && N > 4) {
+        if (!cvmode && tid < PO_HYP && N > 4) {
             int idx[4];
             if (!choice4_from(s_words + tid * 7, N, idx)) s_ctl[7] = 0;
             for (int k = 0; k < 4; k++) s_idx[tid][k] = idx[k];
         }
         __syncthreads();
-        if (tid == 0 && !s_ctl[7]) {                      // a rejected draw shifts everything after it: redo in sequence
+        if (!cvmode && tid == 0 && !s_ctl[7]) {           // a rejected draw shifts everything after it: redo in sequence
             PipeRng r = s_snap[0];
             for (int j = 0; j < PO_HYP; j++) {
                 s_snap[j] = r;
@@ -536,15 +576,31 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
                 for (int b0 = 0; b0 < N; b0 += 64) {
                     const int i0 = b0 + lane, i1 = i0 + 32;
                     bool in0 = false, in1 = false;
-                    if (i0 < N) in0 = p3pdev::is_inlier(p3pdev::reproj_err2(m, sX[i0], sY[i0], sZ[i0], sU[i0], sV[i0], K), P.thr, P.inclusive);
-                    if (i1 < N) in1 = p3pdev::is_inlier(p3pdev::reproj_err2(m, sX[i1], sY[i1], sZ[i1], sU[i1], sV[i1], K), P.thr, P.inclusive);
+                    if (i0 < N) in0 = p3pdev::reproj_inlier(m, sX[i0], sY[i0], sZ[i0], sU[i0], sV[i0], K, P.thr, P.inclusive);
+                    if (i1 < N) in1 = p3pdev::reproj_inlier(m, sX[i1], sY[i1], sZ[i1], sU[i1], sV[i1], K, P.thr, P.inclusive);
                     c += __popc(__ballot_sync(0xffffffffu, in0)) + __popc(__ballot_sync(0xffffffffu, in1));
                 }
             }
             if (lane == 0) s_cnt[h] = c;
         }
         __syncthreads();
-        if (tid == 0) {                                   // ransac.py:90-121 over the 16 pre-scored samples
+        if (tid == 0 && cvmode) {                         // RANSACPointSetRegistrator::run over the 16 pre-scored subsets
+            int it = s_ctl[1], best = s_ctl[2], niters = s_ctl[3];
+            int stop = 0;
+            for (int j = 0; j < PO_HYP; j++) {
+                if (!(it < niters)) { stop = 1; break; }
+                it++;                                     // a subset without a model still is an iteration
+                if (!s_valid[j]) continue;
+                const int good = s_cnt[j];
+                if (good > (best > 3 ? best : 3)) {
+                    best = good;
+                    for (int i = 0; i < 12; i++) s_best[i] = s_models[j][i];
+                    niters = cv_update_num_iters(P.conf, (double)(N - good) / (double)N, 4, niters);
+                }
+            }
+            if (!stop && !(it < niters)) stop = 1;
+            s_ctl[0] = stop; s_ctl[1] = it; s_ctl[2] = best; s_ctl[3] = niters; s_ctl[4] = it;
+        } else if (tid == 0) {                            // ransac.py:90-121 over the 16 pre-scored samples
             int n = s_ctl[1], best = s_ctl[2], n_iter = s_ctl[3], draws = s_ctl[4];
             int j = 0, stop = 0;
             for (; j < PO_HYP; j++) {
@@ -566,10 +622,9 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
         __syncthreads();
         if (s_ctl[0]) break;
     }
-    const int best = s_ctl[2];
+    const int best = (cvmode && s_ctl[2] == 0) ? -1 : s_ctl[2];
     if (tid == 0) {
-        Q.rng[s] = s_snap[0];
-        Q.n_iterations[s] = s_ctl[3];
+        if (!cvmode) { Q.rng[s] = s_snap[0]; Q.n_iterations[s] = s_ctl[3]; }   // ransac.py keeps both between calls; OpenCV nothing
         cnt[8] = s_ctl[3]; cnt[9] = s_ctl[4];
     }
     if (best < 0) {                                       // no sample produced a model
@@ -584,13 +639,17 @@ pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inl
 #pragma unroll
         for (int i = 0; i < 12; i++) m[i] = s_best[i];
         for (int i = tid; i < N; i += PO_THREADS) {
-            const uint8_t in = p3pdev::is_inlier(p3pdev::reproj_err2(m, sX[i], sY[i], sZ[i], sU[i], sV[i], K), P.thr, P.inclusive) ? 1 : 0;
+            const uint8_t in = p3pdev::reproj_inlier(m, sX[i], sY[i], sZ[i], sU[i], sV[i], K, P.thr, P.inclusive) ? 1 : 0;
             sIn[i] = in;
             inliers_out[base + i] = in;
         }
         if (tid < 12) { s_pose[tid] = s_best[tid]; Q.p3p_model[(size_t)s * 12 + tid] = s_best[tid]; }
     }
     __syncthreads();
+    if (cvmode) {       // the refinement runs on the reference's own float64 landmarks (p3p.py:158-163), not on OpenCV's float32 copies
+        for (int i = tid; i < N; i += PO_THREADS) { sX[i] = T.land[(base + i) * 3]; sY[i] = T.land[(base + i) * 3 + 1]; sZ[i] = T.land[(base + i) * 3 + 2]; }
+        __syncthreads();
+    }
     int gn_iters = 0;
     if (P.refine) gn_iters = gn_refine(sX, sY, sZ, sU, sV, sIn, N, K, s_pose, s_gn);
     __syncthreads();
@@ -877,7 +936,7 @@ int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* prm, vo_pipeline**
     d.K = Intr{p.K[0], p.K[4], p.K[2], p.K[5]};
     for (int i = 0; i < 9; i++) { d.K9[i] = p.K[i]; d.Kinv9[i] = p.Kinv[i]; }
     d.thr = p.p3p_threshold; d.inclusive = p.p3p_inclusive; d.log1mconf = p.ransac_log1mconf != 0.0 ? p.ransac_log1mconf : log(1.0 - p.ransac_confidence);
-    d.max_iter = p.ransac_max_iterations; d.refine = p.refine;
+    d.max_iter = p.ransac_max_iterations; d.refine = p.refine; d.conf = p.ransac_confidence;
     d.bearing_thr = p.bearing_threshold; d.tri_mode = p.tri_mode; d.err_thr = p.klt_error_threshold; d.redetect_frac = p.redetect_fraction;
     auto finish = [&]() -> int {
         const size_t S = p.n_seq, C = p.capacity, npx = (size_t)p.H * p.W;

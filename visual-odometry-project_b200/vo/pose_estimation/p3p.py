@@ -1,14 +1,15 @@
 """P3P pose estimation (reference: src/vo/pose_estimation/p3p.py).
 
 estimate_pose runs the P3P minimal solver and the reprojection inlier count for whole batches of
-RANSAC hypotheses on the GPU (vo_p3p_ransac_* in include/vo_b200.h) and replays the reference's
-sequential, adaptive RANSAC loop over them, so the rng stream, the iteration count, the winning
-model and the inlier mask are those of the reference's `use_opencv=False` path.  With
-`use_opencv=True` the reference hands the whole problem to cv2.solvePnPRansac (its own RNG and
-sampler); here that flag only switches the inlier rule to OpenCV's (squared error <=
-reprojectionError^2, inclusive): the default-path result is an APPROXIMATION of the reference's
-(same model class, same inlier rule, different sample stream), pinned by tolerance after the
-refinement (tests/test_loop_gpu.py), not by equality."""
+RANSAC hypotheses on the GPU (vo_p3p_ransac_* in include/vo_b200.h) and replays the sequential
+loop over them on the host:
+  * use_opencv=False: the reference's own RANSAC (ransac.py): numpy rng 2023, adaptive iteration
+    count, the outlier_ratio / n_iterations state that survives between calls.  Same rng position,
+    iteration count, winning model and inlier mask as the reference.
+  * use_opencv=True (the default, what src/main.py runs): cv2.solvePnPRansac's RANSAC restated
+    (vo/algorithms/cv_ransac.py): OpenCV's fixed-seed generator and subset rule, float32 points,
+    float32 errors with `<=`, RANSACUpdateNumIters.  The inlier mask is cv2.solvePnPRansac's own.
+The refinement (p3p.py:188-213) is a Gauss-Newton on the GPU (vo_refine_pose_host)."""
 import numpy as np
 
 from vo import _ops
@@ -42,18 +43,56 @@ class P3PPoseEstimator:
         points_3d, points_2d = features.landmarks, features.keypoints
         assert points_3d.shape[1] == 3 and points_2d.shape[1] == 2, "Invalid shape."
         assert points_3d is not None and points_2d is not None, "3D landmarks and 2D keypoints must be provided."
-        model, inliers = self._gpu_ransac(points_3d, points_2d)
         if self._use_opencv:
+            model, inliers = self._gpu_ransac_opencv(points_3d, points_2d)
             assert model is not None, "OpenCV P3P failed"                       # p3p.py:153
+        else:
+            model, inliers = self._gpu_ransac(points_3d, points_2d)
         if model is not None and self.nonlinear_refinement:
             model = self._nonlinear_refinement(points_3d[inliers], points_2d[inliers], model)
         return model, inliers
+
+    def _gpu_ransac_opencv(self, points_3d, points_2d):
+        """cv2.solvePnPRansac(flags=SOLVEPNP_P3P, iterationsCount=max_iterations, reprojectionError=inlier_threshold,
+        confidence=confidence) (p3p.py:142-151): OpenCV's loop on the host, models and counts of its subsets on the GPU."""
+        from vo.algorithms.cv_ransac import CvRNG, subset4, update_num_iters
+        L32 = np.asarray(points_3d, dtype=np.float64).reshape(-1, 3).astype(np.float32).astype(np.float64)   # solvePnPRansac: CV_32F
+        P32 = np.asarray(points_2d).reshape(-1, 2).astype(np.float32).astype(np.float64)
+        N = L32.shape[0]
+        if N <= 4:
+            return None, None
+        thr2 = float(self.inlier_threshold) ** 2
+        table = np.full(N + 1, np.iinfo(np.int32).max, dtype=np.int64)      # no adaptive stop inside the batch: replayed below
+        rng = CvRNG()
+        niters = int(min(self.max_iterations, np.iinfo(np.int32).max))
+        it, best, best_sample, best_model = 0, 0, None, None
+        batch = self.FIRST_BATCH
+        while it < niters:
+            want = int(min(batch, niters - it))
+            samples = np.array([subset4(rng, N) for _ in range(want)], dtype=np.int32)
+            r = _ops.p3p_ransac(L32, P32, self.intrinsic_matrix, samples, thr2, table, np.iinfo(np.int32).max, want_all=True,
+                                inclusive=True)
+            for j in range(want):
+                if not it < niters:
+                    break
+                it += 1                                         # a subset without a model still is an iteration
+                if not r["valid"][j]:
+                    continue
+                good = int(r["counts"][j])
+                if good > max(best, 3):
+                    best, best_sample, best_model = good, samples[j].copy(), r["models"][j].copy()
+                    niters = update_num_iters(self.confidence, (N - good) / N, 4, niters)
+            batch = self.NEXT_BATCH
+        if best_model is None:
+            return None, None
+        r = _ops.p3p_ransac(L32, P32, self.intrinsic_matrix, best_sample[None], thr2, table, np.iinfo(np.int32).max, inclusive=True)
+        return (best_model[:9].reshape(3, 3).copy(), best_model[9:].reshape(3, 1).copy()), r["inliers"].copy()
 
     def _gpu_ransac(self, points_3d, points_2d):
         rs = self.ransac
         N = points_3d.shape[0]
         table = rs.iterations_table(N)
-        thr = self.inlier_threshold ** 2 if self._use_opencv else self.inlier_threshold
+        thr = self.inlier_threshold                                     # ransac.py:105: squared error < threshold
         n, best_count, best = 0, -1, None
         batch = self.FIRST_BATCH
         drawn, draw_cap = 0, 10 * int(min(self.max_iterations, 1 << 24)) + 4096
@@ -66,7 +105,7 @@ class P3PPoseEstimator:
             want = int(min(batch, max(1, rs.n_iterations - n)))
             samples = np.stack([rs.draw(N) for _ in range(want)]).astype(np.int32)
             r = _ops.p3p_ransac(points_3d, points_2d, self.intrinsic_matrix, samples, thr, table,
-                                rs.n_iterations, start_n=n, start_best=best_count, inclusive=self._use_opencv)
+                                rs.n_iterations, start_n=n, start_best=best_count)
             n, consumed = int(r["n"]), int(r["consumed"])
             drawn += consumed
             if int(r["best"]) >= 0:
