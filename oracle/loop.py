@@ -149,7 +149,7 @@ class LoopOracle:
 
     def __init__(self, K, detector, *, p3p_opencv=False, refine="scipy", tri_opencv=True, inlier_threshold=1.25,
                  outlier_ratio=0.9, confidence=0.9999, max_iterations=10000, bearing_threshold=0.0075,
-                 error_threshold=100.0, redetect_fraction=0.8, klt=None, klt_params=None, eager_detector=False):
+                 error_threshold=100.0, redetect_fraction=0.8, klt=None, klt_params=None, eager_detector=False, capacity=None):
         self.K = np.asarray(K)                               # dtype kept: the reference's KITTI K is float32 (loader.py:94-96)
         self.Kinv = np.linalg.inv(self.K)                    # camera.py:92 (float32 inverse when K is float32)
         self.K64 = np.asarray(K, dtype=np.float64)
@@ -167,6 +167,7 @@ class LoopOracle:
         self.klt_params = klt_params or dict(win=17, max_level=2, max_iters=10, epsilon=0.03)   # klt.py:29-33
         # eager_detector: run the detector on every new frame and keep its corners for the next step's re-detection
         # (what the CUDA pipeline does; the result of a step is the same, klt.py:207-230 detects on that very frame)
+        self.capacity = capacity            # rows the CUDA pipeline's table can hold (an append is cut to the room left)
         self.eager_detector = eager_detector
         self._cached_det = None
         self.curr_pose = np.eye(4)
@@ -211,6 +212,9 @@ class LoopOracle:
             fresh = self._cached_det if self._cached_det is not None else self.detector(prev_gray)
             fresh = np.asarray(fresh, dtype=np.float32).reshape(-1, 2)
             self.num_features = fresh.shape[0]                              # klt.py:114 (find_corners side effect)
+            info["overflow"] = self.capacity is not None and n + len(fresh) > self.capacity
+            if info["overflow"]:
+                fresh = fresh[: self.capacity - n]
             m = len(fresh)
             self.kp = np.concatenate([self.kp, fresh])
             self.land = np.concatenate([self.land, np.full((m, 3), np.nan)])

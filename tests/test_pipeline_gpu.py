@@ -198,3 +198,54 @@ def test_pipeline_gftt_detector_reference_klt_mode(golden):
         assert np.array_equal(pl.read_detections(0), g[f"gftt_{i}"]), i
     assert got["n"] > 800                                    # 486 tracked + 500 appended, minus the losses
     pl.close()
+
+
+def test_pipeline_long_run_edge_cases(ctx):
+    """40 frames of four sequences with a small table: re-detections that overflow the capacity (the append is cut and
+    flagged), a sequence that starts with two landmarks only (fewer than P3P needs: "no pose", the last pose is kept, as
+    documented) and the OpenCV mode side by side -- every step equal to the loop oracle."""
+    import oracle
+    from conftest import synthetic_image
+    from oracle.loop import LoopOracle
+    from vo.pipeline import DETECTOR_HARRIS, Pipeline
+    S, H, W, KP, CAP = 4, 128, 192, 100, 160
+    K = np.array([[250.0, 0, W / 2], [0, 250.0, H / 2], [0, 0, 1]])
+    big = [synthetic_image(H + 60, W + 140, seed=90 + s) for s in range(S)]
+    T = 41
+    def frame(s, t):
+        k = t if t <= 20 else 40 - t                       # forth and back
+        return np.ascontiguousarray(big[s][6 + k:6 + k + H, 6 + 3 * k:6 + 3 * k + W])
+    for opencv in (False, True):
+        pl = Pipeline(S, H, W, K, capacity=CAP, detector=DETECTOR_HARRIS, det_max_corners=KP, refine=True, p3p_opencv=opencv, ctx=ctx)
+        pl.prime(np.stack([frame(s, 0) for s in range(S)]), init_tables=True)
+        los = []
+        for s in range(S):
+            det = lambda im: oracle.harris_keypoints(im, KP, 9, 0.09, 5)[0].astype(np.float32)
+            lo = LoopOracle(K, detector=det, refine="gn", p3p_opencv=opencv, capacity=CAP)
+            lo.init_detect(frame(s, 0))
+            land = np.concatenate([(lo.kp - K[:2, 2]) / K[0, 0] * 8.0, np.full((len(lo.kp), 1), 8.0)], 1)
+            state = np.full(len(lo.kp), 2)
+            if s == 3:                                      # almost nothing triangulated: P3P cannot run for a while
+                state[2:] = 0
+            land[state == 0] = np.nan
+            lo.set_table(lo.kp, land, state, lo.track, lo.pose)
+            lo.num_features = 140 if s == 1 else KP         # sequence 1 re-detects at once: 100 + 100 rows > 160
+            pl.write_table(s, lo.kp, land, state, lo.track, lo.pose, curr_pose=np.eye(4), num_features=lo.num_features)
+            los.append(lo)
+        seen = dict(overflow=0, no_pose=0, redetect=0)
+        for t in range(1, T):
+            summ = pl.step(np.stack([frame(s, t) for s in range(S)]))
+            for s in range(S):
+                info = los[s].step(frame(s, t - 1), frame(s, t))
+                got, want = pl.read_table(s), los[s].table()
+                fl = int(summ["flags"][s])
+                assert bool(fl & 1) == info["redetect"] and bool(fl & 2) == info["no_pose"] and bool(fl & 4) == info.get("overflow", False), (opencv, t, s, fl)
+                seen["overflow"] += bool(fl & 4); seen["no_pose"] += bool(fl & 2); seen["redetect"] += bool(fl & 1)
+                assert got["n"] == len(want["kp"]) <= CAP, (opencv, t, s)
+                assert np.array_equal(got["kp"], want["kp"]) and np.array_equal(got["state"], want["state"]), (opencv, t, s)
+                assert np.array_equal(got["cand"], want["cand"]) and np.array_equal(got["inliers"], info["inliers"]), (opencv, t, s)
+                assert np.allclose(got["curr_pose"], want["curr_pose"], atol=1e-7), (opencv, t, s)
+                assert np.array_equal(np.isnan(got["land"]), np.isnan(want["land"])), (opencv, t, s)
+                assert got["num_features"] == los[s].num_features, (opencv, t, s)
+        assert seen["overflow"] >= 1 and seen["no_pose"] >= 1 and seen["redetect"] >= 2, seen
+        pl.close()
