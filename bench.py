@@ -301,6 +301,13 @@ def bind_near_gpu(local_rank):
             node = int(open(path).read().strip())
         except Exception:
             node = None
+        if node is None or node < 0:                  # containers often hide sysfs' numa_node: ask NVML for the memory affinity
+            try:
+                m = nv.nvmlDeviceGetMemoryAffinity(h, 4, nv.NVML_AFFINITY_SCOPE_NODE)
+                bits = [64 * i + b for i, w in enumerate(m) for b in range(64) if (int(w) >> b) & 1]
+                node = bits[0] if len(bits) == 1 else None
+            except Exception:
+                node = None
         n_words = (os.cpu_count() + 63) // 64
         mask = nv.nvmlDeviceGetCpuAffinity(h, n_words)
         cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
