@@ -281,6 +281,78 @@ def cpu_pipeline_fps(n_seq, steps, warmup, procs, seed=1234):
 
 
 # ------------------------------------------------------------------------------------------------
+def class_api_loop(world, n_frames=12):
+    """main.py:248-287 through the drop-in `vo` classes (one sequence, host arrays between the stages, one C-ABI call per
+    stage): Tracker("klt").trackFeatures -> P3PPoseEstimator.estimate_pose -> State updates -> triangulate_candidates.
+    Returns frames/s over the timed frames (the first two are warm-up)."""
+    from vo.features import Tracker
+    from vo.landmarks import LandmarksTriangulator
+    from vo.pose_estimation import P3PPoseEstimator
+    from vo.primitives import Features, Frame, State
+    from vo.sensors import Camera
+    cam = Camera(intrinsic_matrix=K_INTR)
+    frames = []
+    for t in range(n_frames + 1):
+        g = world.frame(0, world.time_index(t))
+        frames.append(Frame(np.ascontiguousarray(np.stack([g, g, g], -1)), sensor=cam, intrinsics=K_INTR))   # BGR, as cv2.imread gives
+    tri = LandmarksTriangulator(camera1=cam, camera2=cam, use_ransac=True, use_opencv=True, outlier_ratio=0.9, ransac_threshold=0.25,
+                                ransac_confidence=0.999)
+    est = P3PPoseEstimator(use_opencv=True, intrinsic_matrix=K_INTR, inlier_threshold=P3P_THR, outlier_ratio=0.9, confidence=P3P_CONF,
+                           nonlinear_refinement=True)
+    state = State(frames[0])
+    tracker = Tracker(frames[0], mode="klt")
+    f = frames[0].features                      # hand-over in place of the two-view bootstrap: the plane's landmarks
+    n = f.length
+    f.landmarks = World.landmarks_of(f.keypoints.reshape(-1, 2)).reshape(n, 3, 1)
+    f.state = np.full(n, 2.0)
+    f.state[::5] = 0.0                          # some tracks still untriangulated, as after the reference's bootstrap
+    f.landmarks[f.state == 0] = np.nan
+    times = []
+    for t in range(1, n_frames + 1):
+        t0 = time.perf_counter()
+        matches = tracker.trackFeatures(state.curr_frame, frames[t])
+        (R, tv), inl = est.estimate_pose(Features(keypoints=matches.frame2.features.triangulated_inliers_keypoints,
+                                                  landmarks=matches.frame2.features.triangulated_inliers_landmarks))
+        outliers = np.zeros(shape=(matches.frame2.features.length,), dtype=bool)
+        outliers[matches.frame2.features.triangulate_inliers] = ~inl
+        state.update_from_matches(matches)
+        state.update_with_world_pose(np.concatenate((R, tv), axis=1))
+        state.reset_outliers(outliers)
+        state.compute_candidates()
+        if np.sum(state.curr_frame.features.candidate_mask) > 0:
+            lw = tri.triangulate_candidates(state.curr_frame.features, current_pose=state.get_pose())
+            state.update_with_world_landmarks(lw, matches.frame2.features.candidate_mask)
+        if t > 2:
+            times.append(time.perf_counter() - t0)
+    return 1.0 / float(np.mean(times)), float(np.linalg.norm(state.get_pose()[:3, 3] - World.true_position(world.time_index(n_frames))))
+
+
+def class_api_cpu_reference(world, n_frames=4):
+    """The same loop on the host, as the reference runs it (loop oracle: cv2.goodFeaturesToTrack / calcOpticalFlowPyrLK,
+    restated cv2.solvePnPRansac, scipy least_squares, numpy bookkeeping), one sequence, one process."""
+    import cv2
+    import oracle
+    from oracle.loop import LoopOracle
+    det = lambda im: cv2.goodFeaturesToTrack(im, maxCorners=500, qualityLevel=0.01, minDistance=8, blockSize=7).reshape(-1, 2)
+    lo = LoopOracle(K_INTR, detector=det, refine="scipy", klt=_cv_klt, p3p_opencv=True, inlier_threshold=P3P_THR, confidence=P3P_CONF,
+                    max_iterations=P3P_MAX_ITER)
+    fr = [world.frame(0, world.time_index(t)) for t in range(n_frames + 1)]
+    lo.init_detect(fr[0])
+    n = len(lo.kp)
+    state = np.full(n, 2)
+    state[::5] = 0
+    land = World.landmarks_of(lo.kp)
+    land[state == 0] = np.nan
+    lo.set_table(lo.kp, land, state, lo.kp, lo.pose, curr_pose=np.eye(4), num_features=n)
+    times = []
+    for t in range(1, n_frames + 1):
+        t0 = time.perf_counter()
+        lo.step(fr[t - 1], fr[t])
+        if t > 1:
+            times.append(time.perf_counter() - t0)
+    return 1.0 / float(np.mean(times))
+
+
 def bind_near_gpu(local_rank):
     """Pin this process -- and with it the pinned staging buffers it allocates next -- to the NUMA node of its GPU, so
     that uploads do not cross the inter-socket link.  CPU affinity first (NVML's ideal set when it is a proper subset of
@@ -576,6 +648,19 @@ def main():
         raise SystemExit("bench.py: the end-to-end arm returned non-finite poses")
     pl2.close()
 
+    # ---- the drop-in class API (one sequence, host arrays between the stages) ------------------
+    class_api = None
+    if rank == 0 and not args.no_extras:
+        try:
+            fps_c, err_c = class_api_loop(wd)
+            class_api = {"frames_per_s": fps_c, "position_error": err_c,
+                         "note": "src/main.py:248-287 through the vo classes (KLT mode, use_opencv=True, refinement on): one sequence, "
+                                 "one C-ABI call per stage, numpy bookkeeping on the host; ~500 Shi-Tomasi corners as the reference's KLT mode"}
+            if world == 1 and not args.no_cpu_baseline:
+                class_api["cpu_reference_frames_per_s"] = class_api_cpu_reference(wd)
+        except Exception as ex:
+            class_api = {"frames_per_s": None, "note": f"failed: {type(ex).__name__}: {ex}"}
+
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -603,7 +688,7 @@ def main():
                     "api": "vo_pipeline_prefetch_host + vo_pipeline_submit_host + vo_pipeline_wait_host: only the frames go up "
                            "(pinned host buffers), poses + counters come back, every step; two steps in flight"},
             "gpu_launches": int(launches) * world,
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "single_sequence": single,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "single_sequence": single, "class_api": class_api,
         }))
     pl.close()
     if world > 1:
