@@ -44,6 +44,9 @@ void* vo_ctx_stream(vo_ctx* ctx);
 /* synchronous device -> host copy of a resident result buffer (after a device-wide sync) */
 int vo_copy_to_host(vo_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 
+/* page-locked host buffers for the *_host entry points (write_combined: CPU-write-only staging, not snooped by GPU reads) */
+int vo_host_alloc(void** out, size_t bytes, int write_combined);
+int vo_host_free(void* p);
 /* measured FP64 fused-multiply-add rate of the device in GFLOP/s (the ceiling the P3P kernels are compared with) */
 int vo_test_dfma_peak(vo_ctx* ctx, double* gflops);
 

@@ -151,6 +151,20 @@ int vo_test_dfma_peak(vo_ctx* ctx, double* gflops) {
     return VO_OK;
 }
 
+// Page-locked host memory for the frame uploads of the pipelined entry points.  write_combined != 0 asks for
+// cudaHostAllocWriteCombined: the CPU only ever writes these buffers (frames decoded / copied into them), and
+// write-combined pages are not snooped during the GPU's reads, which helps when several GPUs pull frames at once.
+int vo_host_alloc(void** out, size_t bytes, int write_combined) {
+    VO_REQUIRE(out && bytes > 0, "vo_host_alloc: bad argument");
+    *out = nullptr;
+    VO_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+    return VO_OK;
+}
+int vo_host_free(void* p) {
+    if (p) VO_CUDA(cudaFreeHost(p));
+    return VO_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Harris
 // ------------------------------------------------------------------------------------------

@@ -101,6 +101,8 @@ def lib():
             "vo_gftt_dev": (i32, [vp, vp, i32, i32, i32, sz, sz, i32, dbl, dbl, i32, vp, vp, vp, vp, vp]),
             "vo_gftt_host": (i32, [vp, vp, i32, i32, i32, i32, dbl, dbl, i32, vp, vp, vp, vp]),
             "vo_test_dfma_peak": (i32, [vp, vp]),
+            "vo_host_alloc": (i32, [C.POINTER(vp), sz, i32]),
+            "vo_host_free": (i32, [vp]),
             "vo_refine_pose_dev": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp]),
             "vo_refine_pose_host": (i32, [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]),
         })
@@ -163,6 +165,18 @@ def default_context(device: int = 0) -> Context:
     if ctx is None:
         ctx = _default_ctx[device] = Context(device)
     return ctx
+
+
+def pinned_empty(shape, dtype=np.uint8, write_combined=False) -> np.ndarray:
+    """numpy array over page-locked host memory (vo_host_alloc); freed when the array is collected."""
+    import weakref
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    check(lib().vo_host_alloc(C.byref(p), n, int(bool(write_combined))), "vo_host_alloc")
+    buf = (C.c_ubyte * n).from_address(p.value)
+    a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    weakref.finalize(buf, lib().vo_host_free, p)
+    return a
 
 
 def ptr(a: np.ndarray):
