@@ -14,6 +14,8 @@ import bench  # noqa: E402
 from vo import _native as nat  # noqa: E402
 from vo.frontend import Frontend  # noqa: E402
 
+if os.environ.get("VO_LIB"):          # development: time another build of the library side by side
+    nat.LIB_PATH = os.path.abspath(os.environ["VO_LIB"])
 what = sys.argv[1] if len(sys.argv) > 1 else "harris"
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 148
 H, W = bench.H, bench.W

@@ -150,9 +150,13 @@ constexpr int FT_SMEM = FT_IMG_BYTES + 3 * FT_ROWS * FT_HP * 4 + 16;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// WC > 0: the image width is the compile-time constant WC (the row offsets of the stores become immediates:
+// one instruction less per pixel); WC = 0: any width.
+template <int WC>
 __global__ void __launch_bounds__(FT_THREADS, 2)
-harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, double kappa, double* __restrict__ resp,
+harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W_rt, double kappa, double* __restrict__ resp,
                      int tiles_x, int tiles_y, int n_tiles) {
+    const int W = WC > 0 ? WC : W_rt;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint8_t* img = smem_raw;
     int2* hab = reinterpret_cast<int2*>(smem_raw + FT_IMG_BYTES);          // (sum Ix^2, sum Iy^2): one 64-bit access
@@ -182,6 +186,7 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
             "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
             ::"r"(smem_u32(img)), "l"(&tmap), "r"(bx * FT_W - FT_XSHIFT - 5), "r"(by * FT_H - 5), "r"(fr), "r"(smem_u32(mbar)) : "memory");
     };
+    if (tid < FT_ROWS) { hab[tid * FT_HP + FT_W] = make_int2(0, 0); hxy[tid * FT_HP + FT_W] = 0; }   // the zero column (phase V)
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -259,44 +264,47 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
         const int col = tid & 127, half = tid >> 7;
         const int base = 27 * half;
         const int gx = x0 + col;
+        // Columns inside the zero border of the score map (harris.py:129-137) read the spare column 128 of the
+        // H arrays, which holds zeros: their sums are 0 and the score evaluates to +0 without a predicate.
+        const bool x_in = gx >= 0 && gx < W, x_interior = gx >= 5 && gx < W - 5;
+        const int hcol = x_interior ? col : FT_W;
         int rxx[9], ryy[9], rxy[9];
         int vxx = 0, vyy = 0, vxy = 0;
 #pragma unroll
         for (int k = 0; k < 9; k++) {
-            const int2 ab = hab[(base + k) * FT_HP + col];
-            rxx[k] = ab.x; ryy[k] = ab.y; rxy[k] = hxy[(base + k) * FT_HP + col];
+            const int2 ab = hab[(base + k) * FT_HP + hcol];
+            rxx[k] = ab.x; ryy[k] = ab.y; rxy[k] = hxy[(base + k) * FT_HP + hcol];
             vxx += rxx[k]; vyy += ryy[k]; vxy += rxy[k];
         }
         // Branch-free emission (straight-line blocks, so the scheduler can overlap the float64 chains of
-        // neighbouring rows).  The score is always evaluated; one predicate folds the clamp (s > 0,
-        // harris.py:127) with "inside the zero border" (harris.py:129-137); the store is predicated on the
-        // pixel being inside the image.  Tiles that touch neither the top nor the bottom of the image
-        // (CTA-uniform test) take a variant whose predicates are per-thread constants.
-        const bool x_in = gx >= 0 && gx < W, x_interior = gx >= 5 && gx < W - 5;
+        // neighbouring rows).  The clamp s < 0 -> 0 (harris.py:127) costs no compare: with h = s / 2,
+        // |h| + h is s for s > 0 and +0 otherwise, exactly.  h comes out of the last subtraction for free:
+        // fma(det, 0.5, -(kappa/2) * trace^2) rounds the same real number as det - kappa * trace^2, halved
+        // (scaling by two commutes with rounding; the values are far from the subnormal range).
+        // Tiles that touch neither the top nor the bottom of the image (CTA-uniform test) need no row predicate.
+        const double half_kappa = 0.5 * kappa;
         const int gy0 = y0 + base;
         const unsigned int row_bytes = (unsigned int)W * (unsigned int)sizeof(double);
         char* dst0 = reinterpret_cast<char*>(resp + ((size_t)f * H + (size_t)gy0) * W + max(gx, 0));
         const bool y_interior_tile = (y0 >= 5) && (y0 + FT_H <= H - 5);
         if (y_interior_tile) {
-            const unsigned int xi = x_interior ? 1u : 0u, xs = x_in ? 1u : 0u;
+            const unsigned int xs = x_in ? 1u : 0u;
 #pragma unroll
             for (int i = 0; i < 27; i++) {
                 const double sa = (double)vxx, sb = (double)vyy, sc = (double)vxy;
                 const double trace = __dadd_rn(sa, sb);
                 const double det = __dsub_rn(__dmul_rn(sa, sb), __dmul_rn(sc, sc));
-                const double sraw = __dsub_rn(det, __dmul_rn(kappa, __dmul_rn(trace, trace)));
+                const double h = __fma_rn(det, 0.5, -__dmul_rn(half_kappa, __dmul_rn(trace, trace)));
+                const double v = __dadd_rn(fabs(h), h);
                 char* dst = dst0 + (size_t)row_bytes * (unsigned int)i;
                 asm volatile(
-                    "{\n\t.reg .pred p, q, r;\n\t.reg .f64 v;\n\t"
-                    "setp.ne.u32 q, %2, 0;\n\t"
-                    "setp.gt.and.f64 p, %1, 0d0000000000000000, q;\n\t"
-                    "selp.f64 v, %1, 0d0000000000000000, p;\n\t"
-                    "setp.ne.u32 r, %3, 0;\n\t"
-                    "@r st.global.f64 [%0], v;\n\t}"
-                    ::"l"(dst), "d"(sraw), "r"(xi), "r"(xs) : "memory");
+                    "{\n\t.reg .pred r;\n\t"
+                    "setp.ne.u32 r, %2, 0;\n\t"
+                    "@r st.global.f64 [%0], %1;\n\t}"
+                    ::"l"(dst), "d"(v), "r"(xs) : "memory");
                 if (i < 26) {
-                    const int2 nab = hab[(base + i + 9) * FT_HP + col];
-                    const int nxx = nab.x, nyy = nab.y, nxy = hxy[(base + i + 9) * FT_HP + col];
+                    const int2 nab = hab[(base + i + 9) * FT_HP + hcol];
+                    const int nxx = nab.x, nyy = nab.y, nxy = hxy[(base + i + 9) * FT_HP + hcol];
                     vxx += nxx - rxx[i % 9]; vyy += nyy - ryy[i % 9]; vxy += nxy - rxy[i % 9];
                     rxx[i % 9] = nxx; ryy[i % 9] = nyy; rxy[i % 9] = nxy;
                 }
@@ -304,25 +312,25 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W, dou
         } else {
             const int n_rows = x_in ? min(27, H - gy0) : 0;           // rows this thread may store
             const int i_lo = 5 - gy0;                                 // interior rows: i_lo <= i < i_lo + i_span
-            const unsigned i_span = x_interior ? (unsigned)max(H - 10, 0) : 0u;
+            const unsigned i_span = (unsigned)max(H - 10, 0);
 #pragma unroll
             for (int i = 0; i < 27; i++) {
                 const double sa = (double)vxx, sb = (double)vyy, sc = (double)vxy;
                 const double trace = __dadd_rn(sa, sb);
                 const double det = __dsub_rn(__dmul_rn(sa, sb), __dmul_rn(sc, sc));
-                const double sraw = __dsub_rn(det, __dmul_rn(kappa, __dmul_rn(trace, trace)));
+                const double h = __fma_rn(det, 0.5, -__dmul_rn(half_kappa, __dmul_rn(trace, trace)));
+                const double v = __dadd_rn(fabs(h), h);
                 char* dst = dst0 + (size_t)row_bytes * (unsigned int)i;
                 asm volatile(
-                    "{\n\t.reg .pred p, q, r;\n\t.reg .f64 v;\n\t"
+                    "{\n\t.reg .pred q, r;\n\t.reg .f64 v;\n\t"
                     "setp.lt.u32 q, %2, %3;\n\t"
-                    "setp.gt.and.f64 p, %1, 0d0000000000000000, q;\n\t"
-                    "selp.f64 v, %1, 0d0000000000000000, p;\n\t"
+                    "selp.f64 v, %1, 0d0000000000000000, q;\n\t"
                     "setp.lt.s32 r, %4, %5;\n\t"
                     "@r st.global.f64 [%0], v;\n\t}"
-                    ::"l"(dst), "d"(sraw), "r"((unsigned)(i - i_lo)), "r"(i_span), "r"(i), "r"(n_rows) : "memory");
+                    ::"l"(dst), "d"(v), "r"((unsigned)(i - i_lo)), "r"(i_span), "r"(i), "r"(n_rows) : "memory");
                 if (i < 26) {
-                    const int2 nab = hab[(base + i + 9) * FT_HP + col];
-                    const int nxx = nab.x, nyy = nab.y, nxy = hxy[(base + i + 9) * FT_HP + col];
+                    const int2 nab = hab[(base + i + 9) * FT_HP + hcol];
+                    const int nxx = nab.x, nyy = nab.y, nxy = hxy[(base + i + 9) * FT_HP + hcol];
                     vxx += nxx - rxx[i % 9]; vyy += nyy - ryy[i % 9]; vxy += nxy - rxy[i % 9];
                     rxx[i % 9] = nxx; ryy[i % 9] = nyy; rxy[i % 9] = nxy;
                 }
@@ -1396,13 +1404,18 @@ int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, i
                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r == CUDA_SUCCESS) {
-            if (vo_ctx_once(ctx, VO_ATTR_HARRIS_FAST))
-                VO_CUDA(cudaFuncSetAttribute(harris_response_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+            if (vo_ctx_once(ctx, VO_ATTR_HARRIS_FAST)) {
+                VO_CUDA(cudaFuncSetAttribute(harris_response_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+                VO_CUDA(cudaFuncSetAttribute(harris_response_fast<1241>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+            }
             const int tiles_x = vo_div_up(W + FT_XSHIFT, FT_W), tiles_y = vo_div_up(H, FT_H);
             const long long n_tiles = (long long)tiles_x * tiles_y * n_frames;
             VO_REQUIRE(n_tiles < (1ll << 31), "harris: too many tiles");
             const int grid = (int)((n_tiles < 2ll * ctx->sm_count) ? n_tiles : 2ll * ctx->sm_count);
-            harris_response_fast<<<grid, FT_THREADS, FT_SMEM, stream>>>(tmap, H, W, kappa, d_resp, tiles_x, tiles_y, (int)n_tiles);
+            if (W == 1241)      // KITTI-shaped frames (BASELINE.json)
+                harris_response_fast<1241><<<grid, FT_THREADS, FT_SMEM, stream>>>(tmap, H, W, kappa, d_resp, tiles_x, tiles_y, (int)n_tiles);
+            else
+                harris_response_fast<0><<<grid, FT_THREADS, FT_SMEM, stream>>>(tmap, H, W, kappa, d_resp, tiles_x, tiles_y, (int)n_tiles);
             ctx->launches++;
             VO_CHECK_LAUNCH();
             return VO_OK;
