@@ -223,26 +223,36 @@ harris_response_fast(const __grid_constant__ CUtensorMap tmap, int H, int W_rt, 
             int sxx = 0, syy = 0, sxy = 0;
             int2* oab = hab + r * FT_HP + 32 * g;
             int* oxy = hxy + r * FT_HP + 32 * g;
-            // Sobel by 8-bit dot products on the packed pixels (no byte extraction): for product column m the
-            // word s_k = pixels (m, m+1, m+2, m+3) of image row k (funnel shift of two packed words);
+            // Sobel by 8-bit dot products on the packed pixels (no byte extraction): for product column m
             //   gx = sum_k {1,2,1}[k] * (p_k[m] - p_k[m+2]),   gy = sum_j {1,2,1}[j] * (p_0[m+j] - p_2[m+j])
-            // (left - right, top - bottom: the signs cancel in the products, harris.py:103-113).
+            // (left - right, top - bottom: the signs cancel in the products, harris.py:103-113).  Pixels m .. m+2 lie in
+            // the aligned word of image row k for m % 4 = 0, 1 and in that word funnel-shifted by two bytes for
+            // m % 4 = 2, 3; the byte offset (0 or 1) inside the word is folded into the dp4a weights, so four
+            // columns share one shift per image row.
+            uint32_t s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
             for (int m = 0; m < 40; m++) {
-                const int q = m >> 2, sh = 8 * (m & 3);
-                uint32_t s0, s1, s2;
-                if (sh == 0) { s0 = w[0][q]; s1 = w[1][q]; s2 = w[2][q]; }
-                else {
-                    s0 = __funnelshift_r(w[0][q], w[0][q + 1], sh);
-                    s1 = __funnelshift_r(w[1][q], w[1][q + 1], sh);
-                    s2 = __funnelshift_r(w[2][q], w[2][q + 1], sh);
+                const int q = m >> 2;
+                if ((m & 3) == 0) { s0 = w[0][q]; s1 = w[1][q]; s2 = w[2][q]; }
+                if ((m & 3) == 2) {
+                    s0 = __funnelshift_r(w[0][q], w[0][q + 1], 16);
+                    s1 = __funnelshift_r(w[1][q], w[1][q + 1], 16);
+                    s2 = __funnelshift_r(w[2][q], w[2][q + 1], 16);
                 }
                 int gx, gy;
-                asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s0), "r"(0x00FF0001), "r"(0));
-                asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s1), "r"(0x00FE0002), "r"(gx));
-                asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s2), "r"(0x00FF0001), "r"(gx));
-                asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gy) : "r"(s0), "r"(0x00010201), "r"(0));
-                asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gy) : "r"(s2), "r"(0x00FFFEFF), "r"(gy));
+                if ((m & 1) == 0) {
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s0), "r"(0x00FF0001), "r"(0));
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s1), "r"(0x00FE0002), "r"(gx));
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s2), "r"(0x00FF0001), "r"(gx));
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gy) : "r"(s0), "r"(0x00010201), "r"(0));
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gy) : "r"(s2), "r"(0x00FFFEFF), "r"(gy));
+                } else {
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s0), "r"(0xFF000100), "r"(0));
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s1), "r"(0xFE000200), "r"(gx));
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gx) : "r"(s2), "r"(0xFF000100), "r"(gx));
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gy) : "r"(s0), "r"(0x01020100), "r"(0));
+                    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(gy) : "r"(s2), "r"(0xFFFEFF00), "r"(gy));
+                }
                 const int pxx = gx * gx, pyy = gy * gy, pxy = gx * gy;
                 if (m >= 9) {
                     sxx += pxx - ring_xx[m % 9]; syy += pyy - ring_yy[m % 9]; sxy += pxy - ring_xy[m % 9];
