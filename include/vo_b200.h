@@ -186,6 +186,25 @@ int vo_triangulate_dev(vo_ctx* ctx, const double* d_p1, const double* d_p2, int 
 int vo_triangulate_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int n, const double* h_proj1,
                         int proj1_per_point, const double* h_proj2, int mode, double* h_out);
 
+/* ---- Two-view bootstrap: src/vo/landmarks/triangulation.py:88-350 (as src/main.py:185-222 configures it) ---- */
+/* LandmarksTriangulator(use_ransac=True, use_opencv=True).triangulate_matches for n_seq independent frame pairs, one
+ * CTA each: cv2.findFundamentalMat(FM_RANSAC, threshold, confidence) restated (float32 points, cv::RNG subsets of 7
+ * with the collinearity check, 7-point solver, float32 epipolar errors, RANSACUpdateNumIters; triangulation.py:126-134),
+ * E = K^T F K (:224-243), the four [R | t] candidates (:245-277), cheirality vote by DLT triangulation of the F inliers
+ * and the landmarks of ALL matches with the winner (:279-350).
+ * p1, p2 float64 [n_seq][N][2] (frame 1 / frame 2 pixels); n_pts int32 [n_seq] or NULL (= N); 15 <= n <= 8192 (below 15
+ * points OpenCV switches to LMedS: info[0] = 0 is returned).  Outputs: F float64 [n_seq][9] (F33 = 1), M float64
+ * [n_seq][12] (row-major 3x4, frame 1 -> frame 2), landmarks float64 [n_seq][N][3] (frame-1 coordinates), mask uint8
+ * [n_seq][N] (F inlier and in front of both cameras = triangulate_matches' third result), f_mask uint8 [n_seq][N] or
+ * NULL (F inliers = _find_fundamental_matrix_ransac's second result), info int32 [n_seq][4] = {model found, RANSAC
+ * iterations, F inliers, cheirality-valid inliers}.                                                               */
+int vo_bootstrap_dev(vo_ctx* ctx, const double* d_p1, const double* d_p2, int n_seq, int N, const int32_t* d_n_pts,
+                     const double* K9, double threshold, double confidence, int max_iters, double* d_F, double* d_M,
+                     double* d_landmarks, uint8_t* d_mask, uint8_t* d_f_mask, int32_t* d_info, void* stream);
+int vo_bootstrap_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int n_seq, int N, const int32_t* h_n_pts,
+                      const double* K9, double threshold, double confidence, int max_iters, double* h_F, double* h_M,
+                      double* h_landmarks, uint8_t* h_mask, uint8_t* h_f_mask, int32_t* h_info);
+
 /* ---- The front end as one resident object: src/main.py:248-287 (loop body) --------------------- */
 /* Per-sequence state (pyramids of the previous / current frame, last keypoints) stays in HBM; one
  * call advances n_seq independent sequences by one frame: pyramid -> KLT (previous keypoints into

@@ -375,12 +375,61 @@ def make_loop():
     print("loop.npz", {k: np.shape(v) for k, v in out.items() if not k.startswith(("cv_", "noref_"))})
 
 
+def make_bootstrap():
+    """The two-view bootstrap (triangulation.py:88-350) as main.py:185-193 configures it, run by the REFERENCE's
+    LandmarksTriangulator: (a) on the matches of its own KLT tracker between KITTI frames 0 and 2 (main.py:203-222),
+    (b) on synthetic two-view problems with outliers.  Inputs and every result travel in bootstrap.npz."""
+    from vo.features import Tracker
+    from vo.landmarks import LandmarksTriangulator
+    from vo.primitives import Frame, State
+    from vo.sensors import Camera
+
+    vals = open(f"{REF}/tests/test_data/kitti/05/calib.txt").readlines()[1].split(" ")[1:]
+    K = np.array([np.float32(v) for v in vals]).reshape(3, 4)[:, :3]
+    camera = Camera(intrinsic_matrix=K)
+    out = {"K": K}
+
+    def run(tag, p1, p2, thr, conf):
+        tri = LandmarksTriangulator(camera1=camera, camera2=camera, use_ransac=True, use_opencv=True, outlier_ratio=0.9,
+                                    ransac_threshold=thr, ransac_confidence=conf)
+        F, f_inl = tri._find_fundamental_matrix_ransac(p1, p2)
+        M, land, inl = tri._find_relative_pose(p1, p2)
+        out.update({tag + "p1": p1.reshape(-1, 2), tag + "p2": p2.reshape(-1, 2), tag + "thr": thr, tag + "conf": conf,
+                    tag + "F": F, tag + "f_inl": f_inl, tag + "M": M, tag + "land": land.reshape(-1, 3), tag + "inl": inl})
+        print(tag, p1.shape[0], "points", int(f_inl.sum()), "F inliers", int(inl.sum()), "valid")
+
+    frames = []
+    for i in range(3):
+        f = Frame(cv2.imread(f"{REF}/tests/test_data/kitti/05/image_0/{i:06d}.png"), sensor=camera, intrinsics=K)
+        f.frame_id = i
+        frames.append(f)
+    np.random.seed(0)
+    state = State(frames[0])
+    tracker = Tracker(frames[0], mode="klt")
+    matches = tracker.trackFeatures(state.curr_frame, frames[2])
+    run("kitti_", matches.frame1.features.matched_candidate_inliers_keypoints.astype(np.float64),
+        matches.frame2.features.matched_candidate_inliers_keypoints.astype(np.float64), 0.25, 0.999)
+    rng = np.random.default_rng(7)
+    for j, (N, frac, thr, conf) in enumerate([(300, 0.2, 0.25, 0.999), (1000, 0.4, 1.0, 0.99), (64, 0.1, 3.0, 0.999)]):
+        X = np.c_[rng.uniform(-10, 10, N), rng.uniform(-3, 3, N), rng.uniform(6, 40, N)]
+        R, _ = cv2.Rodrigues(rng.uniform(-0.05, 0.05, 3))
+        t = np.array([0.1, -0.05, -1.0]) + rng.normal(0, 0.05, 3)
+        a = (K.astype(np.float64) @ X.T).T
+        b = (K.astype(np.float64) @ (X @ R.T + t).T).T
+        p1 = a[:, :2] / a[:, 2:] + rng.normal(0, 0.1, (N, 2))
+        p2 = b[:, :2] / b[:, 2:] + rng.normal(0, 0.1, (N, 2))
+        no = int(frac * N)
+        p2[:no] += rng.uniform(-40, 40, (no, 2))
+        run(f"syn{j}_", p1.reshape(-1, 2, 1), p2.reshape(-1, 2, 1), thr, conf)
+    np.savez_compressed(os.path.join(OUT, "bootstrap.npz"), **out)
+
+
 def to_pixels(K, M, X):
     x = K @ (M[:, :3] @ X + M[:, 3:])
     return x[:2] / x[2:]
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["harris", "klt", "p3p", "triangulation", "bookkeeping", "loop"]
+    which = sys.argv[1:] or ["harris", "klt", "p3p", "triangulation", "bookkeeping", "loop", "bootstrap"]
     for w in which:
         globals()["make_" + w]()

@@ -336,3 +336,67 @@ def test_cv_solvepnpransac_restatement_equals_cv2(golden):
     assert np.array_equal(lo.state, g["cv_f3_state"]) and int(lo.cand.sum()) == int(g["cv_f3_n_candidates"])
     ref = g["cv_f3_curr_pose"]
     assert np.abs(lo.curr_pose[:3, :3] - ref[:3, :3]).max() < 2e-4 and np.abs(lo.curr_pose[:3, 3] - ref[:3, 3]).max() < 5e-3
+
+
+# ---- two-view bootstrap (triangulation.py:88-350 with cv2.findFundamentalMat's RANSAC restated) ----
+BOOT_TAGS = ("kitti_", "syn0_", "syn1_", "syn2_")
+
+
+def test_bootstrap_oracle_vs_reference(golden):
+    """oracle/bootstrap.py against the REFERENCE's LandmarksTriangulator (tests/golden/bootstrap.npz): the F inlier mask
+    and the final mask are EQUAL, F within 1e-9 (relative, F33 = 1), [R | t] within 1e-9, landmarks within 1e-6 relative."""
+    from oracle import bootstrap as ob
+    g = golden("bootstrap")
+    for tag in BOOT_TAGS:
+        F, M, land, mask, it = ob.bootstrap(g[tag + "p1"], g[tag + "p2"], g["K"], float(g[tag + "thr"]), float(g[tag + "conf"]))
+        f_inl = ob.cv_fm_errors_f32(F, g[tag + "p1"].astype(np.float32), g[tag + "p2"].astype(np.float32)) <= np.float32(float(g[tag + "thr"]) ** 2)
+        assert np.array_equal(f_inl, g[tag + "f_inl"]), tag
+        assert np.abs(F - g[tag + "F"]).max() <= 1e-9 * np.abs(g[tag + "F"]).max(), tag
+        assert np.array_equal(mask, g[tag + "inl"]), tag
+        assert np.abs(M - g[tag + "M"]).max() < 1e-9, tag
+        ref = g[tag + "land"]
+        assert np.nanmax(np.abs(land - ref) / (1 + np.abs(ref))) < 1e-6, tag
+
+
+def test_bootstrap_oracle_vs_cv2_live():
+    """The restated RANSAC against cv2.findFundamentalMat itself on random two-view problems (three thresholds / confidences,
+    10-50 % outliers): masks equal, F to rounding; and the 7-point solver against FM_7POINT (same solutions, any order)."""
+    import itertools
+    import cv2
+    from oracle import bootstrap as ob
+    K = np.array([[718.856, 0, 607.19], [0, 718.856, 185.2], [0, 0, 1]])
+
+    def two_view(N, seed, out_frac, noise=0.3):
+        r = np.random.default_rng(seed)
+        X = np.c_[r.uniform(-10, 10, N), r.uniform(-3, 3, N), r.uniform(6, 40, N)]
+        R, _ = cv2.Rodrigues(r.uniform(-0.05, 0.05, 3))
+        t = np.array([0.1, -0.05, -1.0]) + r.normal(0, 0.05, 3)
+        a = (K @ X.T).T
+        b = (K @ (X @ R.T + t).T).T
+        p1 = a[:, :2] / a[:, 2:] + r.normal(0, noise, (N, 2))
+        p2 = b[:, :2] / b[:, 2:] + r.normal(0, noise, (N, 2))
+        no = int(out_frac * N)
+        p2[:no] += r.uniform(-40, 40, (no, 2))
+        return p1, p2
+    for s in range(40):
+        p1, p2 = two_view(7, s, 0)
+        Fcv, _ = cv2.findFundamentalMat(p1.reshape(-1, 1, 2).astype(np.float32), p2.reshape(-1, 1, 2).astype(np.float32), cv2.FM_7POINT)
+        mine = ob.cv_fm_7point(p1, p2)
+        Fcv = np.zeros((0, 3, 3)) if Fcv is None else Fcv.reshape(-1, 3, 3)
+        assert len(mine) == len(Fcv), s
+        best = min(max(np.abs(mine[i] - Fcv[j]).max() / np.abs(Fcv[j]).max() for i, j in enumerate(perm))
+                   for perm in itertools.permutations(range(len(Fcv)))) if len(Fcv) else 0.0
+        assert best < 1e-6, (s, best)
+    equal = 0
+    for s in range(12):
+        N = [60, 200, 500, 1000][s % 4]
+        p1, p2 = two_view(N, 100 + s, [0.1, 0.3, 0.5][s % 3])
+        thr, conf = [(0.25, 0.999), (1.0, 0.99), (3.0, 0.999)][s % 3]
+        Fcv, mcv = cv2.findFundamentalMat(points1=p1.reshape(-1, 2, 1), points2=p2.reshape(-1, 2, 1), method=cv2.FM_RANSAC,
+                                          ransacReprojThreshold=thr, confidence=conf)
+        F, m, _ = ob.cv_find_fundamental_ransac(p1, p2, thr, conf)
+        same = np.array_equal(m, mcv.astype(bool).ravel())
+        equal += same
+        if same:
+            assert np.abs(F - Fcv).max() <= 1e-9 * np.abs(Fcv).max()
+    assert equal >= 11, equal

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvo_b200.so")
-SOURCES = ["abi.cu", "frontend.cu", "gftt.cu", "harris.cu", "klt.cu", "match.cu", "p3p.cu", "pipeline.cu", "triangulation.cu"]
+SOURCES = ["abi.cu", "bootstrap.cu", "frontend.cu", "gftt.cu", "harris.cu", "klt.cu", "match.cu", "p3p.cu", "pipeline.cu", "triangulation.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -580,4 +580,47 @@ int vo_triangulate_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int
     return VO_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Two-view bootstrap
+// ------------------------------------------------------------------------------------------
+int vo_bootstrap_dev(vo_ctx* ctx, const double* d_p1, const double* d_p2, int n_seq, int N, const int32_t* d_n_pts,
+                     const double* K9, double threshold, double confidence, int max_iters, double* d_F, double* d_M,
+                     double* d_landmarks, uint8_t* d_mask, uint8_t* d_f_mask, int32_t* d_info, void* stream) {
+    VO_REQUIRE(ctx && d_p1 && d_p2 && K9 && d_F && d_M && d_landmarks && d_mask && d_info, "vo_bootstrap_dev: null argument");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    return vo_launch_bootstrap(ctx, d_p1, d_p2, n_seq, N, d_n_pts, K9, threshold, confidence, max_iters, d_F, d_M,
+                               d_landmarks, d_mask, d_f_mask, d_info, pick_stream(ctx, stream));
+}
+
+int vo_bootstrap_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int n_seq, int N, const int32_t* h_n_pts,
+                      const double* K9, double threshold, double confidence, int max_iters, double* h_F, double* h_M,
+                      double* h_landmarks, uint8_t* h_mask, uint8_t* h_f_mask, int32_t* h_info) {
+    VO_REQUIRE(ctx && h_p1 && h_p2 && K9 && h_F && h_M && h_landmarks && h_mask && h_info, "vo_bootstrap_host: null argument");
+    VO_REQUIRE(n_seq >= 1 && N >= 1, "vo_bootstrap_host: n_seq and N must be positive");
+    VO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t S = (size_t)n_seq, rows = S * (size_t)N;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_a = carve(rows * 16), o_b = carve(rows * 16), o_n = carve(S * 4), o_F = carve(S * 72), o_M = carve(S * 96);
+    const size_t o_l = carve(rows * 24), o_m = carve(rows), o_f = carve(rows), o_i = carve(S * 16);
+    int rc = vo_buf_reserve(&ctx->scratch[9], off);
+    if (rc) return rc;
+    unsigned char* b = (unsigned char*)ctx->scratch[9].p;
+    VO_CUDA(cudaMemcpyAsync(b + o_a, h_p1, rows * 16, cudaMemcpyHostToDevice, s));
+    VO_CUDA(cudaMemcpyAsync(b + o_b, h_p2, rows * 16, cudaMemcpyHostToDevice, s));
+    if (h_n_pts) VO_CUDA(cudaMemcpyAsync(b + o_n, h_n_pts, S * 4, cudaMemcpyHostToDevice, s));
+    if ((rc = vo_launch_bootstrap(ctx, (double*)(b + o_a), (double*)(b + o_b), n_seq, N, h_n_pts ? (int*)(b + o_n) : nullptr, K9,
+                                  threshold, confidence, max_iters, (double*)(b + o_F), (double*)(b + o_M), (double*)(b + o_l),
+                                  b + o_m, b + o_f, (int*)(b + o_i), s))) return rc;
+    VO_CUDA(cudaMemcpyAsync(h_F, b + o_F, S * 72, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_M, b + o_M, S * 96, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_landmarks, b + o_l, rows * 24, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_mask, b + o_m, rows, cudaMemcpyDeviceToHost, s));
+    if (h_f_mask) VO_CUDA(cudaMemcpyAsync(h_f_mask, b + o_f, rows, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaMemcpyAsync(h_info, b + o_i, S * 16, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
+    return VO_OK;
+}
+
 }  // extern "C"

@@ -62,7 +62,7 @@ struct vo_ctx {
 // A context is bound to ONE device and its launchers carve working memory from ctx-owned scratch: calls that
 // share a vo_ctx must be ordered on one stream (or be externally serialised).  Use one vo_ctx per stream.
 enum { VO_ATTR_HARRIS_FAST = 1, VO_ATTR_HARRIS_TILED = 2, VO_ATTR_NMS = 4, VO_ATTR_KLT = 8, VO_ATTR_MATCH = 16,
-       VO_ATTR_GFTT = 32, VO_ATTR_PIPE = 64 };
+       VO_ATTR_GFTT = 32, VO_ATTR_PIPE = 64, VO_ATTR_BOOT = 128 };
 static inline bool vo_ctx_once(vo_ctx* ctx, unsigned bit) {
     if (ctx->attr_done & bit) return false;
     ctx->attr_done |= bit;

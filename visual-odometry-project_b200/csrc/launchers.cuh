@@ -50,3 +50,7 @@ int vo_launch_gftt_eig(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, i
 int vo_launch_gftt(vo_ctx* ctx, const uint8_t* d_img, int n_frames, int H, int W, size_t pitch, size_t frame_stride,
                    int max_corners, double quality, double min_distance, int block_size, float* d_eig, float* d_xy, int* d_n,
                    unsigned int* d_stats_or_null, cudaStream_t stream);
+// bootstrap.cu
+int vo_launch_bootstrap(vo_ctx* ctx, const double* d_p1, const double* d_p2, int n_seq, int N, const int* d_n_pts,
+                        const double* K9, double threshold, double confidence, int max_iters, double* d_F, double* d_M,
+                        double* d_landmarks, unsigned char* d_mask, unsigned char* d_f_mask, int* d_info, cudaStream_t stream);

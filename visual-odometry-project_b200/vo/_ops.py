@@ -223,6 +223,33 @@ def triangulate(p1, p2, C1, C2, mode=0, ctx=None):
     return out
 
 
+def bootstrap(points1, points2, K, threshold, confidence, max_iters=1000, ctx=None):
+    """Two-view bootstrap of triangulation.py:88-350 (use_ransac=True, use_opencv=True) on the GPU: cv2.findFundamentalMat's
+    RANSAC, essential-matrix decomposition, cheirality vote, landmarks of all matches.
+    points (N, 2[, 1]) -> dict(found, F (3, 3), M (3, 4), landmarks (N, 3), mask (N,), f_mask (N,), iterations)."""
+    ctx = _ctx(ctx)
+    a = np.ascontiguousarray(np.asarray(points1, dtype=np.float64).reshape(-1, 2))
+    b = np.ascontiguousarray(np.asarray(points2, dtype=np.float64).reshape(-1, 2))
+    if a.shape != b.shape:
+        raise ValueError("bootstrap: input points dimension mismatch")
+    n = a.shape[0]
+    if n < 15:
+        raise ValueError("bootstrap: cv2.findFundamentalMat(FM_RANSAC) needs at least 15 matches for its RANSAC path "
+                         f"(got {n}); the GPU path restates that one only")
+    K9 = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    F, M = np.empty(9, np.float64), np.empty(12, np.float64)
+    land = np.empty((n, 3), np.float64)
+    mask, f_mask = np.empty(n, np.uint8), np.empty(n, np.uint8)
+    info = np.zeros(4, np.int32)
+    rc = nat.lib().vo_bootstrap_host(ctx.handle, nat.ptr(a), nat.ptr(b), 1, n, None, nat.ptr(K9), float(threshold),
+                                     float(confidence), int(max_iters), nat.ptr(F), nat.ptr(M), nat.ptr(land),
+                                     nat.ptr(mask), nat.ptr(f_mask), nat.ptr(info))
+    nat.check(rc, "vo_bootstrap_host")
+    return {"found": bool(info[0]), "F": F.reshape(3, 3), "M": M.reshape(3, 4), "landmarks": land,
+            "mask": mask.astype(bool), "f_mask": f_mask.astype(bool), "iterations": int(info[1]),
+            "n_f_inliers": int(info[2]), "n_valid": int(info[3])}
+
+
 def harris_descriptors(img, kp_xy, desc_radius=9, ctx=None):
     """extractDescriptors alone (harris.py:160-194): uint8 (K, (2r+1)^2) patches for given keypoints."""
     ctx = _ctx(ctx)

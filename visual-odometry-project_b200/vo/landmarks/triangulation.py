@@ -1,8 +1,10 @@
 """Landmark triangulation and two-view bootstrapping (reference: src/vo/landmarks/triangulation.py).
 
-GPU: _linear_triangulation and triangulate_candidates (vo_triangulate_*).  The one-off bootstrap
-(fundamental matrix, essential-matrix decomposition) is host code, as in the reference; its
-triangulations still run on the GPU."""
+GPU: _linear_triangulation and triangulate_candidates (vo_triangulate_*), and the two-view bootstrap as
+src/main.py configures it (use_ransac=True, use_opencv=True): cv2.findFundamentalMat's RANSAC restated, the
+essential-matrix decomposition, the cheirality vote and the landmarks in ONE call (vo_bootstrap_host).  The
+other bootstrap configurations (the reference's own 8-point RANSAC, no RANSAC) keep the reference's host
+arithmetic; their triangulations still run on the GPU."""
 import numpy as np
 
 from vo import _ops
@@ -44,21 +46,27 @@ class LandmarksTriangulator:
         assert C1.shape == (3, 4) and C2.shape == (3, 4), "Matrix C1 and C2 must be 3 rows and 4 columns [R T]"
         return _ops.triangulate(points1, points2, C1, C2, mode=0).reshape(-1, 3, 1)
 
-    # ---- bootstrap (host) ---------------------------------------------------------------------
+    # ---- bootstrap ----------------------------------------------------------------------------
     def triangulate_matches(self, matches):
         """Relative pose + landmarks from the matched keypoints of two frames (triangulation.py:88-108)."""
         p1 = matches.frame1.features.matched_candidate_inliers_keypoints
         p2 = matches.frame2.features.matched_candidate_inliers_keypoints
         return self._find_relative_pose(p1, p2)
 
+    def _gpu_bootstrap(self, points1, points2):
+        K1, K2 = self.camera1.intrinsic_matrix, self.camera2.intrinsic_matrix
+        if not np.array_equal(K1, K2):
+            raise NotImplementedError("the GPU bootstrap assumes one camera (main.py passes the same Camera twice)")
+        r = _ops.bootstrap(points1, points2, K1, self._ransac_reproj_threshold, self._ransac_confidence)
+        if not r["found"]:
+            raise RuntimeError("bootstrap: the fundamental-matrix RANSAC found no model")
+        return r
+
     def _find_fundamental_matrix_ransac(self, points1, points2):
-        """F and its inlier mask (triangulation.py:110-163)."""
+        """F and its inlier mask (triangulation.py:110-163); use_opencv: cv2.findFundamentalMat's RANSAC on the GPU."""
         if self._use_opencv:
-            import cv2
-            F, inl = cv2.findFundamentalMat(points1=points1, points2=points2, method=cv2.FM_RANSAC,
-                                            ransacReprojThreshold=self._ransac_reproj_threshold,
-                                            confidence=self._ransac_confidence)
-            return F, inl.astype(bool).flatten()
+            r = self._gpu_bootstrap(points1, points2)
+            return r["F"], r["f_mask"]
         n1, T1 = normalize_points(points1)
         n2, T2 = normalize_points(points2)
 
@@ -118,6 +126,9 @@ class LandmarksTriangulator:
     def _find_relative_pose(self, points1, points2):
         """M = [R t] from frame 1 to frame 2, landmarks in frame-1 coordinates and (with RANSAC) the
         inlier mask (triangulation.py:279-350)."""
+        if self._use_ransac and self._use_opencv:          # main.py's configuration: everything in one GPU call
+            r = self._gpu_bootstrap(points1, points2)
+            return r["M"], r["landmarks"].reshape(-1, 3, 1), r["mask"]
         if self._use_ransac:
             E, inl = self._find_essential_matrix(points1, points2)
             q1, q2 = points1[inl], points2[inl]
