@@ -8,9 +8,11 @@
 //                                                                       _find_relative_pose)
 // as src/main.py:185-222 configures them (use_ransac=True, use_opencv=True, threshold 0.25, confidence 0.999).
 //
-// cv2.findFundamentalMat is restated (OpenCV calib3d fundam.cpp / ptsetreg.cpp; see oracle/bootstrap.py for the list of
-// rules): float32 points, cv::RNG(2^64-1) subsets of 7 with the collinearity check on the last point, run7Point with
-// solveCubic's closed forms, float32 epipolar errors against (float)thr^2, RANSACUpdateNumIters.  The serial parts of
+// cv2.findFundamentalMat is restated (OpenCV calib3d fundam.cpp / ptsetreg.cpp): float32 points, cv::RNG(2^64-1)
+// subsets of 7 (redraw on repetition; the whole subset is redrawn when its last point is collinear with two earlier
+// ones in either image), run7Point (normalised points, null space of the 7x9 system, cubic in lambda by solveCubic's
+// closed forms, F33 = 1), float32 epipolar errors against (float)thr^2, a model accepted when its count exceeds
+// max(best, 6), RANSACUpdateNumIters after every improvement.  The serial parts of
 // OpenCV's loop (the generator and the accept / update rule) run on thread 0; a round of BS_ROUND samples is solved
 // by 32 threads spread over the warps, and every (sample, root) model is scored by a whole warp with ballot-free
 // shuffle sums.  Float64 throughout, no FMA contraction (build flag).
