@@ -323,6 +323,16 @@ int vo_pipeline_prime_host(vo_pipeline* pl, const uint8_t* h_frames, int init_ta
 /* Device-resident step (asynchronous): d_frames uint8 [n_seq] frames.  The summary [n_seq][VO_PIPE_SUMMARY_DOUBLES]
  * of the last step_dev is at vo_pipeline_summary_dev().                                                          */
 int vo_pipeline_step_dev(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, size_t frame_stride, void* stream);
+/* The two-view bootstrap of src/main.py:203-231 as one step of the resident pipeline: the primed frame's corners are
+ * tracked into `frames` (klt.py:233-266), the matched rows go through vo_bootstrap_* (triangulation.py:88-350, threshold /
+ * confidence as main.py:185-193 passes them: 0.25, 0.999; max_iters = OpenCV's default 1000), then update_with_local_pose,
+ * update_with_local_landmarks and reset_outliers (state.py:25-110, 167-178) are applied to the table.  The summary row
+ * holds the new pose; counters: 3 = matched pairs, 4 = inliers that became landmarks, 6 = triangulated rows, 8 = RANSAC
+ * iterations, 7 |= 2 when no model was found (fewer than 15 pairs or a degenerate scene; the table is left matched). */
+int vo_pipeline_bootstrap_dev(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, size_t frame_stride, double threshold,
+                              double confidence, int max_iters, void* stream);
+int vo_pipeline_bootstrap_host(vo_pipeline* pl, const uint8_t* h_frames, double threshold, double confidence, int max_iters,
+                               double* h_summary);
 const double* vo_pipeline_summary_dev(vo_pipeline* pl);
 /* A step's detector and its pose / state-update kernels run on internal streams and may still be in flight when
  * step_dev returns control to `stream` (they run under the NEXT step's tracker).  vo_pipeline_sync_dev makes `stream`

@@ -249,3 +249,71 @@ def test_pipeline_long_run_edge_cases(ctx):
                 assert got["num_features"] == los[s].num_features, (opencv, t, s)
         assert seen["overflow"] >= 1 and seen["no_pose"] >= 1 and seen["redetect"] >= 2, seen
         pl.close()
+
+
+def test_pipeline_bootstraps_itself_on_kitti(golden):
+    """main.py:203-231 entirely on the device: Shi-Tomasi corners of frame 0 (KLTTracker.__init__), tracked into frame 2,
+    relative pose by the restated cv2.findFundamentalMat RANSAC + essential-matrix decomposition + cheirality vote,
+    landmarks and state updates -- against the table the REFERENCE's own classes had after their bootstrap
+    (tests/golden/loop.npz boot_*), then the loop body on frames 3-5 against the reference's poses."""
+    from vo.pipeline import DETECTOR_GFTT, Pipeline
+    g = golden("loop")
+    frames = kitti_frames()
+    H, W = frames[0].shape
+    pl = Pipeline(1, H, W, g["K"], capacity=512, detector=DETECTOR_GFTT, det_max_corners=500, refine=True, p3p_opencv=False)
+    pl.prime(frames[0][None], init_tables=True)
+    t0 = pl.read_table(0)
+    assert np.array_equal(t0["kp"], g["init_kp"])                                       # cv2.goodFeaturesToTrack's corners
+    summ = pl.bootstrap(frames[2][None], threshold=0.25, confidence=0.999)
+    assert not (summ["flags"][0] & 2)
+    t = pl.read_table(0)
+    assert t["n"] == len(g["boot_kp"]) == summ["n_rows"][0]
+    assert np.abs(t["kp"] - g["boot_kp"]).max() < 1e-2                                   # the tracker's tolerance (cv2: 1e-2 px)
+    assert np.array_equal(t["state"], g["boot_state"])
+    assert int(summ["n_tri"][0]) == int((g["boot_state"] == 2).sum())
+    assert np.allclose(t["curr_pose"], g["boot_curr_pose"], atol=1e-6)
+    assert np.allclose(summ["pose"][0], g["boot_curr_pose"][:3], atol=1e-6)
+    assert np.array_equal(np.isnan(t["land"]), np.isnan(g["boot_land"]))
+    rel = np.abs(t["land"] - g["boot_land"]) / (1 + np.abs(g["boot_land"]))
+    assert np.nanmedian(rel) < 1e-5 and np.nanmax(rel) < 1e-2                            # 1e-3 px of the tracker at depth 45
+    assert np.abs(t["track"] - g["boot_track"]).max() < 1e-2
+    assert np.array_equal(np.isnan(t["pose"]), np.isnan(g["boot_pose"]))
+    assert np.allclose(t["pose"], g["boot_pose"], atol=1e-6, equal_nan=True)
+    assert not t["cand"].any()
+    for i in (3, 4, 5):                                                                  # and the loop carries on from there
+        s = pl.step(frames[i][None])
+        ref = g[f"f{i}_curr_pose"]
+        tol_R, tol_t = (2e-4, 5e-3) if i == 3 else (6e-4, 1.5e-2)
+        assert np.abs(s["pose"][0][:, :3] - ref[:3, :3]).max() < tol_R and np.abs(s["pose"][0][:, 3] - ref[:3, 3]).max() < tol_t, i
+    tt = pl.read_table(0)
+    assert np.array_equal(tt["inliers"], tt["inliers"]) and tt["n"] == len(g["f5_kp"])
+    pl.close()
+
+
+def test_pipeline_bootstrap_batched_synthetic(ctx):
+    """Several sequences bootstrap in one call; each must end where it ends alone, and a sequence with too few matches
+    reports "no model" (flag 2) and keeps its matched table."""
+    from conftest import synthetic_image
+    from vo.pipeline import DETECTOR_HARRIS, Pipeline
+    S, H, W, KP = 3, 160, 240, 150
+    K = np.array([[300.0, 0, W / 2], [0, 300.0, H / 2], [0, 0, 1]])
+    big = [synthetic_image(H + 40, W + 60, seed=90 + s) for s in range(S)]
+    f0 = np.stack([np.ascontiguousarray(b[8:8 + H, 8:8 + W]) for b in big])
+    f1 = np.stack([np.ascontiguousarray(b[10:10 + H, 14:14 + W]) for b in big])
+    f0[2] = 128                                           # sequence 2: a blank first frame, no corner survives the tracker
+    pl = Pipeline(S, H, W, K, capacity=512, detector=DETECTOR_HARRIS, det_max_corners=KP)
+    pl.prime(f0, init_tables=True)
+    summ = pl.bootstrap(f1, threshold=1.0, confidence=0.99)
+    tabs = [pl.read_table(s) for s in range(S)]
+    pl.close()
+    for s in range(2):
+        one = Pipeline(1, H, W, K, capacity=512, detector=DETECTOR_HARRIS, det_max_corners=KP)
+        one.prime(f0[s][None], init_tables=True)
+        s1 = one.bootstrap(f1[s][None], threshold=1.0, confidence=0.99)
+        t1 = one.read_table(0)
+        one.close()
+        assert np.array_equal(s1["counts"][0], summ["counts"][s])
+        for key in ("kp", "state", "track", "cand"):
+            assert np.array_equal(tabs[s][key], t1[key]), (s, key)
+        assert np.array_equal(tabs[s]["land"], t1["land"], equal_nan=True) and np.array_equal(tabs[s]["curr_pose"], t1["curr_pose"])
+    assert summ["flags"][2] & 2 and (tabs[2]["state"] <= 1).all()

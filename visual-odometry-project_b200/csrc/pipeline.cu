@@ -812,6 +812,112 @@ pipe_update_kernel(PipeTable T, PipeSeq Q, PipeParams P, const uint8_t* __restri
     if (tid < VO_PIPE_NCOUNTS) reinterpret_cast<int*>(out + 12)[tid] = cnt[tid];
 }
 
+// ---- two-view bootstrap of a resident sequence (main.py:203-231) ---------------------------------------------
+// After the regroup every kept row is matched (state 1) with its track start in the first frame: rows [n_tri, n_keep)
+// are `matched_candidate_inliers` of both frames.  Their (track start, keypoint) pairs go to the bootstrap kernel
+// (bootstrap.cu) as float64, as the reference hands cv2 its float keypoints.
+__global__ void __launch_bounds__(256)
+pipe_boot_gather_kernel(PipeTable T, PipeSeq Q, PipeParams P, double* __restrict__ p1, double* __restrict__ p2, int* __restrict__ n_pts) {
+    const int s = blockIdx.x, C = P.C;
+    const int n = Q.n_keep[s], n0 = Q.n_tri[s];
+    const size_t base = (size_t)s * C;
+    for (int j = threadIdx.x; j < n - n0; j += blockDim.x) {
+        const float2 a = T.track[base + n0 + j], b = T.kp[base + n0 + j];
+        p1[(base + j) * 2] = (double)a.x; p1[(base + j) * 2 + 1] = (double)a.y;
+        p2[(base + j) * 2] = (double)b.x; p2[(base + j) * 2 + 1] = (double)b.y;
+    }
+    if (threadIdx.x == 0) n_pts[s] = n - n0;
+}
+
+// main.py:213-222: update_with_local_pose(M) (state.py:25-37), update_with_local_landmarks(landmarks[inliers], mask)
+// (state.py:51-110, with the cheirality check of all rows), reset_outliers(~inliers) (state.py:167-178); summary row.
+__global__ void __launch_bounds__(UP_THREADS)
+pipe_boot_apply_kernel(PipeTable T, PipeSeq Q, PipeParams P, const double* __restrict__ M_all, const double* __restrict__ land,
+                       const uint8_t* __restrict__ mask, const int* __restrict__ info, double* __restrict__ summary) {
+    __shared__ double s_c2w[12], s_c2w_prev[12], s_w2c[12], s_w2c_prev[12];
+    __shared__ int s_nbehind, s_ntri, s_ninl;
+    const int s = blockIdx.x, tid = threadIdx.x, C = P.C;
+    const int n = Q.n_keep[s], n0 = Q.n_tri[s];
+    const size_t base = (size_t)s * C;
+    int* cnt = Q.counts + (size_t)s * VO_PIPE_NCOUNTS;
+    const bool found = info[4 * s] != 0;
+    if (tid == 0) {
+        double* cw = Q.c2w + (size_t)s * 12; double* cp = Q.c2w_prev + (size_t)s * 12;
+        double* wc = Q.w2c + (size_t)s * 12; double* wp = Q.w2c_prev + (size_t)s * 12;
+        for (int k = 0; k < 12; k++) { cp[k] = cw[k]; wp[k] = wc[k]; }         // state.py:19-23: prev <- curr
+        if (found) {
+            const double* M = M_all + (size_t)s * 12;                          // [R | t], frame 1 -> frame 2
+            double inv[12];                                                    // inv(M) = [R^T | -R^T t]
+            for (int i = 0; i < 3; i++) {
+                for (int j = 0; j < 3; j++) inv[4 * i + j] = M[4 * j + i];
+                inv[4 * i + 3] = -(M[i] * M[3] + M[4 + i] * M[7] + M[8 + i] * M[11]);
+            }
+            double c[12];                                                      // curr = prev @ inv(M)
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 4; j++)
+                    c[4 * i + j] = cp[4 * i] * inv[j] + cp[4 * i + 1] * inv[4 + j] + cp[4 * i + 2] * inv[8 + j] + (j == 3 ? cp[4 * i + 3] : 0.0);
+            for (int k = 0; k < 12; k++) cw[k] = c[k];
+            // world-to-camera in the estimator's layout (R row-major, then t): the rigid inverse of curr
+            for (int i = 0; i < 3; i++) {
+                for (int j = 0; j < 3; j++) wc[3 * i + j] = c[4 * j + i];
+                wc[9 + i] = -(c[i] * c[3] + c[4 + i] * c[7] + c[8 + i] * c[11]);
+            }
+        }
+        for (int k = 0; k < 12; k++) { s_c2w[k] = cw[k]; s_c2w_prev[k] = cp[k]; s_w2c[k] = wc[k]; s_w2c_prev[k] = wp[k]; }
+        s_nbehind = 0; s_ntri = 0; s_ninl = 0;
+    }
+    __syncthreads();
+    if (found) {
+        int my_inl = 0;
+        for (int i = tid; i < n; i += UP_THREADS) {
+            const size_t r = base + i;
+            T.cand[r] = 0;
+            if (i < n0 || !mask[base + i - n0]) continue;
+            const double* X = land + (base + i - n0) * 3;                      // frame-1 coordinates -> world (state.py:59-63)
+            for (int k = 0; k < 3; k++)
+                T.land[r * 3 + k] = s_c2w_prev[4 * k] * X[0] + s_c2w_prev[4 * k + 1] * X[1] + s_c2w_prev[4 * k + 2] * X[2] + s_c2w_prev[4 * k + 3];
+            T.state[r] = 2;
+            my_inl++;
+        }
+        if (my_inl) atomicAdd(&s_ninl, my_inl);
+        __syncthreads();
+        int my_b = 0;
+        for (int i = tid; i < n; i += UP_THREADS) {                            // state.py:92-110 (all rows)
+            const size_t r = base + i;
+            const double X = T.land[r * 3], Y = T.land[r * 3 + 1], Z = T.land[r * 3 + 2];
+            const double zc = s_w2c[6] * X + s_w2c[7] * Y + s_w2c[8] * Z + s_w2c[11];
+            const double zp = s_w2c_prev[6] * X + s_w2c_prev[7] * Y + s_w2c_prev[8] * Z + s_w2c_prev[11];
+            bool reset = false;
+            if (zc < 0.0 || zp < 0.0) {
+                for (int k = 0; k < 3; k++) T.land[r * 3 + k] = nan64();
+                reset = true;
+                my_b++;
+            }
+            if (i >= n0 && !mask[base + i - n0]) reset = true;                 // main.py:211-212, 222: the bootstrap's outliers
+            if (reset) {
+                T.state[r] = 0;
+                T.track[r] = T.kp[r];
+                for (int k = 0; k < 12; k++) T.pose[r * 12 + k] = s_c2w[k];
+            }
+        }
+        if (my_b) atomicAdd(&s_nbehind, my_b);
+    }
+    __syncthreads();
+    int my_t = 0;
+    for (int i = tid; i < n; i += UP_THREADS) my_t += T.state[base + i] == 2;
+    if (my_t) atomicAdd(&s_ntri, my_t);
+    __syncthreads();
+    if (tid == 0) {
+        cnt[0] = n; cnt[3] = n - n0; cnt[4] = s_ninl; cnt[5] = 0; cnt[6] = s_ntri; cnt[8] = info[4 * s + 1]; cnt[9] = info[4 * s + 1];
+        cnt[10] = s_nbehind; cnt[11] = 0;
+        if (!found) cnt[7] |= 2;
+    }
+    double* out = summary + (size_t)s * VO_PIPE_SUMMARY_DOUBLES;
+    if (tid < 12) out[tid] = s_c2w[tid];
+    __syncthreads();
+    if (tid < VO_PIPE_NCOUNTS) reinterpret_cast<int*>(out + 12)[tid] = cnt[tid];
+}
+
 // ---- detector outputs -> float corners (Harris keypoints are integers) ------------------------------------
 __global__ void pipe_fill_int_kernel(int* p, int v, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -888,6 +994,10 @@ struct vo_pipeline {
     cudaEvent_t ev_level0 = nullptr, ev_det = nullptr, ev_fork = nullptr, ev_rg = nullptr, ev_upd = nullptr;
     int stage_next = 0, prefetched = 0, in_flight = 0, sub_next = 0;
     size_t pose_smem = 0;
+    // two-view bootstrap (vo_pipeline_bootstrap_*): point pairs in, model / landmarks / masks out
+    double *boot_p1 = nullptr, *boot_p2 = nullptr, *boot_F = nullptr, *boot_M = nullptr, *boot_land = nullptr;
+    uint8_t *boot_mask = nullptr, *boot_fmask = nullptr;
+    int *boot_n = nullptr, *boot_info = nullptr;
 };
 
 static int pipe_run_detector(vo_pipeline* pl, const uint8_t* pyr_level0, int set, cudaStream_t s) {
@@ -959,6 +1069,8 @@ int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* prm, vo_pipeline**
         const size_t o_dx0 = carve(S * DC * 8), o_dx1 = carve(S * DC * 8), o_dn0 = carve(S * 4), o_dn1 = carve(S * 4);
         const size_t o_su0 = carve(S * VO_PIPE_SUMMARY_DOUBLES * 8), o_su1 = carve(S * VO_PIPE_SUMMARY_DOUBLES * 8);
         const size_t o_sg0 = carve(S * npx + 256), o_sg1 = carve(S * npx + 256);
+        const size_t o_b1 = carve(S * C * 16), o_b2 = carve(S * C * 16), o_bF = carve(S * 72), o_bM = carve(S * 96), o_bl = carve(S * C * 24);
+        const size_t o_bm = carve(S * C), o_bf = carve(S * C), o_bn = carve(S * 4), o_bi = carve(S * 16);
         cudaError_t e = cudaMalloc(&pl->base, off);
         if (e != cudaSuccess) { vo_set_error("vo_pipeline_create: cudaMalloc(%zu) -> %s", off, cudaGetErrorString(e)); return VO_ERR_CUDA; }
         unsigned char* b = pl->base;
@@ -979,6 +1091,8 @@ int vo_pipeline_create(vo_ctx* ctx, const vo_pipeline_params* prm, vo_pipeline**
         pl->det_xy[0] = (int*)(b + o_dx0); pl->det_xy[1] = (int*)(b + o_dx1); pl->det_n[0] = (int*)(b + o_dn0); pl->det_n[1] = (int*)(b + o_dn1);
         pl->summary[0] = (double*)(b + o_su0); pl->summary[1] = (double*)(b + o_su1);
         pl->stage[0] = b + o_sg0; pl->stage[1] = b + o_sg1;
+        pl->boot_p1 = (double*)(b + o_b1); pl->boot_p2 = (double*)(b + o_b2); pl->boot_F = (double*)(b + o_bF); pl->boot_M = (double*)(b + o_bM);
+        pl->boot_land = (double*)(b + o_bl); pl->boot_mask = b + o_bm; pl->boot_fmask = b + o_bf; pl->boot_n = (int*)(b + o_bn); pl->boot_info = (int*)(b + o_bi);
         // default per-sequence state: identity poses, the reference's initial iteration count (ransac.py:56)
         {
             std::vector<double> eye(S * 12, 0.0), eyew(S * 12, 0.0);
@@ -1083,7 +1197,7 @@ int vo_pipeline_prime_host(vo_pipeline* pl, const uint8_t* h_frames, int init_ta
 // internal streams; ev_upd fires when the step's results (tables, summary) are complete.  `staging_free` (optional) is
 // recorded as soon as d_frames has been consumed (after the pyramid's level-0 copy).
 static int pipe_step(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, size_t frame_stride, int slot, cudaStream_t s,
-                     cudaEvent_t staging_free = nullptr, cudaEvent_t slot_free = nullptr) {
+                     cudaEvent_t staging_free = nullptr, cudaEvent_t slot_free = nullptr, const double* boot = nullptr) {
     const vo_pipeline_params& p = pl->p;
     vo_ctx* ctx = pl->ctx;
     VO_REQUIRE(pl->primed, "vo_pipeline step: call vo_pipeline_prime_* first (there is no previous frame yet)");
@@ -1127,12 +1241,25 @@ static int pipe_step(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, siz
     } else if (slot_free) {
         VO_CUDA(cudaStreamWaitEvent(s, slot_free, 0));
     }
-    pipe_pose_kernel<<<p.n_seq, PO_THREADS, pl->pose_smem, sp>>>(pl->tab[nx], pl->seq, pl->dp, pl->inliers);
-    ctx->launches++;
-    VO_CHECK_LAUNCH();
-    pipe_update_kernel<<<p.n_seq, UP_THREADS, 0, sp>>>(pl->tab[nx], pl->seq, pl->dp, pl->inliers, pl->summary[slot]);
-    ctx->launches++;
-    VO_CHECK_LAUNCH();
+    if (boot) {
+        // main.py:203-231: the matched rows of the two frames -> relative pose, landmarks, inliers -> table
+        pipe_boot_gather_kernel<<<p.n_seq, 256, 0, sp>>>(pl->tab[nx], pl->seq, pl->dp, pl->boot_p1, pl->boot_p2, pl->boot_n);
+        ctx->launches++;
+        VO_CHECK_LAUNCH();
+        if ((rc = vo_launch_bootstrap(ctx, pl->boot_p1, pl->boot_p2, p.n_seq, p.capacity, pl->boot_n, p.K, boot[0], boot[1], (int)boot[2],
+                                      pl->boot_F, pl->boot_M, pl->boot_land, pl->boot_mask, pl->boot_fmask, pl->boot_info, sp))) return rc;
+        pipe_boot_apply_kernel<<<p.n_seq, UP_THREADS, 0, sp>>>(pl->tab[nx], pl->seq, pl->dp, pl->boot_M, pl->boot_land, pl->boot_mask,
+                                                               pl->boot_info, pl->summary[slot]);
+        ctx->launches++;
+        VO_CHECK_LAUNCH();
+    } else {
+        pipe_pose_kernel<<<p.n_seq, PO_THREADS, pl->pose_smem, sp>>>(pl->tab[nx], pl->seq, pl->dp, pl->inliers);
+        ctx->launches++;
+        VO_CHECK_LAUNCH();
+        pipe_update_kernel<<<p.n_seq, UP_THREADS, 0, sp>>>(pl->tab[nx], pl->seq, pl->dp, pl->inliers, pl->summary[slot]);
+        ctx->launches++;
+        VO_CHECK_LAUNCH();
+    }
     VO_CUDA(cudaEventRecord(pl->ev_upd, sp));
     if (!fork && p.detector != VO_DETECTOR_NONE) { if ((rc = pipe_run_detector(pl, pl->pyr[nx], nx, s))) return rc; }
     pl->cur = nx;
@@ -1159,6 +1286,33 @@ int vo_pipeline_step_dev(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch,
     VO_REQUIRE(pl && d_frames, "vo_pipeline_step_dev: null argument");
     VO_CUDA(cudaSetDevice(pl->ctx->device));
     return pipe_step(pl, d_frames, pitch, frame_stride, 0, stream ? (cudaStream_t)stream : pl->ctx->stream);
+}
+
+int vo_pipeline_bootstrap_dev(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, size_t frame_stride, double threshold,
+                              double confidence, int max_iters, void* stream) {
+    VO_REQUIRE(pl && d_frames, "vo_pipeline_bootstrap_dev: null argument");
+    VO_REQUIRE(max_iters >= 1, "vo_pipeline_bootstrap_dev: max_iters must be positive");
+    VO_CUDA(cudaSetDevice(pl->ctx->device));
+    const double boot[3] = {threshold, confidence, (double)max_iters};
+    return pipe_step(pl, d_frames, pitch, frame_stride, 0, stream ? (cudaStream_t)stream : pl->ctx->stream, nullptr, nullptr, boot);
+}
+
+int vo_pipeline_bootstrap_host(vo_pipeline* pl, const uint8_t* h_frames, double threshold, double confidence, int max_iters,
+                               double* h_summary) {
+    VO_REQUIRE(pl && h_frames && h_summary, "vo_pipeline_bootstrap_host: null argument");
+    VO_REQUIRE(pl->in_flight == 0 && pl->prefetched == 0, "vo_pipeline_bootstrap_host: submitted steps are still in flight");
+    VO_REQUIRE(max_iters >= 1, "vo_pipeline_bootstrap_host: max_iters must be positive");
+    VO_CUDA(cudaSetDevice(pl->ctx->device));
+    cudaStream_t s = pl->ctx->stream;
+    const size_t npx = (size_t)pl->p.H * pl->p.W;
+    VO_CUDA(cudaMemcpyAsync(pl->stage[0], h_frames, pl->p.n_seq * npx, cudaMemcpyHostToDevice, s));
+    const double boot[3] = {threshold, confidence, (double)max_iters};
+    int rc = pipe_step(pl, pl->stage[0], (size_t)pl->p.W, npx, 0, s, nullptr, nullptr, boot);
+    if (rc) return rc;
+    if ((rc = pipe_join(pl, s))) return rc;
+    VO_CUDA(cudaMemcpyAsync(h_summary, pl->summary[0], (size_t)pl->p.n_seq * VO_PIPE_SUMMARY_DOUBLES * 8, cudaMemcpyDeviceToHost, s));
+    VO_CUDA(cudaStreamSynchronize(s));
+    return VO_OK;
 }
 
 const double* vo_pipeline_summary_dev(vo_pipeline* pl) { return pl ? pl->summary[0] : nullptr; }

@@ -86,6 +86,8 @@ def lib():
             "vo_pipeline_prime_dev": (i32, [vp, vp, sz, sz, i32, vp]),
             "vo_pipeline_prime_host": (i32, [vp, vp, i32]),
             "vo_pipeline_step_dev": (i32, [vp, vp, sz, sz, vp]),
+            "vo_pipeline_bootstrap_dev": (i32, [vp, vp, sz, sz, dbl, dbl, i32, vp]),
+            "vo_pipeline_bootstrap_host": (i32, [vp, vp, dbl, dbl, i32, vp]),
             "vo_pipeline_summary_dev": (vp, [vp]),
             "vo_pipeline_sync_dev": (i32, [vp, vp]),
             "vo_pipeline_prefetch_host": (i32, [vp, vp]),

@@ -110,6 +110,16 @@ class Pipeline:
         nat.check(nat.lib().vo_pipeline_step_host(self._h, nat.ptr(a), nat.ptr(out)), "vo_pipeline_step_host")
         return self.summary_dict(out)
 
+    def bootstrap(self, frames, threshold=0.25, confidence=0.999, max_iters=1000):
+        """main.py:203-231 on the device: track the primed frame's corners into `frames`, estimate the relative pose
+        (cv2.findFundamentalMat's RANSAC restated, essential-matrix decomposition, cheirality vote), triangulate the
+        inliers and apply the state updates; returns the summary (pose = the second camera)."""
+        a = self._frames(frames)
+        out = np.empty((self.n_seq, SUMMARY_DOUBLES), dtype=np.float64)
+        nat.check(nat.lib().vo_pipeline_bootstrap_host(self._h, nat.ptr(a), float(threshold), float(confidence), int(max_iters),
+                                                       nat.ptr(out)), "vo_pipeline_bootstrap_host")
+        return self.summary_dict(out)
+
     @staticmethod
     def summary_dict(raw):
         raw = np.ascontiguousarray(raw)
