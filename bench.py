@@ -353,6 +353,76 @@ def class_api_cpu_reference(world, n_frames=4):
     return 1.0 / float(np.mean(times))
 
 
+def bootstrap_problems(S, N, seed=77):
+    """S synthetic two-view problems (a 3-D point cloud, not the bench's plane: a plane leaves F undetermined), 0.3 px
+    noise, 30 % gross outliers: float64 (S, N, 2) pixel pairs and the true relative poses."""
+    rng = np.random.default_rng(seed)
+    P1, P2, Ms = np.empty((S, N, 2)), np.empty((S, N, 2)), np.empty((S, 3, 4))
+    for s in range(S):
+        X = np.c_[rng.uniform(-10, 10, N), rng.uniform(-3, 3, N), rng.uniform(6, 40, N)]
+        w = rng.uniform(-0.05, 0.05, 3)
+        th = np.linalg.norm(w); k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        t = np.array([0.1, -0.05, -1.0]) + rng.normal(0, 0.05, 3)
+        a = (K_INTR @ X.T).T
+        b = (K_INTR @ (X @ R.T + t).T).T
+        P1[s] = a[:, :2] / a[:, 2:] + rng.normal(0, 0.3, (N, 2))
+        P2[s] = b[:, :2] / b[:, 2:] + rng.normal(0, 0.3, (N, 2))
+        no = int(0.3 * N)
+        P2[s, :no] += rng.uniform(-40, 40, (no, 2))
+        Ms[s] = np.c_[R, t / np.linalg.norm(t)]
+    return P1, P2, Ms
+
+
+def bootstrap_leg(ctx, dev, stream, tstream, S, N=1000, with_cpu=False):
+    """vo_bootstrap_dev on S problems of N matches (threshold 1.0 px, confidence 0.999), device-resident inputs; beside it
+    the reference's own call (cv2.findFundamentalMat + the decomposition / triangulations on the host, one core)."""
+    import torch
+    from vo import _native as nat
+    L = nat.lib()
+    P1, P2, Ms = bootstrap_problems(S, N)
+    d1, d2 = torch.from_numpy(P1).to(dev), torch.from_numpy(P2).to(dev)
+    dF = torch.empty((S, 9), dtype=torch.float64, device=dev); dM = torch.empty((S, 12), dtype=torch.float64, device=dev)
+    dL = torch.empty((S, N, 3), dtype=torch.float64, device=dev)
+    dm = torch.empty((S, N), dtype=torch.uint8, device=dev); di = torch.empty((S, 4), dtype=torch.int32, device=dev)
+    K9 = np.ascontiguousarray(K_INTR.reshape(9))
+
+    def call():
+        nat.check(L.vo_bootstrap_dev(ctx.handle, d1.data_ptr(), d2.data_ptr(), S, N, None, nat.ptr(K9), 1.0, 0.999, 1000,
+                                     dF.data_ptr(), dM.data_ptr(), dL.data_ptr(), dm.data_ptr(), None, di.data_ptr(), stream), "vo_bootstrap_dev")
+    call()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(tstream)
+    for _ in range(3):
+        call()
+    e1.record(tstream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    M = dM.cpu().numpy().reshape(S, 3, 4)
+    info = di.cpu().numpy()
+    rot_err = float(np.median([np.abs(M[s][:, :3] - Ms[s][:, :3]).max() for s in range(S)]))
+    dir_err = float(np.median([np.abs(M[s][:, 3] - Ms[s][:, 3]).max() for s in range(S)]))
+    out = {"ms_per_call": ms, "problems_per_call": S, "matches_per_problem": N, "problems_per_s": S / (ms / 1e3),
+           "ransac_iterations_mean": float(info[:, 1].mean()), "models_found": int(info[:, 0].sum()),
+           "median_rotation_error": rot_err, "median_translation_direction_error": dir_err,
+           "note": "vo_bootstrap_dev: cv2.findFundamentalMat's RANSAC restated + essential-matrix decomposition + cheirality "
+                   "vote + landmarks, one CTA per problem, inputs resident in HBM"}
+    if with_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import cv2
+        n_cpu = min(S, 8)
+        t0 = time.perf_counter()
+        for s in range(n_cpu):
+            cv2.findFundamentalMat(points1=P1[s].reshape(-1, 2, 1), points2=P2[s].reshape(-1, 2, 1), method=cv2.FM_RANSAC,
+                                   ransacReprojThreshold=1.0, confidence=0.999)
+        dt = time.perf_counter() - t0
+        out["cpu_cv2_findFundamentalMat_problems_per_s"] = n_cpu / dt
+        out["cpu_sample"] = f"{n_cpu} of the same problems through cv2.findFundamentalMat alone (the reference's call, triangulation.py:126-134) on one host core"
+    return out
+
+
 def bind_near_gpu(local_rank):
     """Pin this process -- and with it the pinned staging buffers it allocates next -- to the NUMA node of its GPU, so
     that uploads do not cross the inter-socket link.  CPU affinity first (NVML's ideal set when it is a proper subset of
@@ -679,6 +749,14 @@ def main():
         except Exception as ex:
             class_api = {"frames_per_s": None, "note": f"failed: {type(ex).__name__}: {ex}"}
 
+    # ---- two-view bootstrap (main.py:203-231, once per sequence): S problems in one launch ----------
+    boot = None
+    if rank == 0 and not args.no_extras:
+        try:
+            boot = bootstrap_leg(ctx, dev, stream, tstream, S, with_cpu=(world == 1 and not args.no_cpu_baseline))
+        except Exception as ex:
+            boot = {"ms_per_call": None, "note": f"failed: {type(ex).__name__}: {ex}"}
+
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -707,6 +785,7 @@ def main():
                            "(pinned host buffers), poses + counters come back, every step; two steps in flight"},
             "gpu_launches": int(launches) * world,
             "roofline": roofline, "roofline_tracker": roofline_klt, "cpu_baseline": cpu, "clocks": clocks, "single_sequence": single, "class_api": class_api,
+            "bootstrap": boot,
         }))
     pl.close()
     if world > 1:
