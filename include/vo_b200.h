@@ -186,6 +186,12 @@ int vo_triangulate_dev(vo_ctx* ctx, const double* d_p1, const double* d_p2, int 
 int vo_triangulate_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int n, const double* h_proj1,
                         int proj1_per_point, const double* h_proj2, int mode, double* h_out);
 
+/* Host helper of the drop-in P3PPoseEstimator's default path (p3p.py:142-151, cv2.solvePnPRansac): `count` subsets of
+ * `model_points` distinct indices below n_points as RANSACPointSetRegistrator::getSubset draws them from cv::RNG
+ * (state in / out; OpenCV seeds every run with 2^64 - 1).  Control flow only -- the models and inlier counts of the
+ * subsets come from vo_p3p_ransac_*.  out int32 [count][model_points].                                           */
+int vo_cv_rng_subsets_host(uint64_t* state, int n_points, int model_points, int count, int32_t* out);
+
 /* ---- Two-view bootstrap: src/vo/landmarks/triangulation.py:88-350 (as src/main.py:185-222 configures it) ---- */
 /* LandmarksTriangulator(use_ransac=True, use_opencv=True).triangulate_matches for n_seq independent frame pairs, one
  * CTA each: cv2.findFundamentalMat(FM_RANSAC, threshold, confidence) restated (float32 points, cv::RNG subsets of 7

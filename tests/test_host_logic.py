@@ -207,3 +207,14 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_cv_rng_subsets_native_equals_python():
+    """vo_cv_rng_subsets_host (the native getSubset loop the default pose path uses) against the literal Python loop:
+    same subsets, same generator state afterwards."""
+    from vo.algorithms.cv_ransac import CvRNG, subset4, subsets
+    for n, count in [(37, 500), (5, 100), (1000, 256), (4, 10)]:
+        a, b = CvRNG(), CvRNG()
+        want = np.array([subset4(a, n) for _ in range(count)], dtype=np.int32)
+        got = subsets(b, n, count)
+        assert np.array_equal(got, want) and a.state == b.state, (n, count)

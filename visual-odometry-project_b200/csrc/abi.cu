@@ -623,4 +623,27 @@ int vo_bootstrap_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int n
     return VO_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// cv::RNG subsets for the host-driven OpenCV-style RANSAC (control flow only: no device work)
+// ------------------------------------------------------------------------------------------
+int vo_cv_rng_subsets_host(uint64_t* state, int n_points, int model_points, int count, int32_t* out) {
+    VO_REQUIRE(state && out && count >= 0, "vo_cv_rng_subsets_host: null argument");
+    VO_REQUIRE(model_points >= 1 && model_points <= 16 && n_points >= model_points, "vo_cv_rng_subsets_host: need 1 <= model_points <= 16 <= n_points");
+    uint64_t st = *state;
+    for (int c = 0; c < count; c++) {
+        int32_t* id = out + (size_t)c * model_points;
+        for (int i = 0; i < model_points; i++) {
+            for (;;) {
+                st = (uint64_t)(uint32_t)st * 4164903690ull + (st >> 32);       // cv::RNG::next
+                const int32_t v = (int32_t)((uint32_t)st % (uint32_t)n_points);  // uniform(0, n)
+                bool dup = false;
+                for (int j = 0; j < i; j++) dup |= (id[j] == v);
+                if (!dup) { id[i] = v; break; }
+            }
+        }
+    }
+    *state = st;
+    return VO_OK;
+}
+
 }  // extern "C"

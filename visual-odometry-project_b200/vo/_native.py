@@ -64,6 +64,7 @@ def lib():
                                          vp, vp, vp, vp, vp, vp, vp, vp]),
             "vo_triangulate_dev": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp, vp]),
             "vo_triangulate_host": (i32, [vp, vp, vp, i32, vp, i32, vp, i32, vp]),
+            "vo_cv_rng_subsets_host": (i32, [vp, i32, i32, i32, vp]),
             "vo_bootstrap_dev": (i32, [vp, vp, vp, i32, i32, vp, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, vp]),
             "vo_bootstrap_host": (i32, [vp, vp, vp, i32, i32, vp, vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp]),
         }

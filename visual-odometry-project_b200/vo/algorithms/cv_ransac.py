@@ -6,7 +6,7 @@ models and inlier counts of whole batches of subsets come from the GPU (vo_p3p_r
 rule).  With it the default path returns cv2.solvePnPRansac's own inlier mask instead of an approximation of it."""
 import numpy as np
 
-__all__ = ["CvRNG", "update_num_iters", "subset4"]
+__all__ = ["CvRNG", "update_num_iters", "subset4", "subsets"]
 
 
 class CvRNG:
@@ -46,3 +46,14 @@ def subset4(rng: CvRNG, n: int):
                 break
         idx.append(v)
     return idx
+
+
+def subsets(rng: CvRNG, n: int, count: int, model_points: int = 4) -> np.ndarray:
+    """`count` consecutive getSubset results as int32 (count, model_points); advances `rng` (native loop:
+    vo_cv_rng_subsets_host -- the Python one above costs more than the GPU batch it feeds)."""
+    from vo import _native as nat
+    st = np.array([rng.state], dtype=np.uint64)
+    out = np.empty((count, model_points), dtype=np.int32)
+    nat.check(nat.lib().vo_cv_rng_subsets_host(nat.ptr(st), int(n), int(model_points), int(count), nat.ptr(out)), "vo_cv_rng_subsets_host")
+    rng.state = int(st[0])
+    return out

@@ -55,7 +55,7 @@ class P3PPoseEstimator:
     def _gpu_ransac_opencv(self, points_3d, points_2d):
         """cv2.solvePnPRansac(flags=SOLVEPNP_P3P, iterationsCount=max_iterations, reprojectionError=inlier_threshold,
         confidence=confidence) (p3p.py:142-151): OpenCV's loop on the host, models and counts of its subsets on the GPU."""
-        from vo.algorithms.cv_ransac import CvRNG, subset4, update_num_iters
+        from vo.algorithms.cv_ransac import CvRNG, subsets, update_num_iters
         L32 = np.asarray(points_3d, dtype=np.float64).reshape(-1, 3).astype(np.float32).astype(np.float64)   # solvePnPRansac: CV_32F
         P32 = np.asarray(points_2d).reshape(-1, 2).astype(np.float32).astype(np.float64)
         N = L32.shape[0]
@@ -69,7 +69,7 @@ class P3PPoseEstimator:
         batch = self.FIRST_BATCH
         while it < niters:
             want = int(min(batch, niters - it))
-            samples = np.array([subset4(rng, N) for _ in range(want)], dtype=np.int32)
+            samples = subsets(rng, N, want)
             r = _ops.p3p_ransac(L32, P32, self.intrinsic_matrix, samples, thr2, table, np.iinfo(np.int32).max, want_all=True,
                                 inclusive=True)
             for j in range(want):
