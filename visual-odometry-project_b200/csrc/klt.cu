@@ -648,10 +648,10 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
     constexpr int W2 = WIN * WIN, PN = WIN + 3, DN = WIN + 1;
     constexpr int T = (W2 + 31) / 32;                      // window pixels per lane
     constexpr int PATCH_BYTES = (PN * PN + 15) & ~15;
-    constexpr int IV_BYTES = (T * 32 * 2 + 15) & ~15;      // padded to whole warps: the unrolled loops read every slot
+    constexpr int GI_BYTES = T * 32 * 8;                   // padded to whole warps: the unrolled loops read every slot
     constexpr int AN = WIN + 2;                            // side of the interpolated patch of the fast setup
     constexpr int DP_BYTES = ((AN * AN > DN * DN ? AN * AN : DN * DN) * 4 + 15) & ~15;
-    constexpr int PER_WARP = (PATCH_BYTES + DP_BYTES + IV_BYTES + T * 32 * 4 + 15) & ~15;
+    constexpr int PER_WARP = (PATCH_BYTES + DP_BYTES + GI_BYTES + 15) & ~15;
     __shared__ __align__(16) unsigned char smem[KLT_SWARPS * PER_WARP];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pt = blockIdx.x * KLT_SWARPS + warp;
@@ -660,8 +660,7 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
     uint8_t* patch = smem + warp * PER_WARP;                                  // I (PN^2), later J (DN^2)
     short* dpatch = reinterpret_cast<short*>(patch + PATCH_BYTES);             // [DN*DN][2]
     int* At = reinterpret_cast<int*>(patch + PATCH_BYTES);                     // [AN*AN] (fast setup, same storage)
-    short* Iw = reinterpret_cast<short*>(patch + PATCH_BYTES + DP_BYTES);      // [W2]
-    int* Gw = reinterpret_cast<int*>(patch + PATCH_BYTES + DP_BYTES + IV_BYTES);   // [W2]  (Ix | Iy << 16)
+    int2* GI = reinterpret_cast<int2*>(patch + PATCH_BYTES + DP_BYTES);        // [W2]  x = Ix | Iy << 16, y = I: one 64-bit load per slot
 
     const uint8_t* Ip = pyr_prev + (size_t)f * lay.frame_bytes;
     const uint8_t* Jp = pyr_next + (size_t)f * lay.frame_bytes;
@@ -681,7 +680,7 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
     unsigned int jw[T];
 #pragma unroll
     for (int t = 0; t < T; t++) jw[t] = 0u;
-    for (int i = W2 + lane; i < T * 32; i += 32) { Iw[i] = 0; Gw[i] = 0; }   // padding slots stay zero
+    for (int i = W2 + lane; i < T * 32; i += 32) GI[i] = make_int2(0, 0);    // padding slots stay zero
     bool st = true;
     float e_out = 0.f;
     float outx = 0.f, outy = 0.f;
@@ -749,8 +748,7 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
                 const int iv = valid ? descale(a11, W_BITS - 5) : 0;
                 const int ix = valid ? descale(((a02 - a00) + (a22 - a20)) * 3 + (a12 - a10) * 10, W_BITS) : 0;
                 const int iy = valid ? descale(((a20 - a00) + (a22 - a02)) * 3 + (a21 - a01) * 10, W_BITS) : 0;
-                Iw[t * 32 + lane] = (short)iv;
-                Gw[t * 32 + lane] = (ix & 0xFFFF) | (iy << 16);
+                GI[t * 32 + lane] = make_int2((ix & 0xFFFF) | (iy << 16), iv);
                 sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
             }
         } else {
@@ -781,15 +779,14 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
 #pragma unroll 1
             for (int t = 0; t < T; t++) {
                 const int y = slot_y(t), x = slot_x(t), i = t * 32 + lane;
-                if (y >= WIN) { Iw[i] = 0; Gw[i] = 0; continue; }
+                if (y >= WIN) { GI[i] = make_int2(0, 0); continue; }
                 const uint8_t* s0 = patch + (y + 1) * PN + (x + 1);
                 const int iv = descale((int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[PN] * iw10 + (int)s0[PN + 1] * iw11, W_BITS - 5);
                 const short* d0 = dpatch + 2 * (y * DN + x);
                 const short* d1 = d0 + 2 * DN;
                 const int ix = descale((int)d0[0] * iw00 + (int)d0[2] * iw01 + (int)d1[0] * iw10 + (int)d1[2] * iw11, W_BITS);
                 const int iy = descale((int)d0[1] * iw00 + (int)d0[3] * iw01 + (int)d1[1] * iw10 + (int)d1[3] * iw11, W_BITS);
-                Iw[i] = (short)iv;
-                Gw[i] = (ix & 0xFFFF) | (iy << 16);
+                GI[i] = make_int2((ix & 0xFFFF) | (iy << 16), iv);
                 sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
             }
         }
@@ -857,8 +854,9 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
 #pragma unroll
                 for (int t = 0; t < T; t++) {                // slots past the window hold zeros: they add nothing
                     const int acc = dp2a_hi_su(w_hi, jw[t], dp2a_lo_su(w_lo, jw[t], 1 << (W_BITS - 6)));
-                    const int diff = (acc >> (W_BITS - 5)) - (int)Iw[t * 32 + lane];
-                    const int g = Gw[t * 32 + lane];
+                    const int2 gi = GI[t * 32 + lane];
+                    const int diff = (acc >> (W_BITS - 5)) - gi.y;
+                    const int g = gi.x;
                     sb1 += diff * (int)(short)(g & 0xFFFF);
                     sb2 += diff * (g >> 16);
                 }
@@ -866,7 +864,7 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
 #pragma unroll
                 for (int t = 0; t < T; t++) {
                     const int acc = dp2a_hi_su(w_hi, jw[t], dp2a_lo_su(w_lo, jw[t], 1 << (W_BITS - 6)));
-                    const int diff = (acc >> (W_BITS - 5)) - (int)Iw[t * 32 + lane];
+                    const int diff = (acc >> (W_BITS - 5)) - GI[t * 32 + lane].y;
                     se += diff < 0 ? -diff : diff;
                 }
             }
