@@ -120,6 +120,66 @@ def cv_fm_7point(m1, m2):
     return out
 
 
+def fm_7point_elimination(m1, m2):
+    """The same solver with the null space taken the way the CUDA kernel takes it (Gauss-Jordan elimination with complete
+    pivoting, basis orthonormalised) instead of an SVD: the solutions are the singular members of the pencil the null space
+    spans, whatever its basis.  tests/test_oracle_golden.py checks that OpenCV's RANSAC ends identically with either."""
+    m1 = np.asarray(m1, np.float32).reshape(7, 2).astype(np.float64)
+    m2 = np.asarray(m2, np.float32).reshape(7, 2).astype(np.float64)
+    c1, c2 = m1.mean(0), m2.mean(0)
+    s1 = np.sqrt(((m1 - c1) ** 2).sum(1)).mean()
+    s2 = np.sqrt(((m2 - c2) ** 2).sum(1)).mean()
+    if s1 < FLT_EPSILON or s2 < FLT_EPSILON:
+        return []
+    s1, s2 = np.sqrt(2.0) / s1, np.sqrt(2.0) / s2
+    a, b = (m1 - c1) * s1, (m2 - c2) * s2
+    x0, y0, x1, y1 = a[:, 0], a[:, 1], b[:, 0], b[:, 1]
+    A = np.stack([x1 * x0, x1 * y0, x1, y1 * x0, y1 * y0, y1, x0, y0, np.ones(7)], 1)
+    perm = list(range(9))
+    for k in range(7):
+        sub = np.abs(A[k:, k:])
+        if not sub.max() > 0:
+            return []
+        i, j = np.unravel_index(np.argmax(sub), sub.shape)
+        i, j = i + k, j + k
+        A[[k, i]] = A[[i, k]]
+        A[:, [k, j]] = A[:, [j, k]]
+        perm[k], perm[j] = perm[j], perm[k]
+        A[k, k:] *= 1.0 / A[k, k]
+        for r in range(7):
+            if r != k and A[r, k] != 0:
+                A[r, k:] -= A[r, k] * A[k, k:]
+    f1, f2 = np.zeros(9), np.zeros(9)
+    for k in range(7):
+        f1[perm[k]], f2[perm[k]] = -A[k, 7], -A[k, 8]
+    f1[perm[7]] = 1.0
+    f2[perm[8]] = 1.0
+    f1 /= np.linalg.norm(f1)
+    f2 -= (f1 @ f2) * f1
+    f2 /= np.linalg.norm(f2)
+    f1 = f1 - f2
+    roots = cv_solve_cubic(_det3_pencil(f1, f2))
+    T1 = np.array([[s1, 0, -s1 * c1[0]], [0, s1, -s1 * c1[1]], [0, 0, 1]])
+    T2 = np.array([[s2, 0, -s2 * c2[0]], [0, s2, -s2 * c2[1]], [0, 0, 1]])
+    out = []
+    for lam in roots:
+        mu = 1.0
+        s = f1[8] * lam + f2[8]
+        F = np.empty(9)
+        if abs(s) > DBL_EPSILON:
+            mu = 1.0 / s
+            lam = lam * mu
+            F[8] = 1.0
+        else:
+            F[8] = 0.0
+        F[:8] = f1[:8] * lam + f2[:8] * mu
+        F = T2.T @ F.reshape(3, 3) @ T1
+        if abs(F[2, 2]) > FLT_EPSILON:
+            F = F * (1.0 / F[2, 2])
+        out.append(F)
+    return out
+
+
 def _collinear_last(pts):
     """haveCollinearPoints (fundam.cpp): the LAST point against every pair of earlier ones."""
     i = len(pts) - 1

@@ -98,3 +98,39 @@ def test_bootstrap_too_few_points_is_reported():
     from vo import _ops
     with pytest.raises(ValueError):
         _ops.bootstrap(np.zeros((10, 2)), np.zeros((10, 2)), np.eye(3), 0.25, 0.999)
+
+
+def test_bootstrap_edge_cases_vs_oracle():
+    """The smallest population OpenCV's RANSAC path accepts (15), duplicated matches (getSubset's collinearity / proximity
+    check redraws), a planar scene (F not unique) and gross outliers only (few inliers): iteration counts and masks equal
+    to the oracle's."""
+    from oracle import bootstrap as ob
+    from vo import _ops
+    K = np.array([[718.856, 0, 607.19], [0, 718.856, 185.2], [0, 0, 1]])
+    rng = np.random.default_rng(11)
+
+    def scene(N, planar=False, noise=0.2, n_out=0):
+        X = np.c_[rng.uniform(-10, 10, N), np.full(N, 1.6) if planar else rng.uniform(-3, 3, N), rng.uniform(6, 40, N)]
+        w = rng.uniform(-0.05, 0.05, 3); th = np.linalg.norm(w); k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+        t = np.array([0.1, -0.05, -1.0]) + rng.normal(0, 0.05, 3)
+        a = (K @ X.T).T; b = (K @ (X @ R.T + t).T).T
+        p1 = a[:, :2] / a[:, 2:] + rng.normal(0, noise, (N, 2)); p2 = b[:, :2] / b[:, 2:] + rng.normal(0, noise, (N, 2))
+        p2[:n_out] += rng.uniform(-40, 40, (n_out, 2))
+        return p1, p2
+    cases = {"fifteen": scene(15), "planar": scene(400, planar=True, n_out=80), "mostly_outliers": scene(200, n_out=170)}
+    p1, p2 = scene(120, n_out=20)
+    cases["duplicates"] = (np.r_[p1, p1[:60]], np.r_[p2, p2[:60]])
+    for name, (p1, p2) in cases.items():
+        r = _ops.bootstrap(p1, p2, K, 0.5, 0.999)
+        F, M, land, mask, it = ob.bootstrap(p1, p2, K, 0.5, 0.999)
+        if F is None:
+            assert not r["found"], name
+            continue
+        assert r["found"] and r["iterations"] == it, (name, r["iterations"], it)
+        f_inl = ob.cv_fm_errors_f32(F, p1.astype(np.float32), p2.astype(np.float32)) <= np.float32(0.25)
+        assert np.array_equal(r["f_mask"], f_inl), name
+        assert np.array_equal(r["mask"], mask), name
+        if name != "planar":                                 # on a plane E is ill-conditioned: the masks agree, the pose need not to 1e-7
+            assert np.abs(r["M"] - M).max() < 1e-6, name

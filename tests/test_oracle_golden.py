@@ -400,3 +400,31 @@ def test_bootstrap_oracle_vs_cv2_live():
         if same:
             assert np.abs(F - Fcv).max() <= 1e-9 * np.abs(Fcv).max()
     assert equal >= 11, equal
+
+
+def test_bootstrap_null_space_by_elimination_is_equivalent():
+    """The CUDA kernel takes the null space of the 7x9 system by Gauss-Jordan elimination, OpenCV by an SVD.  The solutions
+    (singular members of the pencil) do not depend on the basis: OpenCV's RANSAC restated with either solver ends with the
+    same iteration count and the same mask -- on point clouds and on planes (where F is not unique), with and without noise."""
+    from oracle import bootstrap as ob
+    K = np.array([[718.856, 0, 607.19], [0, 718.856, 185.2], [0, 0, 1]])
+
+    def so3(w):
+        th = np.linalg.norm(w); k = w / th
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    for planar in (False, True):
+        for noise in (0.0, 0.3):
+            for seed in range(3):
+                r = np.random.default_rng(50 + seed)
+                N = 300
+                X = np.c_[r.uniform(-10, 10, N), np.full(N, 1.6) if planar else r.uniform(-3, 3, N), r.uniform(6, 40, N)]
+                R, t = so3(r.uniform(-0.05, 0.05, 3)), np.array([0.1, -0.05, -1.0]) + r.normal(0, 0.05, 3)
+                a = (K @ X.T).T; b = (K @ (X @ R.T + t).T).T
+                p1 = a[:, :2] / a[:, 2:] + r.normal(0, noise, (N, 2))
+                p2 = b[:, :2] / b[:, 2:] + r.normal(0, noise, (N, 2))
+                p2[:60] += r.uniform(-40, 40, (60, 2))
+                Fa, ma, ia = ob.cv_find_fundamental_ransac(p1, p2, 0.5, 0.999)
+                Fb, mb, ib = ob.cv_find_fundamental_ransac(p1, p2, 0.5, 0.999, solver=ob.fm_7point_elimination)
+                assert ia == ib and np.array_equal(ma, mb), (planar, noise, seed)
+                assert np.abs(Fa - Fb).max() <= 1e-6 * np.abs(Fa).max()
