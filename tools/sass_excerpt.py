@@ -13,7 +13,7 @@ txt = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "visual-odometry-
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
 want = ["harris_response_fast", "klt_track_packed", "klt_track_fast", "pyr_down_kernel", "harris_localmax", "harris_nms_scan", "harris_nms_bands",
         "p3p_solve_kernel", "p3p_count_kernel", "pipe_pose_kernel", "pipe_update_kernel", "pipe_regroup_kernel", "gftt_eig_kernel", "gftt_select_kernel",
-        "knn2_kernel", "bgr2gray_kernel", "refine_pose_kernel", "triangulate_kernel"]
+        "knn2_kernel", "bgr2gray_kernel", "refine_pose_kernel", "triangulate_kernel", "bootstrap_kernel", "pipe_boot_apply_kernel"]
 keys = ["UTMALDG", "SYNCS", "IDP.4A", "IDP.2A", "REDUX", "SHFL", "DFMA", "DMUL", "DADD", "MUFU", "I2F.F64", "LDS", "STS", "LDG", "STG", "ATOMS", "BAR",
         "VOTE", "POPC", "IMAD", "LOP3", "PRMT"]
 out = [f"# SASS evidence (cuobjdump -sass libvo_b200.so, sm_100a), {tag}", "",
