@@ -1415,17 +1415,23 @@ int vo_launch_harris_response(vo_ctx* ctx, const uint8_t* d_img, int n_frames, i
                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r == CUDA_SUCCESS) {
             if (vo_ctx_once(ctx, VO_ATTR_HARRIS_FAST)) {
-                VO_CUDA(cudaFuncSetAttribute(harris_response_fast<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-                VO_CUDA(cudaFuncSetAttribute(harris_response_fast<1241>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+#define VO_HR_ATTR(WC) VO_CUDA(cudaFuncSetAttribute(harris_response_fast<WC>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+                VO_HR_ATTR(0) VO_HR_ATTR(1226) VO_HR_ATTR(1241) VO_HR_ATTR(1920) VO_HR_ATTR(4096)
+#undef VO_HR_ATTR
             }
             const int tiles_x = vo_div_up(W + FT_XSHIFT, FT_W), tiles_y = vo_div_up(H, FT_H);
             const long long n_tiles = (long long)tiles_x * tiles_y * n_frames;
             VO_REQUIRE(n_tiles < (1ll << 31), "harris: too many tiles");
             const int grid = (int)((n_tiles < 2ll * ctx->sm_count) ? n_tiles : 2ll * ctx->sm_count);
-            if (W == 1241)      // KITTI-shaped frames (BASELINE.json)
-                harris_response_fast<1241><<<grid, FT_THREADS, FT_SMEM, stream>>>(tmap, H, W, kappa, d_resp, tiles_x, tiles_y, (int)n_tiles);
-            else
-                harris_response_fast<0><<<grid, FT_THREADS, FT_SMEM, stream>>>(tmap, H, W, kappa, d_resp, tiles_x, tiles_y, (int)n_tiles);
+            // width-specialised instances (store offsets as immediates): KITTI (1241 in BASELINE.json, 1226 for the
+            // reference's sequence 05), full HD, 4K DCI (BASELINE's stress config); any other width takes the generic one
+#define VO_HR_LAUNCH(WC) harris_response_fast<WC><<<grid, FT_THREADS, FT_SMEM, stream>>>(tmap, H, W, kappa, d_resp, tiles_x, tiles_y, (int)n_tiles)
+            if (W == 1241) VO_HR_LAUNCH(1241);
+            else if (W == 1226) VO_HR_LAUNCH(1226);
+            else if (W == 1920) VO_HR_LAUNCH(1920);
+            else if (W == 4096) VO_HR_LAUNCH(4096);
+            else VO_HR_LAUNCH(0);
+#undef VO_HR_LAUNCH
             ctx->launches++;
             VO_CHECK_LAUNCH();
             return VO_OK;

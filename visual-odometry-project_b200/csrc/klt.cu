@@ -590,7 +590,7 @@ klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__
     }
 }
 
-constexpr int KLT_SWARPS = 8;
+constexpr int KLT_SWARPS = 4;   // warps (keypoints) per CTA: a CTA holds its slot until its slowest warp converges, small CTAs lose less
 
 
 // ---------------------------------------------------------------------------------------------
@@ -640,7 +640,7 @@ __device__ __forceinline__ int dp2a_hi_su(unsigned int a, unsigned int b, int c)
 }
 
 template <int WIN>
-__global__ void __launch_bounds__(KLT_SWARPS * 32, 4)
+__global__ void __launch_bounds__(KLT_SWARPS * 32, 8)
 klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__ pyr_next, PyrLayout lay,
                 int max_iters, double eps2, double min_eig, const float* __restrict__ prev_pts, int n_pts,
                 float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err,
