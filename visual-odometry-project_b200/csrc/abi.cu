@@ -628,7 +628,7 @@ int vo_bootstrap_host(vo_ctx* ctx, const double* h_p1, const double* h_p2, int n
 // ------------------------------------------------------------------------------------------
 int vo_cv_rng_subsets_host(uint64_t* state, int n_points, int model_points, int count, int32_t* out) {
     VO_REQUIRE(state && out && count >= 0, "vo_cv_rng_subsets_host: null argument");
-    VO_REQUIRE(model_points >= 1 && model_points <= 16 && n_points >= model_points, "vo_cv_rng_subsets_host: need 1 <= model_points <= 16 <= n_points");
+    VO_REQUIRE(model_points >= 1 && model_points <= 16 && n_points >= model_points, "vo_cv_rng_subsets_host: need 1 <= model_points <= 16 and n_points >= model_points");
     uint64_t st = *state;
     for (int c = 0; c < count; c++) {
         int32_t* id = out + (size_t)c * model_points;
