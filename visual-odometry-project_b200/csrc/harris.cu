@@ -996,11 +996,24 @@ harris_nms_bands(NmsArgs a) {
                     unsigned int z[8];
 #pragma unroll
                     for (int u = 0; u < 8; u++) { const unsigned int j = j0 + u * N_THREADS + tid; z[u] = j < n ? ent_h[j] : 0u; }
+                    // slots first, then the selected entries in two groups of four: their loads are in flight together
+                    // (one load -> store chain per entry made this loop 14 % of the kernel)
+                    unsigned int slot[8];
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         const unsigned int j = j0 + u * N_THREADS + tid;
                         const unsigned int rk = (gmax - z[u]) >> shift;
-                        if (j < n && rk >= r_lo && rk <= r_hi) ent_b[atomicAdd(&cur[rk], 1u)] = ent_a[j];
+                        slot[u] = (j < n && rk >= r_lo && rk <= r_hi) ? atomicAdd(&cur[rk], 1u) : NMS_EMPTY;
+                    }
+#pragma unroll
+                    for (int g = 0; g < 2; g++) {
+                        uint4 e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (slot[4 * g + u] != NMS_EMPTY) e[u] = __ldg(&ent_a[j0 + (4 * g + u) * N_THREADS + tid]);
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (slot[4 * g + u] != NMS_EMPTY) ent_b[slot[4 * g + u]] = e[u];
                     }
                 }
                 r_sorted = lo;
