@@ -795,7 +795,7 @@ harris_nms_scan(NmsArgs a) {
 // ---- so a window test is 2r+1 funnel shifts and a score load only for the rare neighbour found.  The loop
 // ---- stops when the picks decided so far (local maxima + band picks down to the current bin) number K.
 constexpr int NMS_BINS = 2048;
-constexpr int NMS_BAND = 1024;       // entries per band (one per thread)
+constexpr int NMS_BAND = 512;        // entries per band (at most one per thread; 512 measured best: fewer band members per window)
 constexpr int NMS_NEW_CAP = 1024;    // new picks per round (the surplus waits for the next round)
 constexpr int NMS_LAZY = 8192;       // entries put in order per scatter pass
 constexpr int NMS_HASH = 2048;       // open-addressing table for the (at most NMS_BAND) undecided entries of a band
