@@ -34,7 +34,11 @@ def test_golden_zero_fill(ctx, golden):
     ((120, 160), 300, 2, 5),
     ((64, 64), 50, 5, 3),
     ((200, 300), 500, 7, 9),    # r > patch_radius + 1: numpy's negative-slice case can trigger
-    ((376, 1241), 1000, 5, 9),  # KITTI-shaped, BASELINE configs[1]
+    ((376, 1241), 1000, 5, 9),  # KITTI-shaped, BASELINE configs[1] (width-specialised response kernel)
+    ((120, 1226), 300, 5, 9),   # the other width-specialised instances: KITTI sequence 05, full HD, 4K DCI (odd heights:
+    ((75, 1920), 300, 5, 9),    # the last tile row is partial)
+    ((61, 4096), 300, 5, 9),
+    ((75, 1921), 300, 5, 9),    # ... and the generic instance next to one of them
 ])
 def test_vs_oracle(ctx, shape, K, r, ps):
     img = synthetic_image(shape[0], shape[1], seed=shape[0] * 7 + K)
