@@ -476,7 +476,7 @@ __device__ int gn_refine(const double* sX, const double* sY, const double* sZ, c
     return gn_iters;
 }
 
-__global__ void __launch_bounds__(PO_THREADS)
+__global__ void __launch_bounds__(PO_THREADS, 4)   // 128 registers: a quarter less of the SM taken away from the tracker it runs under
 pipe_pose_kernel(PipeTable T, PipeSeq Q, PipeParams P, uint8_t* __restrict__ inliers_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int C = P.C;
