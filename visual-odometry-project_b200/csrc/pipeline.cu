@@ -688,7 +688,8 @@ refine_pose_kernel(const double* __restrict__ landmarks, const double* __restric
 
 // ---- update: state.py + triangulation.py:38-86 ----------------------------------------------------
 constexpr int UP_THREADS = 256;
-__global__ void __launch_bounds__(UP_THREADS)
+__global__ void __launch_bounds__(UP_THREADS, 2)   // 128 registers (it runs under the tracker)
+
 pipe_update_kernel(PipeTable T, PipeSeq Q, PipeParams P, const uint8_t* __restrict__ inliers, double* __restrict__ summary) {
     __shared__ double s_c2w[12], s_w2c[12], s_w2c_prev[12], s_proj2[12];
     __shared__ int s_ncand, s_nbehind, s_ntri;
