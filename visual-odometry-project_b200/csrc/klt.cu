@@ -669,13 +669,14 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
     const float half = (float)(WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
     const int top = lay.n_levels - 1;
-    // Window pixel of (slot t, lane): slots 0..8 hold rows 2t and 2t+1, columns 0..15 (lane = 16 * row parity + column),
-    // slot 9 holds column 16 of row `lane`.  With t a compile-time constant every address is a per-lane base plus an
+    // Window pixel of (slot t, lane): slots 0..8 hold rows t (lanes 0-15) and 9 + t (lanes 16-31), columns 0..15 -- a lane
+    // walks DOWN nine consecutive rows, so the bottom taps of one slot are the top taps of the next and a reload of the
+    // J taps costs two byte loads per slot instead of four; slot 9 holds column 16 of row `lane`.  With t a compile-time constant every address is a per-lane base plus an
     // immediate, so the unrolled loops carry no index arithmetic.  (The generic setup below keeps running counters.)
     static_assert(WIN == 17, "the slot mapping of klt_track_packed is laid out for a 17 x 17 window");
     const int ly0 = lane / WIN, lx0 = lane - ly0 * WIN;      // generic setup: i = lane + 32 t walks the window row-major
     const int hi = lane >> 4, lx = lane & 15;
-    auto slot_y = [&](int t) { return t < T - 1 ? 2 * t + hi : lane; };
+    auto slot_y = [&](int t) { return t < T - 1 ? t + 9 * hi : lane; };
     auto slot_x = [&](int t) { return t < T - 1 ? lx : 16; };
     unsigned int jw[T];
 #pragma unroll
@@ -737,10 +738,10 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
                 }
             }
             __syncwarp();
-            const int* a_lane = At + hi * AN + lx;
+            const int* a_lane = At + 9 * hi * AN + lx;
 #pragma unroll
             for (int t = 0; t < T; t++) {
-                const int* r0 = t < T - 1 ? a_lane + t * 2 * AN : At + lane * AN + 16;
+                const int* r0 = t < T - 1 ? a_lane + t * AN : At + lane * AN + 16;
                 const bool valid = slot_y(t) < WIN;
                 const int* r1 = r0 + AN;
                 const int* r2 = r1 + AN;
@@ -827,21 +828,29 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
                 if (inside) {
                     const uint8_t* base = J + (size_t)iny * pitch + inx;
                     const int ip = (int)pitch;
-                    int off = hi * ip + lx;
+                    // rows 9 hi .. 9 hi + 9 of this lane's column pair (the lanes of the lower half stop one row early:
+                    // row 18 is outside the staged region and belongs to no window pixel)
+                    const uint8_t* col = base + 9 * hi * ip + lx;
+                    unsigned int pk[T];
 #pragma unroll
-                    for (int t = 0; t < T; t++) {
-                        const uint8_t* s0 = t < T - 1 ? base + off : base + lane * ip + 16;
-                        jw[t] = slot_y(t) < WIN ? ((unsigned)s0[0] | ((unsigned)s0[1] << 8) | ((unsigned)s0[ip] << 16) | ((unsigned)s0[ip + 1] << 24)) : 0u;
-                        off += 2 * ip;
+                    for (int k = 0; k < T; k++) {
+                        pk[k] = (k < T - 1 || hi == 0) ? ((unsigned)col[0] | ((unsigned)col[1] << 8)) : 0u;
+                        col += ip;
+                    }
+#pragma unroll
+                    for (int t = 0; t < T - 1; t++) jw[t] = slot_y(t) < WIN ? (pk[t] | (pk[t + 1] << 16)) : 0u;
+                    {
+                        const uint8_t* s0 = base + lane * ip + 16;
+                        jw[T - 1] = slot_y(T - 1) < WIN ? ((unsigned)s0[0] | ((unsigned)s0[1] << 8) | ((unsigned)s0[ip] << 16) | ((unsigned)s0[ip + 1] << 24)) : 0u;
                     }
                 } else {
                     __syncwarp();
                     stage_patch_fast<DN>(J, rows, cols, pitch, inx, iny, patch, lane);
                     __syncwarp();
-                    const uint8_t* p_lane = patch + hi * DN + lx;
+                    const uint8_t* p_lane = patch + 9 * hi * DN + lx;
 #pragma unroll
                     for (int t = 0; t < T; t++) {
-                        const uint8_t* s0 = t < T - 1 ? p_lane + t * 2 * DN : patch + lane * DN + 16;
+                        const uint8_t* s0 = t < T - 1 ? p_lane + t * DN : patch + lane * DN + 16;
                         jw[t] = slot_y(t) < WIN ? ((unsigned)s0[0] | ((unsigned)s0[1] << 8) | ((unsigned)s0[DN] << 16) | ((unsigned)s0[DN + 1] << 24)) : 0u;
                     }
                 }
