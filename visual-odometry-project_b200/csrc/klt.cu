@@ -738,19 +738,36 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
                 }
             }
             __syncwarp();
-            const int* a_lane = At + 9 * hi * AN + lx;
+            // A lane walks down its column: per row of A the horizontal difference d = right - left (Scharr x) and the
+            // smoothed value sm = 3 left + 10 centre + 3 right (Scharr y) are formed once and slide through three
+            // registers each; a slot then costs one new row (3 loads) instead of a 3x3 neighbourhood (9 loads).
+            // Integer arithmetic regrouped, same integers:  ix = 3 (d0 + d2) + 10 d1,  iy = sm2 - sm0.
+            auto emit = [&](int t, bool valid, int c1, int d0, int d1, int d2, int sm0, int sm2) {
+                const int iv = valid ? descale(c1, W_BITS - 5) : 0;
+                const int ix = valid ? descale((d0 + d2) * 3 + d1 * 10, W_BITS) : 0;
+                const int iy = valid ? descale(sm2 - sm0, W_BITS) : 0;
+                GI[t * 32 + lane] = make_int2((ix & 0xFFFF) | (iy << 16), iv);
+                sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
+            };
+            {
+                const int* a_lane = At + 9 * hi * AN + lx;
+                int d0, d1, d2, sm0, sm1, sm2, c1, c2;
+                { const int l = a_lane[0], c = a_lane[1], r = a_lane[2]; d0 = r - l; sm0 = (l + r) * 3 + c * 10; }
+                { const int l = a_lane[AN], c = a_lane[AN + 1], r = a_lane[AN + 2]; d1 = r - l; sm1 = (l + r) * 3 + c * 10; c1 = c; }
 #pragma unroll
-            for (int t = 0; t < T; t++) {
-                const int* r0 = t < T - 1 ? a_lane + t * AN : At + lane * AN + 16;
-                const bool valid = slot_y(t) < WIN;
+                for (int t = 0; t < T - 1; t++) {
+                    const int* rw = a_lane + (t + 2) * AN;
+                    { const int l = rw[0], c = rw[1], r = rw[2]; d2 = r - l; sm2 = (l + r) * 3 + c * 10; c2 = c; }
+                    emit(t, slot_y(t) < WIN, c1, d0, d1, d2, sm0, sm2);
+                    d0 = d1; d1 = d2; sm0 = sm1; sm1 = sm2; c1 = c2;
+                }
+            }
+            {   // slot T - 1: column 16 of row `lane`
+                const int* r0 = At + lane * AN + 16;
                 const int* r1 = r0 + AN;
                 const int* r2 = r1 + AN;
                 const int a00 = r0[0], a01 = r0[1], a02 = r0[2], a10 = r1[0], a11 = r1[1], a12 = r1[2], a20 = r2[0], a21 = r2[1], a22 = r2[2];
-                const int iv = valid ? descale(a11, W_BITS - 5) : 0;
-                const int ix = valid ? descale(((a02 - a00) + (a22 - a20)) * 3 + (a12 - a10) * 10, W_BITS) : 0;
-                const int iy = valid ? descale(((a20 - a00) + (a22 - a02)) * 3 + (a21 - a01) * 10, W_BITS) : 0;
-                GI[t * 32 + lane] = make_int2((ix & 0xFFFF) | (iy << 16), iv);
-                sA11 += ix * ix; sA12 += ix * iy; sA22 += iy * iy;
+                emit(T - 1, slot_y(T - 1) < WIN, a11, a02 - a00, a12 - a10, a22 - a20, (a00 + a02) * 3 + a01 * 10, (a20 + a22) * 3 + a21 * 10);
             }
         } else {
         {
