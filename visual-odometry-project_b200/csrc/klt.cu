@@ -718,14 +718,19 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
             // the integer identity  sum_k w_k Scharr(I)(p + k) = Scharr(sum_k w_k I(. + k))(p)  holds exactly: first
             // the un-descaled bilinear patch A (AN x AN, 32-bit), then per window pixel one 3x3 neighbourhood of A
             // gives I (centre), Ix and Iy.  Same integers as the reference order, a third of the instructions.
-            {   // AN x AN = 19 x 19 positions: row pairs x 16 columns (10 slots), then columns 16..18 (2 slots)
-                const uint8_t* p_lane = patch + hi * PN + lx;
-                int* o_lane = At + hi * AN + lx;
+            {   // AN x AN = 19 x 19 positions: rows 0-9 (lanes 0-15) / 10-18 (lanes 16-31) x 16 columns, then columns 16..18.
+                // A lane walks down its column: the two pixels of a patch row feed the A row above (weights iw10, iw11)
+                // and the A row below (iw00, iw01) -- two byte loads per position instead of four, same integers.
+                const uint8_t* p_lane = patch + 10 * hi * PN + lx;
+                int* o_lane = At + 10 * hi * AN + lx;
+                int top = (int)p_lane[0] * iw00 + (int)p_lane[1] * iw01;
 #pragma unroll
-                for (int t = 0; t < 10; t++) {
-                    const uint8_t* s0 = p_lane + t * 2 * PN;
-                    const int a = (int)s0[0] * iw00 + (int)s0[1] * iw01 + (int)s0[PN] * iw10 + (int)s0[PN + 1] * iw11;
-                    if (2 * t + hi < AN) o_lane[t * 2 * AN] = a;
+                for (int k = 0; k < 10; k++) {
+                    const uint8_t* s1 = p_lane + (k + 1) * PN;               // lanes 16-31, k = 9: one row past the patch (this warp's
+                    const int q0 = (int)s1[0], q1 = (int)s1[1];               // own A area follows it); that A row is not stored
+                    const int a = top + q0 * iw10 + q1 * iw11;
+                    if (10 * hi + k < AN) o_lane[k * AN] = a;
+                    top = q0 * iw00 + q1 * iw01;
                 }
                 // remaining 3 x 19 = 57 positions, column-major: position q = lane + 32 u -> (row q % 19, column 16 + q / 19)
 #pragma unroll
