@@ -91,6 +91,7 @@ int vo_ctx_create(vo_ctx** out, int device) {
         c->env_klt_generic = (e = getenv("VO_KLT_GENERIC")) && e[0] == '1';
         c->env_frontend_serial = (e = getenv("VO_FRONTEND_SERIAL")) && e[0] == '1';
         c->nms_band = (e = getenv("VO_NMS_BAND")) ? atoi(e) : 0;
+        c->env_nms_no_spec = (e = getenv("VO_NMS_NO_SPEC")) && e[0] == '1';
     }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         vo_set_error("vo_ctx_create: cudaStreamCreate failed");

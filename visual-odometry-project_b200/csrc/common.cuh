@@ -43,7 +43,7 @@ struct vo_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;  // context-owned stream used by the *_host entry points
-    VoBuf scratch[16];
+    VoBuf scratch[17];               // [16]: per-frame state the NMS carries from one call to the next (harris.cu)
     VoBuf pinned[4];
     unsigned long long launches = 0;  // kernels launched through this context
     // One-time opt-ins (cudaFuncSetAttribute is per device): a bit per kernel family, set by vo_ctx_once().
@@ -53,6 +53,8 @@ struct vo_ctx {
     bool env_klt_generic = false;     // VO_KLT_GENERIC=1: runtime-window tracker for every window size
     bool env_frontend_serial = false; // VO_FRONTEND_SERIAL=1: no fork/join across streams
     int nms_band = 0;                 // VO_NMS_BAND (0 = built-in default)
+    bool env_nms_no_spec = false;     // VO_NMS_NO_SPEC=1: never start the NMS from a speculative threshold
+    unsigned long long nms_state_key = 0;   // shape the carried NMS state belongs to
     // vo_klt_track_*_host keeps the pyramid of the last `next` image: a tracker that is called with consecutive frame
     // pairs (klt.py:233-239) uploads and pyramids every frame once, not twice.
     struct { unsigned long long hash = 0; size_t bytes = 0; int H = 0, W = 0, channels = 0, n_frames = 0, max_level = 0, win = 0;

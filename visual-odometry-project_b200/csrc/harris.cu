@@ -622,6 +622,14 @@ struct NmsArgs {
     int bitmaps_in_smem;
     unsigned int smem_bytes;           // dynamic shared memory of the band kernel
     unsigned int band;                 // entries per band (<= N_THREADS)
+    // Speculative threshold.  The first K picks usually end far above the K-th best local maximum (most of them are not
+    // local maxima of their window), so a call may start from the spec_rank[f]-th best local maximum instead -- the rank
+    // the K-th pick of the PREVIOUS call had among the local maxima of frame f, with a margin.  Everything found above a
+    // threshold is exact whatever the threshold is (a pixel's fate depends on higher priorities only); if fewer than K
+    // picks lie above the speculative one, flag[f] asks for a second pass (pass = 1) from the safe threshold.
+    unsigned int* spec_rank;           // [F] carried between calls (0 = unknown), or null: no speculation
+    unsigned int* flag;                // [F] 0 done / 1 second pass needed / 2 speculative pass running
+    int pass;
 };
 
 // ---- bitmaps: bit p = pixel p (row-major, no row padding) ----
@@ -656,6 +664,16 @@ harris_nms_select(NmsArgs a) {
     unsigned int* pi = a.pick_idx + (size_t)f * a.lm_cap;
     const unsigned int n_lm = min(a.lm_count[f], a.lm_cap);
     const int tid = threadIdx.x;
+    if (a.pass == 1) {                                        // second pass: only the frames whose speculation fell short
+        if (a.flag[f] != 1u) return;
+        for (unsigned int w = tid; w < a.bm_words; w += N_THREADS) sup[w] = 0u;
+    }
+    unsigned int rank = (unsigned int)K;                      // threshold = rank-th best local maximum
+    if (a.pass == 0 && a.spec_rank != nullptr) {
+        const unsigned int sr = a.spec_rank[f];
+        if (sr >= 1u && sr < (unsigned int)K && n_lm >= sr) rank = sr;
+    }
+    const bool speculative = rank < (unsigned int)K;
     unsigned long long tk = 1ull;                             // "every positive score"
     unsigned int ti = 0xFFFFFFFFu;
     // the list of local maxima is staged in shared memory when it fits: the 12 radix passes then run at
@@ -669,9 +687,9 @@ harris_nms_select(NmsArgs a) {
         for (unsigned int j = tid; j < n_lm; j += N_THREADS) { sk[j] = lmk[j]; si[j] = lmi[j]; }
         kk = sk; ii = si;
     }
-    if (tid == 0) s_np = 0;
+    if (tid == 0) { s_np = 0; if (a.flag != nullptr) a.flag[f] = speculative ? 2u : 0u; }
     __syncthreads();
-    if (n_lm >= (unsigned)K && K > 0) block_select_kth(kk, ii, n_lm, (unsigned)K, hist, s_misc, &tk, &ti);
+    if (n_lm >= rank && K > 0) block_select_kth(kk, ii, n_lm, rank, hist, s_misc, &tk, &ti);
     for (unsigned int j = tid; j < n_lm; j += N_THREADS) {
         const unsigned long long k = kk[j];
         const unsigned int i = ii[j];
@@ -706,6 +724,9 @@ harris_nms_select(NmsArgs a) {
 // ---- every box.  Only these can still become picks.
 constexpr int SCAN_PER_THREAD = 8;
 
+// LOOP = false: one CTA per chunk of 2048 pixels (grid.x = number of chunks); LOOP = true: the second pass of a speculative
+// call -- few CTAs per frame that leave at once unless the frame asked for it, and walk the chunks otherwise
+template <bool LOOP>
 __global__ void __launch_bounds__(256, 8)
 harris_nms_scan(NmsArgs a) {
     __shared__ unsigned int s_base;
@@ -713,6 +734,7 @@ harris_nms_scan(NmsArgs a) {
     // per warp: the pixels that pass the cheap test, then the kept ones {pixel, score lo, score hi}
     __shared__ unsigned int s_qp[8][32 * SCAN_PER_THREAD], s_ql[8][32 * SCAN_PER_THREAD], s_qh[8][32 * SCAN_PER_THREAD];
     const int f = blockIdx.y;
+    if (LOOP && a.flag[f] != 1u) return;                   // second pass: only the frames whose speculation fell short
     const unsigned int npx = (unsigned int)a.H * a.W;
     const double* resp = a.resp + (size_t)f * npx;
     const unsigned int* sup = a.sup + (size_t)f * a.bm_words;
@@ -722,8 +744,10 @@ harris_nms_scan(NmsArgs a) {
     const unsigned int ti = a.thr_idx[f];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int lt = (1u << lane) - 1u;
-    const unsigned int base = blockIdx.x * (256u * SCAN_PER_THREAD) + threadIdx.x;
-    const unsigned int cta_row = (blockIdx.x * (256u * SCAN_PER_THREAD)) / (unsigned)a.W;   // uniform: row of the CTA's first pixel
+    const unsigned int n_chunks = (npx + 256u * SCAN_PER_THREAD - 1u) / (256u * SCAN_PER_THREAD);
+  for (unsigned int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const unsigned int base = chunk * (256u * SCAN_PER_THREAD) + threadIdx.x;
+    const unsigned int cta_row = (chunk * (256u * SCAN_PER_THREAD)) / (unsigned)a.W;   // uniform: row of the CTA's first pixel
     unsigned long long k[SCAN_PER_THREAD];
 #pragma unroll
     for (int j = 0; j < SCAN_PER_THREAD; j++) {            // all loads first (coalesced, 8 in flight per thread)
@@ -785,6 +809,9 @@ harris_nms_scan(NmsArgs a) {
         enth[o + i] = e.z;
         ent[o + i] = make_uint4(e.x, e.y, e.z, (py << 16) | px);
     }
+    if (!LOOP) break;
+    __syncthreads();                                       // the queues and s_base are reused by the next chunk
+  }
 }
 
 // ---- NMS step 4 (one CTA per frame): the entries are ordered into priority bins (high word of the score, 2048
@@ -906,6 +933,7 @@ harris_nms_bands(NmsArgs a) {
     if (threadIdx.x < 8) s_dbg[threadIdx.x] = 0;
 #endif
     const int f = blockIdx.x;
+    if (a.pass == 1 && a.flag[f] != 1u) return;            // second pass: only the frames whose speculation fell short
     const int H = a.H, W = a.W, r = a.r, K = a.K;
     const unsigned int npx = (unsigned int)H * W;
     const double* resp = a.resp + (size_t)f * npx;
@@ -1340,6 +1368,31 @@ harris_nms_bands(NmsArgs a) {
         }
         out[2 * j] = x; out[2 * j + 1] = y;
     }
+    if (a.flag != nullptr) {
+        // a speculative start is good when K picks were found above its threshold; the state for the next call is the rank
+        // the K-th pick has among this frame's local maxima, with a margin (K = "start from the safe threshold")
+        const bool fell_short = a.pass == 0 && a.flag[f] == 2u && n_picks < (unsigned)K;
+        if (tid == 0) s_misc[1] = 0u;
+        __syncthreads();
+        if (!fell_short && a.spec_rank != nullptr && n_out >= (unsigned)K && K > 0) {
+            const unsigned long long kk = sk[K - 1];
+            const unsigned int ki = si[K - 1];
+            const unsigned long long* lmk = a.lm_key + (size_t)f * a.lm_cap;
+            const unsigned int* lmi = a.lm_idx + (size_t)f * a.lm_cap;
+            unsigned int c = 0;
+            for (unsigned int j = tid; j < n_lm; j += N_THREADS) c += prio_ge(lmk[j], lmi[j], kk, ki) ? 1u : 0u;
+            c = __reduce_add_sync(0xFFFFFFFFu, c);
+            if (lane == 0 && c) atomicAdd(&s_misc[1], c);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            a.flag[f] = fell_short ? 1u : 0u;
+            if (!fell_short && a.spec_rank != nullptr) {
+                const unsigned int rk = s_misc[1];
+                a.spec_rank[f] = (n_out >= (unsigned)K && rk > 0u) ? min((unsigned)K, rk + rk / 8u + 8u) : (unsigned)K;
+            }
+        }
+    }
 #ifdef VO_NMS_TIMING
     __syncthreads();
     if (tid == 0) {   // probe build only: cycles of {sort, bands, final}, bands processed
@@ -1469,7 +1522,7 @@ size_t vo_harris_lm_cap(int H, int W, int r) {
 struct NmsCarve {
     size_t npx, lm_cap, bm_words, smem_bands, total;
     bool bm_smem;
-    size_t o_lmk, o_lmi, o_cnt, o_sup, o_mem, o_ea, o_eb, o_eh, o_pk, o_pi, o_stats, o_tk, o_ti, o_ctr;
+    size_t o_lmk, o_lmi, o_cnt, o_sup, o_mem, o_ea, o_eb, o_eh, o_pk, o_pi, o_stats, o_tk, o_ti, o_ctr, o_flag;
 };
 static void nms_carve(int n_frames, int H, int W, int radius, int num_keypoints, NmsCarve* c) {
     const size_t npx = (size_t)H * W, F = n_frames;
@@ -1491,7 +1544,7 @@ static void nms_carve(int n_frames, int H, int W, int radius, int num_keypoints,
     c->o_ea = carve(F * npx * 16); c->o_eb = carve(F * npx * 16); c->o_eh = carve(F * npx * 4);
     c->o_pk = carve(F * lm_cap * 8); c->o_pi = carve(F * lm_cap * 4);
     c->o_stats = carve(F * 16);
-    c->o_tk = carve(F * 8); c->o_ti = carve(F * 4); c->o_ctr = carve(F * 16);
+    c->o_tk = carve(F * 8); c->o_ti = carve(F * 4); c->o_ctr = carve(F * 16); c->o_flag = carve(F * 4);
     c->total = off;
 }
 
@@ -1500,6 +1553,8 @@ static void nms_carve(int n_frames, int H, int W, int radius, int num_keypoints,
 int vo_harris_nms_reserve(vo_ctx* ctx, int n_frames, int H, int W, int radius, int num_keypoints) {
     NmsCarve cv;
     nms_carve(n_frames, H, W, radius, num_keypoints, &cv);
+    const int rc = vo_buf_reserve(&ctx->scratch[16], (size_t)n_frames * 4);   // carried speculation state
+    if (rc) return rc;
     return vo_buf_reserve(&ctx->scratch[0], cv.total);
 }
 
@@ -1558,17 +1613,35 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     // measured: up to ~2000 keypoints per frame half-size bands win (fewer band members per window, shorter rounds:
     // 1.932 -> 1.917 ms per step at K = 1000), at 10 000 keypoints (4096x2160) full bands do (1494 vs 1336 frames/s)
     a.band = (unsigned)((ctx->nms_band >= 32 && ctx->nms_band <= N_THREADS) ? ctx->nms_band : (num_keypoints <= 2048 ? NMS_BAND / 2 : NMS_BAND));
-    harris_nms_select<<<n_frames, N_THREADS, NMS_SELECT_SMEM * 12, stream>>>(a);
-    ctx->launches++;
-    VO_CHECK_LAUNCH();
-    dim3 g3(vo_div_up((int)npx, 256 * SCAN_PER_THREAD), n_frames);
-    harris_nms_scan<<<g3, 256, 0, stream>>>(a);
-    ctx->launches++;
-    VO_CHECK_LAUNCH();
-    if (radius == 5) harris_nms_bands<5><<<n_frames, N_THREADS, smem_bands, stream>>>(a);
-    else harris_nms_bands<0><<<n_frames, N_THREADS, smem_bands, stream>>>(a);
-    ctx->launches++;
-    VO_CHECK_LAUNCH();
+    // carried state of the speculative threshold: one rank per frame slot, reset when the shape of the calls changes
+    a.flag = (unsigned int*)(base + cv.o_flag);
+    a.spec_rank = nullptr;
+    if (!ctx->env_nms_no_spec && num_keypoints >= 64) {
+        const unsigned long long key = ((unsigned long long)n_frames << 48) ^ ((unsigned long long)H << 34) ^ ((unsigned long long)W << 20) ^
+                                       ((unsigned long long)num_keypoints << 5) ^ (unsigned long long)radius;
+        const void* before = ctx->scratch[16].p;
+        if ((rc = vo_buf_reserve(&ctx->scratch[16], F * 4, stream))) return rc;
+        if (ctx->scratch[16].p != before || ctx->nms_state_key != key) {
+            VO_CUDA(cudaMemsetAsync(ctx->scratch[16].p, 0, F * 4, stream));
+            ctx->nms_state_key = key;
+        }
+        a.spec_rank = (unsigned int*)ctx->scratch[16].p;
+    }
+    const dim3 g3(vo_div_up((int)npx, 256 * SCAN_PER_THREAD), n_frames);
+    for (int pass = 0; pass < ((a.spec_rank) ? 2 : 1); pass++) {   // pass 1: the frames whose speculation fell short (usually none)
+        a.pass = pass;
+        harris_nms_select<<<n_frames, N_THREADS, NMS_SELECT_SMEM * 12, stream>>>(a);
+        ctx->launches++;
+        VO_CHECK_LAUNCH();
+        if (pass == 0) harris_nms_scan<false><<<g3, 256, 0, stream>>>(a);
+        else harris_nms_scan<true><<<dim3(16, n_frames), 256, 0, stream>>>(a);
+        ctx->launches++;
+        VO_CHECK_LAUNCH();
+        if (radius == 5) harris_nms_bands<5><<<n_frames, N_THREADS, smem_bands, stream>>>(a);
+        else harris_nms_bands<0><<<n_frames, N_THREADS, smem_bands, stream>>>(a);
+        ctx->launches++;
+        VO_CHECK_LAUNCH();
+    }
     return VO_OK;
 }
 
