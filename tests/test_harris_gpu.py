@@ -193,3 +193,23 @@ def test_full_kitti_frame_vs_reference(ctx, golden):
     from vo.primitives import Frame
     fr = HarrisCornerDetector(num_keypoints=200).extractKeypoints(Frame(img.copy()))
     assert np.array_equal(fr.features.keypoints.reshape(-1, 2).astype(np.int32), g["harris_full_kp200"])
+
+
+def test_speculative_threshold_is_invisible(ctx):
+    """The NMS starts from the rank the K-th pick had in the previous call of the same frame slot (harris.cu,
+    "speculative threshold").  Whatever the history -- the same frame again (speculation holds), a frame with far fewer
+    strong corners (it falls short: second pass), a blank frame, then the first one again -- the keypoints are the oracle's."""
+    a = synthetic_image(200, 320, seed=5)
+    b = (synthetic_image(200, 320, seed=6) // 8 + 100).astype(np.uint8)       # low contrast: other score scale
+    b[60:140, 100:220] = synthetic_image(80, 120, seed=7)                      # ... with one busy region
+    blank = np.full((200, 320), 77, np.uint8)
+    want = {id(im): oracle.harris_nms(oracle.harris_response(im, 9, 0.09), 300, 5) for im in (a, b, blank)}
+    for im in (a, a, a, b, b, a, blank, a, b):
+        kp, _, _ = _detect(ctx, im, 300)
+        assert np.array_equal(kp, want[id(im)])
+    # batches: every slot carries its own state
+    batch1, batch2 = np.stack([a, b, blank]), np.stack([b, blank, a])
+    for batch in (batch1, batch1, batch2, batch2, batch1):
+        kp, _, _ = _detect(ctx, batch, 300)
+        for f in range(3):
+            assert np.array_equal(kp[f], want[id((a, b, blank)[[0, 1, 2][f]] if batch is batch1 else (b, blank, a)[f])])

@@ -687,7 +687,7 @@ harris_nms_select(NmsArgs a) {
         for (unsigned int j = tid; j < n_lm; j += N_THREADS) { sk[j] = lmk[j]; si[j] = lmi[j]; }
         kk = sk; ii = si;
     }
-    if (tid == 0) { s_np = 0; if (a.flag != nullptr) a.flag[f] = speculative ? 2u : 0u; }
+    if (tid == 0) { s_np = 0; if (a.flag != nullptr && a.pass == 0) a.flag[f] = speculative ? 2u : 0u; }   // pass 1 keeps its 1 for scan / bands
     __syncthreads();
     if (n_lm >= rank && K > 0) block_select_kth(kk, ii, n_lm, rank, hist, s_misc, &tk, &ti);
     for (unsigned int j = tid; j < n_lm; j += N_THREADS) {
