@@ -423,7 +423,7 @@ template <int R, int B>
 __global__ void __launch_bounds__(L_THREADS)
 harris_localmax(const double* __restrict__ resp, int H, int W, int r_rt, unsigned int lm_cap,
                 unsigned long long* __restrict__ lm_key, unsigned int* __restrict__ lm_idx,
-                unsigned int* __restrict__ lm_count) {
+                unsigned int* __restrict__ lm_count, unsigned int* __restrict__ cmap, int cbw, int cbh) {
     constexpr unsigned int FULL = 0xFFFFFFFFu;
     constexpr int NBLK = 32 / B, LANES = NBLK * B, OUT_W = (NBLK - 2) * B;   // the outer blocks are halo
     __shared__ unsigned int s_queue[L_THREADS / 32][L_CHUNK * B * OUT_W + 32];
@@ -441,6 +441,9 @@ harris_localmax(const double* __restrict__ resp, int H, int W, int r_rt, unsigne
     const int n_brows = (y1 - y0 + B - 1) / B + 2;     // block row k covers rows y0 - B + k*B ...
     unsigned int* queue = s_queue[warp];
     int n_q = 0;
+    // the lane that owns a block of the coarse map (block row k of this CTA -> cm_lane[k * cbw])
+    unsigned int* cm_lane = (cmap != nullptr && lane == leader && decides)
+                                ? cmap + ((size_t)f * cbh + (y0 / B - 1)) * cbw + (strip * (NBLK - 2) - 1 + lane / B) : nullptr;
     unsigned int nb1 = 0u, nb2 = 0u;                   // 3-block row maxima of the two previous block rows
     unsigned int gprev[B];
 #pragma unroll
@@ -478,6 +481,9 @@ harris_localmax(const double* __restrict__ resp, int H, int W, int r_rt, unsigne
             unsigned int t = cm;                       // block maximum, valid on the block's first lane
 #pragma unroll
             for (int d = 1; d < B; d++) t = max(t, __shfl_down_sync(FULL, cm, d));
+            // by-product: the block maxima (monotone 32-bit image of the score) as a coarse map of the frame; the
+            // entry scan reads it instead of the score map and touches only the blocks at or above its threshold
+            if (cm_lane != nullptr && k0 + c >= 1 && k0 + c <= n_brows - 2) cm_lane[(k0 + c) * cbw] = t;
             const unsigned int nb = max(t, max(__shfl_up_sync(FULL, t, B), __shfl_down_sync(FULL, t, B)));
             const unsigned int m9 = __shfl_sync(FULL, max(nb, max(nb1, nb2)), leader);   // 3x3 blocks around block row k-1
             // m9 >= every gprev[i], so equality means "not beaten by the nine blocks".  Cheap test first; the
@@ -627,6 +633,8 @@ struct NmsArgs {
     // the K-th pick of the PREVIOUS call had among the local maxima of frame f, with a margin.  Everything found above a
     // threshold is exact whatever the threshold is (a pixel's fate depends on higher priorities only); if fewer than K
     // picks lie above the speculative one, flag[f] asks for a second pass (pass = 1) from the safe threshold.
+    const unsigned int* cmap;          // [F][cbh][cbw] maxima of the 3x3 blocks (ceil(score bits / 2^32)), or null
+    int cbw, cbh;
     unsigned int* spec_rank;           // [F] carried between calls (0 = unknown), or null: no speculation
     unsigned int* flag;                // [F] 0 done / 1 second pass needed / 2 speculative pass running
     int pass;
@@ -812,6 +820,117 @@ harris_nms_scan(NmsArgs a) {
     if (!LOOP) break;
     __syncthreads();                                       // the queues and s_base are reused by the next chunk
   }
+}
+
+// ---- NMS step 3, coarse-map variant (3x3 blocks, radius >= 5): the same entry list from the block maxima the
+// ---- local-maximum pass left behind.  A block whose maximum is below the threshold, or whose nine pixels all lie in
+// ---- boxes, holds no entry and its part of the score map is never read.  With the speculative threshold about one
+// ---- block in twenty survives, so the pass reads the coarse map (0.44 B/pixel) and a few percent of the score map
+// ---- instead of all of it.  (From the safe threshold a third of the blocks survive, scattered: the dense scan is the
+// ---- faster one then, and the second pass uses it.)  A warp owns SB_ROWS x 32 blocks: the block maxima and the box
+// ---- bits of all of them are requested first, then the pixels of the surviving blocks are visited 128 at a time.
+constexpr int SB_ROWS = 4;            // block rows per warp
+
+__global__ void __launch_bounds__(256)
+harris_nms_scan_blocks(NmsArgs a) {
+    __shared__ unsigned char s_blk[8][SB_ROWS * 32];
+    const int f = blockIdx.z;
+    const int H = a.H, W = a.W, cbw = a.cbw, cbh = a.cbh;
+    const unsigned int npx = (unsigned int)H * W;
+    const double* resp = a.resp + (size_t)f * npx;
+    const unsigned int* sup = a.sup + (size_t)f * a.bm_words;
+    const unsigned int* cm = a.cmap + (size_t)f * cbw * cbh;
+    uint4* ent = a.ent_a + (size_t)f * npx;
+    unsigned int* enth = a.ent_h + (size_t)f * npx;
+    const unsigned long long tk = a.thr_key[f];
+    const unsigned int ti = a.thr_idx[f];
+    const unsigned int gthr = (unsigned int)((tk + 0xFFFFFFFFull) >> 32);   // block maxima are ceil(key / 2^32)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int lt = (1u << lane) - 1u;
+    const int gbx = blockIdx.x * 32 + lane;
+    const int by0 = (blockIdx.y * 8 + warp) * SB_ROWS;
+    if (by0 >= cbh) return;                                    // warp-uniform
+    unsigned char* blk = s_blk[warp];
+    const int x = 3 * gbx, len = min(3, W - x);
+    unsigned int c[SB_ROWS];
+#pragma unroll
+    for (int rb = 0; rb < SB_ROWS; rb++)
+        c[rb] = (gbx < cbw && by0 + rb < cbh) ? __ldg(cm + (size_t)(by0 + rb) * cbw + gbx) : 0u;
+    bool active[SB_ROWS];
+    unsigned int bits[SB_ROWS][3];
+#pragma unroll
+    for (int rb = 0; rb < SB_ROWS; rb++) {
+        active[rb] = c[rb] >= gthr && c[rb] != 0u;
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++) {
+            const int y = 3 * (by0 + rb) + dy;
+            bits[rb][dy] = (active[rb] && y < H) ? bm_get_range(sup, (unsigned int)(y * W + x), len) : 0xFFFFFFFFu;
+        }
+    }
+    int nb = 0;
+#pragma unroll
+    for (int rb = 0; rb < SB_ROWS; rb++) {
+        const unsigned int full = (1u << len) - 1u;            // all nine pixels inside boxes: nothing to emit
+        const bool boxed = (bits[rb][0] & full) == full && (bits[rb][1] & full) == full && (bits[rb][2] & full) == full;
+        const bool act = active[rb] && !boxed;
+        const unsigned int m = __ballot_sync(0xFFFFFFFFu, act);
+        if (act) blk[nb + __popc(m & lt)] = (unsigned char)((rb << 5) | lane);
+        nb += __popc(m);
+    }
+    if (nb == 0) return;
+    __syncwarp();
+    const int n_items = nb * 9;
+    unsigned int hmin = 0xFFFFFFFFu, hmax = 0u;
+    bool any = false;
+    for (int i0 = 0; i0 < n_items; i0 += 128) {
+        unsigned int p[4];
+        unsigned long long k[4];
+        unsigned int sw[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int i = i0 + 32 * u + lane;
+            p[u] = 0xFFFFFFFFu; k[u] = 0ull; sw[u] = 0xFFFFFFFFu;
+            if (i < n_items) {
+                const int j = i / 9, q = i - 9 * j, dy = q / 3, dx = q - 3 * dy;
+                const int e = blk[j];
+                const int yy = 3 * (by0 + (e >> 5)) + dy, xx = 3 * (blockIdx.x * 32 + (e & 31)) + dx;
+                if (yy < H && xx < W) {
+                    p[u] = (unsigned int)(yy * W + xx);
+                    k[u] = (unsigned long long)__double_as_longlong(__ldg(resp + p[u]));
+                    sw[u] = __ldg(sup + (p[u] >> 5));
+                }
+            }
+        }
+        bool keep[4];
+        unsigned int mk[4], tot = 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            keep[u] = p[u] != 0xFFFFFFFFu && k[u] != 0ull && prio_ge(k[u], p[u], tk, ti) && !((sw[u] >> (p[u] & 31u)) & 1u);
+            mk[u] = __ballot_sync(0xFFFFFFFFu, keep[u]);
+            tot += __popc(mk[u]);
+        }
+        if (tot == 0) continue;                                // warp-uniform
+        any = true;
+        unsigned int o = 0;
+        if (lane == 0) o = atomicAdd(&a.counters[f * 4 + 0], tot);   // few warps per frame get here: no same-address pile-up
+        o = __shfl_sync(0xFFFFFFFFu, o, 0);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (keep[u]) {
+                const unsigned int t = o + __popc(mk[u] & lt);
+                const unsigned int hi = (unsigned int)(k[u] >> 32);
+                const unsigned int py = p[u] / (unsigned)W, px = p[u] - py * (unsigned)W;
+                enth[t] = hi;
+                ent[t] = make_uint4(p[u], (unsigned int)k[u], hi, (py << 16) | px);
+                hmin = min(hmin, hi); hmax = max(hmax, hi);
+            }
+            o += __popc(mk[u]);
+        }
+    }
+    if (!any) return;
+    hmin = __reduce_min_sync(0xFFFFFFFFu, hmin);
+    hmax = __reduce_max_sync(0xFFFFFFFFu, hmax);
+    if (lane == 0) { atomicMin(&a.counters[f * 4 + 2], hmin); atomicMax(&a.counters[f * 4 + 3], hmax); }
 }
 
 // ---- NMS step 4 (one CTA per frame): the entries are ordered into priority bins (high word of the score, 2048
@@ -1522,7 +1641,8 @@ size_t vo_harris_lm_cap(int H, int W, int r) {
 struct NmsCarve {
     size_t npx, lm_cap, bm_words, smem_bands, total;
     bool bm_smem;
-    size_t o_lmk, o_lmi, o_cnt, o_sup, o_mem, o_ea, o_eb, o_eh, o_pk, o_pi, o_stats, o_tk, o_ti, o_ctr, o_flag;
+    size_t o_lmk, o_lmi, o_cnt, o_sup, o_mem, o_ea, o_eb, o_eh, o_pk, o_pi, o_stats, o_tk, o_ti, o_ctr, o_flag, o_cm;
+    int cbw, cbh;
 };
 static void nms_carve(int n_frames, int H, int W, int radius, int num_keypoints, NmsCarve* c) {
     const size_t npx = (size_t)H * W, F = n_frames;
@@ -1545,6 +1665,8 @@ static void nms_carve(int n_frames, int H, int W, int radius, int num_keypoints,
     c->o_pk = carve(F * lm_cap * 8); c->o_pi = carve(F * lm_cap * 4);
     c->o_stats = carve(F * 16);
     c->o_tk = carve(F * 8); c->o_ti = carve(F * 4); c->o_ctr = carve(F * 16); c->o_flag = carve(F * 4);
+    c->cbw = vo_div_up(W, 3); c->cbh = vo_div_up(H, 3);
+    c->o_cm = carve(radius >= 5 ? F * (size_t)c->cbw * c->cbh * 4 : 0);     // coarse map of the 3x3 block maxima
     c->total = off;
 }
 
@@ -1588,11 +1710,13 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
         unsigned int* lmc = (unsigned int*)(base + o_cnt);
         const int bs = radius >= 5 ? 3 : (radius >= 3 ? 2 : 1);      // block size: the 3x3 blocks must fit the window
         const int out_w = (32 / bs - 2) * bs;
+        // the coarse map is worth its 12 us only when the scan can use it: with a speculative threshold
+        unsigned int* cm = (bs == 3 && !ctx->env_nms_no_spec && num_keypoints >= 64) ? (unsigned int*)(base + cv.o_cm) : nullptr;
         dim3 g1(vo_div_up(vo_div_up(W, out_w), L_THREADS / 32), vo_div_up(H, L_ROWS), n_frames);
-        if (radius == 5) harris_localmax<5, 3><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc);
-        else if (bs == 3) harris_localmax<0, 3><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc);
-        else if (bs == 2) harris_localmax<0, 2><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc);
-        else harris_localmax<0, 1><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc);
+        if (radius == 5) harris_localmax<5, 3><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc, cm, cv.cbw, cv.cbh);
+        else if (bs == 3) harris_localmax<0, 3><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc, cm, cv.cbw, cv.cbh);
+        else if (bs == 2) harris_localmax<0, 2><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc, nullptr, 0, 0);
+        else harris_localmax<0, 1><<<g1, L_THREADS, 0, stream>>>(d_resp, H, W, radius, (unsigned)lm_cap, lmk, lmi, lmc, nullptr, 0, 0);
     }
     ctx->launches++;
     VO_CHECK_LAUNCH();
@@ -1616,6 +1740,7 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
     // carried state of the speculative threshold: one rank per frame slot, reset when the shape of the calls changes
     a.flag = (unsigned int*)(base + cv.o_flag);
     a.spec_rank = nullptr;
+    a.cmap = nullptr; a.cbw = cv.cbw; a.cbh = cv.cbh;
     if (!ctx->env_nms_no_spec && num_keypoints >= 64) {
         const unsigned long long key = ((unsigned long long)n_frames << 48) ^ ((unsigned long long)H << 34) ^ ((unsigned long long)W << 20) ^
                                        ((unsigned long long)num_keypoints << 5) ^ (unsigned long long)radius;
@@ -1626,6 +1751,7 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
             ctx->nms_state_key = key;
         }
         a.spec_rank = (unsigned int*)ctx->scratch[16].p;
+        if (radius >= 5) a.cmap = (const unsigned int*)(base + cv.o_cm);
     }
     const dim3 g3(vo_div_up((int)npx, 256 * SCAN_PER_THREAD), n_frames);
     for (int pass = 0; pass < ((a.spec_rank) ? 2 : 1); pass++) {   // pass 1: the frames whose speculation fell short (usually none)
@@ -1633,7 +1759,8 @@ int vo_launch_harris_nms(vo_ctx* ctx, const double* d_resp, int n_frames, int H,
         harris_nms_select<<<n_frames, N_THREADS, NMS_SELECT_SMEM * 12, stream>>>(a);
         ctx->launches++;
         VO_CHECK_LAUNCH();
-        if (pass == 0) harris_nms_scan<false><<<g3, 256, 0, stream>>>(a);
+        if (pass == 0 && a.cmap != nullptr) harris_nms_scan_blocks<<<dim3(vo_div_up(cv.cbw, 32), vo_div_up(cv.cbh, 8 * SB_ROWS), n_frames), 256, 0, stream>>>(a);
+        else if (pass == 0) harris_nms_scan<false><<<g3, 256, 0, stream>>>(a);
         else harris_nms_scan<true><<<dim3(16, n_frames), 256, 0, stream>>>(a);
         ctx->launches++;
         VO_CHECK_LAUNCH();
