@@ -88,7 +88,7 @@ def test_near_integer_positions(ctx):
     assert np.array_equal(st, st_o) and np.array_equal(nxt, nxt_o) and np.array_equal(err, err_o)
 
 
-@pytest.mark.parametrize("shape", [(97, 131), (376, 1241), (61, 63), (64, 256), (130, 243), (33, 1000)])
+@pytest.mark.parametrize("shape", [(97, 131), (376, 1241), (61, 63), (64, 256), (130, 243), (33, 1000), (12, 40), (23, 17)])
 def test_pyramid_levels_vs_oracle(ctx, shape):
     """vo_klt_build_pyramid_dev level by level against the oracle's cv2.pyrDown restatement (bit-exact), sizes whose
     last input word straddles the border in every way (W % 4 = 0..3), two frames per call"""
