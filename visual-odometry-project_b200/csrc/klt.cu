@@ -590,7 +590,10 @@ klt_track_fast(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__
     }
 }
 
-constexpr int KLT_SWARPS = 4;   // warps (keypoints) per CTA: a CTA holds its slot until its slowest warp converges, small CTAs lose less
+// warps (keypoints) per CTA.  A CTA holds its slot until its slowest warp converges, so small CTAs lose less: 8 -> 4 gave
+// 1.5 % of the step, 4 -> 1 another 0.4 % (1.6718 -> 1.6653 ms; 2 is slower than both: 1.6765 ms).  32 one-warp CTAs fill
+// an SM's 64-register budget exactly.
+constexpr int KLT_SWARPS = 1;
 
 
 // ---------------------------------------------------------------------------------------------
@@ -640,7 +643,7 @@ __device__ __forceinline__ int dp2a_hi_su(unsigned int a, unsigned int b, int c)
 }
 
 template <int WIN>
-__global__ void __launch_bounds__(KLT_SWARPS * 32, 8)
+__global__ void __launch_bounds__(KLT_SWARPS * 32, 32 / KLT_SWARPS)
 klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict__ pyr_next, PyrLayout lay,
                 int max_iters, double eps2, double min_eig, const float* __restrict__ prev_pts, int n_pts,
                 float* __restrict__ next_pts, uint8_t* __restrict__ status, float* __restrict__ err,
