@@ -1092,8 +1092,8 @@ harris_nms_bands(NmsArgs a) {
     long long t_0 = clock64(), t_1 = t_0, t_2 = t_0, t_x = 0, acc_i = 0, acc_a = 0, acc_b = 0;
     unsigned int n_bands = 0;
 #endif
+    int shift = 0;                             // bin rank of a score: (gmax - high word) >> shift, in [0, NMS_BINS)
     if (n > 0) {
-        int shift = 0;
         while (((gmax - gmin) >> shift) >= (unsigned)NMS_BINS) shift++;
         // ---- counting sort of the entries by bin rank ----
         for (unsigned int j0 = 0; j0 < n; j0 += 8 * N_THREADS) {          // loads batched: this loop is latency bound
@@ -1368,6 +1368,74 @@ harris_nms_bands(NmsArgs a) {
     __syncthreads();
     for (unsigned int j = tid; j < P2; j += N_THREADS) { sk[j] = 0ull; si[j] = 0xFFFFFFFFu; }
     __syncthreads();
+    // Every pick is kept and the scores have bin ranks (the usual case): the order is "bin rank, then priority inside the
+    // bin", so a counting sort by bin plus a rank among the handful of picks that share a bin replaces the 66 stages of
+    // the bitonic network (25 of the kernel's ~175 us per frame).  A bin shared by many picks (plateaus of equal scores)
+    // falls back to the network.
+    unsigned long long* tk = reinterpret_cast<unsigned long long*>(smem_raw + (size_t)P2 * 12);
+    unsigned int* ti = reinterpret_cast<unsigned int*>(tk + P2);
+    unsigned int* hb = ti + P2;                               // [BINS] picks per bin -> first slot of the bin
+    unsigned int* hc = hb + NMS_BINS;                         // [BINS] scatter cursors
+    bool bin_sort = (sort_all || n_picks <= (unsigned)K) && n_picks > 0 && P2 >= 2u && n_picks <= P2 &&
+                    (size_t)P2 * 24 + (size_t)NMS_BINS * 8 + 16 <= a.smem_bytes;
+    unsigned int b_max = 0u;                                  // bins: linear in the scores' high words between the picks' extremes
+    int b_shift = 0;
+    auto pick_bin = [&](unsigned long long k) -> unsigned int { return (b_max - (unsigned int)(k >> 32)) >> b_shift; };
+    if (bin_sort) {
+        if (tid == 0) { s_misc[2] = 0u; s_cnt[6] = 0xFFFFFFFFu; s_cnt[7] = 0u; }
+        for (int j = tid; j < NMS_BINS; j += N_THREADS) hb[j] = 0u;
+        __syncthreads();
+        {
+            unsigned int h_lo = 0xFFFFFFFFu, h_hi = 0u;
+            for (unsigned int j = tid; j < n_picks; j += N_THREADS) {
+                const unsigned int h = (unsigned int)(qk[j] >> 32);
+                h_lo = min(h_lo, h); h_hi = max(h_hi, h);
+            }
+            h_lo = __reduce_min_sync(0xFFFFFFFFu, h_lo); h_hi = __reduce_max_sync(0xFFFFFFFFu, h_hi);
+            if (lane == 0) { atomicMin(&s_cnt[6], h_lo); atomicMax(&s_cnt[7], h_hi); }
+        }
+        __syncthreads();
+        b_max = s_cnt[7];
+        while (((b_max - s_cnt[6]) >> b_shift) >= (unsigned)NMS_BINS) b_shift++;
+        for (unsigned int j = tid; j < n_picks; j += N_THREADS) atomicAdd(&hb[pick_bin(qk[j])], 1u);
+        __syncthreads();
+        {   // exclusive scan over the 2048 bins, two per thread
+            const unsigned int c0 = hb[2 * tid], c1 = hb[2 * tid + 1];
+            if (max(c0, c1) > 48u) s_misc[2] = 1u;            // crowded bin: its ranking loop would be the slow part
+            unsigned int sa = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int va = __shfl_up_sync(0xFFFFFFFFu, sa, o);
+                if (lane >= o) sa += va;
+            }
+            if (lane == 31) s_ws[warp] = sa;
+            __syncthreads();
+            unsigned int oa = 0;
+            for (int w = 0; w < warp; w++) oa += s_ws[w];
+            const unsigned int ea = oa + sa - (c0 + c1);
+            hb[2 * tid] = ea; hb[2 * tid + 1] = ea + c0;
+            hc[2 * tid] = ea; hc[2 * tid + 1] = ea + c0;
+        }
+        __syncthreads();
+        bin_sort = s_misc[2] == 0u;
+    }
+    if (bin_sort) {
+        for (unsigned int j = tid; j < n_picks; j += N_THREADS) {
+            const unsigned long long k = qk[j];
+            const unsigned int slot = atomicAdd(&hc[pick_bin(k)], 1u);
+            tk[slot] = k; ti[slot] = qi[j];
+        }
+        __syncthreads();
+        for (unsigned int j = tid; j < n_picks; j += N_THREADS) {
+            const unsigned long long k = tk[j];
+            const unsigned int i = ti[j], b = pick_bin(k);
+            const unsigned int lo = hb[b], hi = b + 1u < (unsigned int)NMS_BINS ? hb[b + 1u] : n_picks;
+            unsigned int c = lo;
+            for (unsigned int m = lo; m < hi; m++) c += prio_gt(tk[m], ti[m], k, i) ? 1u : 0u;
+            sk[c] = k; si[c] = i;
+        }
+        __syncthreads();
+    } else
     if (sort_all || n_picks <= (unsigned)K) {                 // every pick is kept: plain copy
         for (unsigned int j = tid; j < n_picks; j += N_THREADS) { sk[j] = qk[j]; si[j] = qi[j]; }
     } else {
@@ -1392,7 +1460,9 @@ harris_nms_bands(NmsArgs a) {
     // bitonic sort, highest priority first.  Element e = tid + 1024 u lives in registers; compare-exchanges with a
     // partner less than 32 elements away (45 of the 66 stages for 2048 elements) are warp shuffles, the others go
     // through shared memory.  P2 <= 4096 here: at most four elements per thread.
-    if (P2 <= 4u * N_THREADS) {
+    if (bin_sort) {
+        // already in order
+    } else if (P2 <= 4u * N_THREADS) {
         unsigned long long kr[4];
         unsigned int ir[4];
 #pragma unroll
