@@ -1206,13 +1206,17 @@ static int pipe_step(vo_pipeline* pl, const uint8_t* d_frames, size_t pitch, siz
     int rc;
     const bool fork = !ctx->env_frontend_serial;
     cudaStream_t sd = fork ? pl->side : s, sp = fork ? pl->pose_stream : s;
-    // the detector of the previous step has left its corners (what this step's append may take)
-    if (fork && p.detector != VO_DETECTOR_NONE) VO_CUDA(cudaStreamWaitEvent(s, pl->ev_det, 0));
     // new frame -> pyramid; the detector runs on it on the side stream (its corners are what the NEXT step appends
     // when a sequence runs low: klt.py:207-230 detects on the old frame, which is this step's new frame)
     if ((rc = vo_launch_klt_pyramid(ctx, d_frames, p.n_seq, p.H, p.W, pitch, frame_stride, p.klt_max_level, p.klt_win,
                                     pl->pyr[nx], s, pl->ev_level0))) return rc;
     if (staging_free) VO_CUDA(cudaEventRecord(staging_free, s));
+    // The detector of the previous step has left its corners (what this step's append may take).  Only the append and
+    // what follows it wait for that: the pyramid above writes the slot of the frame before last, which nothing reads
+    // any more (the previous tracker is ahead of it on this stream, the detector that read its level 0 finished before
+    // that tracker started), so the level-0 copy and the pyramid slip in while the last band CTAs are still running.
+    // (The wait has to be queued before this step's detector re-records ev_det.)
+    if (fork && p.detector != VO_DETECTOR_NONE) VO_CUDA(cudaStreamWaitEvent(s, pl->ev_det, 0));
     if (p.detector != VO_DETECTOR_NONE && fork) {
         VO_CUDA(cudaStreamWaitEvent(sd, pl->ev_level0, 0));
         if ((rc = pipe_run_detector(pl, pl->pyr[nx], nx, sd))) return rc;
