@@ -976,7 +976,7 @@ __device__ __forceinline__ unsigned int nms_find_blocker(const unsigned int* M, 
                                                          unsigned int p, unsigned long long k) {
     const int r = R > 0 ? R : r_rt;
     const int x0 = max(px - r, 0), len = min(px + r, W - 1) - x0 + 1;
-    if (R > 0) {
+    if constexpr (R > 0) {
         unsigned int fld[2 * R + 1], any = 0u;
 #pragma unroll
         for (int i = 0; i <= 2 * R; i++) {               // all window rows first: 2 loads each, independent
@@ -1000,22 +1000,23 @@ __device__ __forceinline__ unsigned int nms_find_blocker(const unsigned int* M, 
             }
         }
         return NMS_EMPTY;
-    }
-    for (int dy = -r; dy <= r; dy++) {
-        const int y = py + dy;
-        if (y < 0 || y >= H) continue;
-        const unsigned int q0 = (unsigned int)(y * W + x0);
-        unsigned int f = bm_get_range(M, q0, len);
-        if (dy == 0) f &= ~(1u << (px - x0));
-        while (f) {
-            const unsigned int q = q0 + (unsigned int)(__ffs(f) - 1);
-            f &= f - 1u;
-            const bool dead = bm_test(S, q);
-            const unsigned long long kq = nms_lookup(tab, q);
-            if (!dead && prio_gt(kq, q, k, p)) return q;
+    } else {
+        for (int dy = -r; dy <= r; dy++) {
+            const int y = py + dy;
+            if (y < 0 || y >= H) continue;
+            const unsigned int q0 = (unsigned int)(y * W + x0);
+            unsigned int f = bm_get_range(M, q0, len);
+            if (dy == 0) f &= ~(1u << (px - x0));
+            while (f) {
+                const unsigned int q = q0 + (unsigned int)(__ffs(f) - 1);
+                f &= f - 1u;
+                const bool dead = bm_test(S, q);
+                const unsigned long long kq = nms_lookup(tab, q);
+                if (!dead && prio_gt(kq, q, k, p)) return q;
+            }
         }
+        return NMS_EMPTY;
     }
-    return NMS_EMPTY;
 }
 
 // the new picks of a round suppress their boxes (one box row per thread) and are appended to the pick list
@@ -1062,7 +1063,6 @@ harris_nms_bands(NmsArgs a) {
     unsigned long long* pk = a.pick_key + (size_t)f * a.lm_cap;
     unsigned int* pi = a.pick_idx + (size_t)f * a.lm_cap;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int win = 2 * r + 1;
 
     unsigned int* endR = reinterpret_cast<unsigned int*>(smem_raw);   // [BINS] entries with rank <= R (rank 0 = top bin)
     unsigned int* cur = endR + NMS_BINS;                              // [BINS] scatter cursors

@@ -677,7 +677,6 @@ klt_track_packed(const uint8_t* __restrict__ pyr_prev, const uint8_t* __restrict
     // J taps costs two byte loads per slot instead of four; slot 9 holds column 16 of row `lane`.  With t a compile-time constant every address is a per-lane base plus an
     // immediate, so the unrolled loops carry no index arithmetic.  (The generic setup below keeps running counters.)
     static_assert(WIN == 17, "the slot mapping of klt_track_packed is laid out for a 17 x 17 window");
-    const int ly0 = lane / WIN, lx0 = lane - ly0 * WIN;      // generic setup: i = lane + 32 t walks the window row-major
     const int hi = lane >> 4, lx = lane & 15;
     auto slot_y = [&](int t) { return t < T - 1 ? t + 9 * hi : lane; };
     auto slot_x = [&](int t) { return t < T - 1 ? lx : 16; };

@@ -215,7 +215,6 @@ __global__ void __launch_bounds__(RG_THREADS)
 pipe_regroup_kernel(PipeTable A, PipeTable B, PipeSeq Q, PipeParams P, const float2* __restrict__ nxt,
                     const uint8_t* __restrict__ status, const float* __restrict__ err) {
     __shared__ int warp_tot[RG_THREADS / 32];
-    __shared__ int s_cnt[3];
     const int s = blockIdx.x;
     const int n = Q.n_rows[s];
     const size_t base = (size_t)s * P.C;
@@ -259,7 +258,6 @@ pipe_regroup_kernel(PipeTable A, PipeTable B, PipeSeq Q, PipeParams P, const flo
         o2 += t2; o1 += t1; o0 += t0;
     }
     if (threadIdx.x == 0) {
-        s_cnt[0] = c2; s_cnt[1] = c1; s_cnt[2] = c0;
         int* cnt = Q.counts + (size_t)s * VO_PIPE_NCOUNTS;
         cnt[1] = n;                         // rows tracked
         cnt[2] = c2 + c1 + c0;              // rows kept
